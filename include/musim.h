@@ -1,0 +1,127 @@
+/* musim.h -- C ABI of the B200-native muspinsim hot path (libmusim.so).
+ *
+ * The reference (muspinsim v2.3.1) has no FFI for this path: the hot loop is the Python
+ * `for cfg in self._config[rank::size]` of ExperimentRunner.run (muspinsim/experiment.py:358-382)
+ * calling run_single (experiment.py:434-498) once per configuration snapshot, which in turn
+ * calls Hermitian.diag (spinop.py:51-82), Operator.basis_change (spinop.py:330-355),
+ * Hamiltonian.evolve / fast_evolve / integrate_decaying (hamiltonian.py:40-217), the Cython
+ * kernel parallel_fast_time_evolve (cython/parallel.pyx:16-68) and Lindbladian.evolve /
+ * integrate_decaying (lindbladian.py:43-173).  The entry points below replace that whole loop
+ * with ONE batched call per group of configurations (a per-configuration FFI would only
+ * re-create the reference's overhead).
+ *
+ * Conventions
+ *   - plain C, no torch types; returns 0 on success or a negative MUSIM_E* code, never throws;
+ *   - complex matrices are row-major, interleaved (re, im) doubles;
+ *   - units as in the reference: H in MHz (frequency), B in T, gamma in MHz/T, times in us;
+ *   - `musim_run` takes DEVICE pointers owned by the caller (e.g. torch tensors) and is
+ *     asynchronous on `stream`; `musim_run_host` takes HOST pointers and includes the
+ *     host<->device copies and a final synchronisation;
+ *   - one handle per device; a handle is not thread-safe.
+ */
+#ifndef MUSIM_H
+#define MUSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct musim_handle musim_handle;
+
+/* error codes */
+#define MUSIM_OK 0
+#define MUSIM_EINVAL -1   /* bad argument (maps to ValueError on the Python side) */
+#define MUSIM_ECUDA -2    /* CUDA runtime error; see musim_last_error */
+#define MUSIM_ENOMEM -3
+#define MUSIM_ENOTCONV -4 /* eigensolver did not converge */
+#define MUSIM_EUNSUP -5   /* unsupported size / mode */
+
+/* evaluation modes (which reference function each configuration would have gone through) */
+#define MUSIM_MODE_EVOLVE 0       /* Hamiltonian.evolve, thermal rho0     hamiltonian.py:40-117 */
+#define MUSIM_MODE_FAST 1         /* Hamiltonian.fast_evolve (T=inf|B=0)  hamiltonian.py:166-217 */
+#define MUSIM_MODE_INTEGRAL 2     /* Hamiltonian.integrate_decaying / tau hamiltonian.py:119-164 */
+#define MUSIM_MODE_LINDBLAD 3     /* Lindbladian.evolve                   lindbladian.py:43-111 */
+#define MUSIM_MODE_LINDBLAD_INT 4 /* Lindbladian.integrate_decaying / tau lindbladian.py:113-173 */
+#define MUSIM_MODE_INTEGRAL_FAST 5 /* integrate_decaying when the other spins are maximally mixed
+                                      (T=inf|B=0): same value, weights |O'|^2/d_other */
+
+/* Create a handle for one spin system on CUDA device `device`.
+ *   d            Hilbert-space dimension (= prod dims)
+ *   dims[n]      2I+1 of each spin, in Kronecker order (last spin fastest, spinsys.py:581-592)
+ *   gammas[n]    gyromagnetic ratios, MHz/T (constants.py:12-53)
+ *   muon_index   index of the muon in the spin list (spinsys.py:651)
+ *   H0           d*d complex: field-independent Hamiltonian = MuonSpinSystem.hamiltonian
+ *                (spinsys.py:613-626)
+ *   Z            3*d*d complex: Z_a = sum_i gamma_i S_i^a so that Hz = sum_a B_a Z_a
+ *                (ExperimentRunner.Hz, experiment.py:238-250)
+ *   M            3*d*d complex: M_a = S_mu^a (x) 1 so that the observable is sum_a p_a M_a
+ *                (MuonSpinSystem.muon_operator, spinsys.py:707-732)
+ *   n_diss, diss_spin[], diss_rate[]   dissipation terms (simconfig.py:287-290;
+ *                ExperimentRunner.dissipation_operators, experiment.py:271-325); 0 if none.
+ * All pointers are HOST pointers and are copied. */
+int musim_create(musim_handle **h, int device, int d, int n_spins, const int *dims,
+                 const double *gammas, int muon_index, const double *H0, const double *Z,
+                 const double *M, int n_diss, const int *diss_spin, const double *diss_rate);
+
+/* Replace H0 / Z (resident-system fitting: FittingRunner re-creates the system per function
+ * evaluation, fitting.py:126-135; here only the coupling-dependent matrices are re-uploaded). */
+int musim_update_system(musim_handle *h, const double *H0, const double *Z);
+
+/* Use an explicit initial density matrix (d*d complex, HOST) for every configuration instead
+ * of the thermal product state of ExperimentRunner.rho0 (experiment.py:170-236).  This is the
+ * per-call boundary Hamiltonian.evolve(rho0, times, operators) (hamiltonian.py:40).  NULL
+ * restores the thermal construction. */
+int musim_set_rho0(musim_handle *h, const double *rho0);
+
+/* Tunables: "eigh" (0 auto, 1 Jacobi, 2 Householder+QL), "polar" (0 auto, 1 direct sincos,
+ * 2 time-factorised), "chunk" (configurations per launch group, 0 auto). */
+int musim_set_option(musim_handle *h, const char *key, long value);
+
+/* Evaluate n_cfg configurations and ACCUMULATE  w[c] * signal_c  into out[slot[c], :].
+ *   B[n,3], p[n,3], T[n]  field (T), muon polarisation and temperature (K, may be inf) of
+ *                 each configuration AFTER the crystallite rotation of
+ *                 ExperimentRunner.load_config (experiment.py:384-432)
+ *   w[n]          orientation weight / avg_N (experiment.py:498, simconfig.py:368)
+ *   slot[n]       row of `out` this configuration is accumulated into
+ *                 (MuSpinConfig.store_time_slice, simconfig.py:347-368)
+ *   times[nt]     HOST pointer; ignored (nt = 1) for the integral modes
+ *   tau           decay time for the integral modes (MU_TAU, constants.py:14)
+ *   out[n_slots, nt]   DEVICE, float64, += semantics
+ * B, p, T, w, slot, out are DEVICE pointers. */
+int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double *B, const double *p,
+              const double *T, const double *w, const int32_t *slot, int nt, const double *times,
+              double tau, int n_slots, double *out, void *cuda_stream);
+
+/* Same with HOST pointers for everything; `out` is read, accumulated into and written back. */
+int musim_run_host(musim_handle *h, int mode, int64_t n_cfg, const double *B, const double *p,
+                   const double *T, const double *w, const int32_t *slot, int nt,
+                   const double *times, double tau, int n_slots, double *out);
+
+/* Batched complex-Hermitian eigensolver on its own (replaces np.linalg.eigh in
+ * Hermitian.diag, spinop.py:69).  A[batch,d,d] complex row-major (only read), evals[batch,d]
+ * ascending, evecs[batch,d,d] complex row-major with eigenvectors in COLUMNS (numpy
+ * convention).  DEVICE pointers.  method: 0 auto, 1 Jacobi, 2 Householder+QL. */
+int musim_eigh(int device, int d, int64_t batch, const double *A, double *evals, double *evecs,
+               int method, void *cuda_stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t musim_launch_count(musim_handle *h);
+
+/* Milliseconds of device time spent in the named phase ("eigh", "rotate", "polar", ...)
+ * during the last musim_run_host / musim_run with profiling enabled (option "profile" = 1). */
+double musim_phase_ms(musim_handle *h, const char *phase);
+
+/* FP64 peak micro-benchmarks used as roofline denominators (MEASURED_PEAKS.json has no FP64
+ * entry).  kind 0: DFMA (vector pipe), 1: DMMA m8n8k4 (mma.sync f64).  Returns TFLOP/s. */
+int musim_fp64_peak(int device, int kind, double *tflops);
+
+const char *musim_last_error(musim_handle *h);
+int musim_destroy(musim_handle *h);
+int musim_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSIM_H */

@@ -1,0 +1,208 @@
+"""ctypes binding of libmusim.so (include/musim.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, an
+exception is raised.  PyTorch is used only by callers for device buffers / streams /
+torch.distributed; nothing here depends on it.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmusim.so")
+
+MODE_EVOLVE, MODE_FAST, MODE_INTEGRAL, MODE_LINDBLAD, MODE_LINDBLAD_INT, MODE_INTEGRAL_FAST = range(6)
+
+_ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ENOTCONV", -5: "EUNSUP"}
+
+# every symbol include/musim.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "musim_create",
+    "musim_update_system",
+    "musim_set_rho0",
+    "musim_set_option",
+    "musim_run",
+    "musim_run_host",
+    "musim_eigh",
+    "musim_launch_count",
+    "musim_phase_ms",
+    "musim_fp64_peak",
+    "musim_last_error",
+    "musim_destroy",
+    "musim_version",
+]
+
+
+class MusimError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libmusim.so; raise if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MusimError(
+            "CUDA library %s is missing: build it with `make -C muspinsim_b200/csrc` "
+            "(there is no CPU fallback)" % LIB_PATH
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    lib.musim_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, vp, vp]
+    lib.musim_create.restype = i32
+    lib.musim_update_system.argtypes = [vp, vp, vp]
+    lib.musim_update_system.restype = i32
+    lib.musim_set_rho0.argtypes = [vp, vp]
+    lib.musim_set_rho0.restype = i32
+    lib.musim_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_long]
+    lib.musim_set_option.restype = i32
+    lib.musim_run.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32, vp, dbl, i32, vp, vp]
+    lib.musim_run.restype = i32
+    lib.musim_run_host.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32, vp, dbl, i32, vp]
+    lib.musim_run_host.restype = i32
+    lib.musim_eigh.argtypes = [i32, i32, i64, vp, vp, vp, i32, vp]
+    lib.musim_eigh.restype = i32
+    lib.musim_launch_count.argtypes = [vp]
+    lib.musim_launch_count.restype = i64
+    lib.musim_phase_ms.argtypes = [vp, ctypes.c_char_p]
+    lib.musim_phase_ms.restype = dbl
+    lib.musim_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(dbl)]
+    lib.musim_fp64_peak.restype = i32
+    lib.musim_last_error.argtypes = [vp]
+    lib.musim_last_error.restype = ctypes.c_char_p
+    lib.musim_destroy.argtypes = [vp]
+    lib.musim_destroy.restype = i32
+    lib.musim_version.argtypes = []
+    lib.musim_version.restype = i32
+    _lib = lib
+    return lib
+
+
+def _c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Handle:
+    """RAII wrapper around musim_handle for one spin system on one device."""
+
+    def __init__(self, device, dims, gammas, muon_index, H0, Z, M, diss_spin=(), diss_rate=()):
+        self._lib = load()
+        self._h = ctypes.c_void_p()
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        gammas = _f64(gammas)
+        d = int(np.prod(dims))
+        H0, Z, M = _c128(H0), _c128(Z), _c128(M)
+        if H0.shape != (d, d) or Z.shape != (3, d, d) or M.shape != (3, d, d):
+            raise ValueError("H0 must be (d,d); Z and M must be (3,d,d)")
+        ds = np.ascontiguousarray(diss_spin, dtype=np.int32)
+        dr = _f64(diss_rate)
+        rc = self._lib.musim_create(
+            ctypes.byref(self._h), int(device), d, len(dims), _ptr(dims), _ptr(gammas), int(muon_index),
+            _ptr(H0), _ptr(Z), _ptr(M), len(ds), _ptr(ds) if len(ds) else None, _ptr(dr) if len(ds) else None,
+        )
+        self.d = d
+        self.device = int(device)
+        self._check(rc)
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = ""
+        if self._h:
+            msg = (self._lib.musim_last_error(self._h) or b"").decode()
+        text = "libmusim error %s (%d): %s" % (_ERRORS.get(rc, "?"), rc, msg)
+        if rc == -1:
+            raise ValueError(text)
+        raise MusimError(text)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.musim_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        self._check(self._lib.musim_set_option(self._h, key.encode(), int(value)))
+
+    def set_rho0(self, rho0):
+        if rho0 is None:
+            self._check(self._lib.musim_set_rho0(self._h, None))
+        else:
+            r = _c128(rho0)
+            if r.shape != (self.d, self.d):
+                raise ValueError("rho0 must be (d,d)")
+            self._check(self._lib.musim_set_rho0(self._h, _ptr(r)))
+
+    def update_system(self, H0=None, Z=None):
+        H0 = _c128(H0) if H0 is not None else None
+        Z = _c128(Z) if Z is not None else None
+        self._check(self._lib.musim_update_system(self._h, _ptr(H0), _ptr(Z)))
+
+    def run_host(self, mode, B, p, T, w, slot, times, tau, out):
+        """All numpy (host) arrays; `out` [n_slots, nt] float64 is accumulated into in place."""
+        B, p, w = _f64(B), _f64(p), _f64(w)
+        n = B.shape[0]
+        T = _f64(T) if T is not None else None
+        slot = np.ascontiguousarray(slot, dtype=np.int32)
+        times = _f64(times) if times is not None else None
+        if not (out.flags.c_contiguous and out.dtype == np.float64 and out.ndim == 2):
+            raise ValueError("out must be a C-contiguous float64 [n_slots, nt] array")
+        nt = len(times) if times is not None else 1
+        rc = self._lib.musim_run_host(
+            self._h, int(mode), n, _ptr(B), _ptr(p), _ptr(T), _ptr(w), _ptr(slot), nt, _ptr(times),
+            float(tau), out.shape[0], _ptr(out),
+        )
+        self._check(rc)
+        return out
+
+    def run_device(self, mode, n_cfg, B_ptr, p_ptr, T_ptr, w_ptr, slot_ptr, times, tau, n_slots, out_ptr, stream=0):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
+        times = _f64(times) if times is not None else None
+        nt = len(times) if times is not None else 1
+        rc = self._lib.musim_run(
+            self._h, int(mode), int(n_cfg), B_ptr, p_ptr, T_ptr, w_ptr, slot_ptr, nt, _ptr(times),
+            float(tau), int(n_slots), out_ptr, stream,
+        )
+        self._check(rc)
+
+    @property
+    def launches(self):
+        return int(self._lib.musim_launch_count(self._h))
+
+    def phase_ms(self, name):
+        return float(self._lib.musim_phase_ms(self._h, name.encode()))
+
+
+def fp64_peak(device=0, kind=0):
+    lib = load()
+    v = ctypes.c_double()
+    rc = lib.musim_fp64_peak(int(device), int(kind), ctypes.byref(v))
+    if rc:
+        raise MusimError("musim_fp64_peak failed (%d)" % rc)
+    return v.value
+
+
+def eigh_device(device, d, batch, A_ptr, evals_ptr, evecs_ptr, method=0, stream=0):
+    lib = load()
+    rc = lib.musim_eigh(int(device), int(d), int(batch), A_ptr, evals_ptr, evecs_ptr, int(method), stream)
+    if rc:
+        raise MusimError("musim_eigh failed: %s (%d)" % (_ERRORS.get(rc, "?"), rc))

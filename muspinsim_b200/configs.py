@@ -1,0 +1,262 @@
+"""Configuration table: array-based restatement of the reference's configuration expansion.
+
+The reference materialises one Python namedtuple per configuration
+(`MuSpinConfig.__getitem__`, /root/reference/muspinsim/simconfig.py:497-519) and rotates field
+and polarisation one at a time with an `ase` quaternion (`ExperimentRunner.load_config`,
+experiment.py:384-432).  Here the whole table is built as structure-of-arrays
+(B_rot[n,3], p_rot[n,3], T[n], w[n], slot[n]) with vectorised numpy, which is what the GPU
+consumes.  Range classification (x axis / averaged / file ranges), ordering and normalisation
+follow simconfig.py:134-171, 300-316 and `store_time_slice` (simconfig.py:347-368).
+"""
+
+from collections import OrderedDict
+
+import numpy as np
+import scipy.constants as cnst
+
+_KEYS = OrderedDict(
+    [
+        ("polarization", "mupol"),
+        ("field", "B"),
+        ("intrinsic_field", "intrinsic_B"),
+        ("time", "t"),
+        ("orientation", "orient"),
+        ("temperature", "T"),
+    ]
+)  # simconfig.py:23-30
+
+
+def default_spec():
+    """Keyword defaults of the .in format (input/keyword.py:357-484)."""
+    return {
+        "name": "muspinsim",
+        "spins": ["mu", "e"],
+        "couplings": [],
+        "polarization": [[1.0, 0.0, 0.0]],
+        "field": [[0.0, 0.0, 0.0]],
+        "intrinsic_field": [[0.0, 0.0, 0.0]],
+        "time": np.linspace(0.0, 10.0, 101),
+        "orientation": [[0.0, 0.0, 0.0]],
+        "orientation_mode": "zyz",
+        "temperature": [np.inf],
+        "x_axis": "time",
+        "y_axis": "asymmetry",
+        "average_axes": ["orientation"],
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# quaternions, vectorised (ase.quaternions semantics; simconfig.py:596-613, utils.py:53-68)
+# ------------------------------------------------------------------------------------------
+def quat_mul(a, b):
+    """Hamilton product of [...,4] arrays, q = (w, x, y, z)."""
+    aw, ax, ay, az = np.moveaxis(a, -1, 0)
+    bw, bx, by, bz = np.moveaxis(b, -1, 0)
+    return np.stack(
+        [
+            aw * bw - ax * bx - ay * by - az * bz,
+            aw * bx + ax * bw + ay * bz - az * by,
+            aw * by + ay * bw + az * bx - ax * bz,
+            aw * bz + az * bw + ax * by - ay * bx,
+        ],
+        axis=-1,
+    )
+
+
+def _axis_quat(axis, theta):
+    theta = np.asarray(theta, dtype=float)
+    q = np.zeros(theta.shape + (4,))
+    q[..., 0] = np.cos(theta / 2.0)
+    q[..., 1 + axis] = np.sin(theta / 2.0)
+    return q
+
+
+def quat_from_euler(a, b, c, mode="zyz"):
+    """q = q_z(c) * q_{y|x}(b) * q_z(a)."""
+    if mode not in ("zyz", "zxz"):
+        raise ValueError("Invalid Euler angles mode {0}".format(mode))
+    qb = _axis_quat(1 if mode == "zyz" else 0, b)
+    return quat_mul(quat_mul(_axis_quat(2, c), qb), _axis_quat(2, a))
+
+
+def quat_rotation_matrices(q):
+    """[...,4] -> [...,3,3] so that R @ v == Quaternion(q).rotate(v)."""
+    w, x, y, z = np.moveaxis(q, -1, 0)
+    R = np.empty(q.shape[:-1] + (3, 3))
+    R[..., 0, 0] = w * w + x * x - y * y - z * z
+    R[..., 0, 1] = 2 * (x * y - w * z)
+    R[..., 0, 2] = 2 * (x * z + w * y)
+    R[..., 1, 0] = 2 * (x * y + w * z)
+    R[..., 1, 1] = w * w - x * x + y * y - z * z
+    R[..., 1, 2] = 2 * (y * z - w * x)
+    R[..., 2, 0] = 2 * (x * z - w * y)
+    R[..., 2, 1] = 2 * (y * z + w * x)
+    R[..., 2, 2] = w * w - x * x - y * y + z * z
+    return R
+
+
+def orientation_table(rows, mode="zyz"):
+    """`orientation` rows (2: polar theta,phi; 3: Euler; 4: Euler + weight) ->
+    (conjugate quaternions [n,4], weights [n]).  simconfig.py:596-613."""
+    rows = np.atleast_2d(np.asarray(rows, dtype=float))
+    n, k = rows.shape
+    w = np.ones(n)
+    if k == 2:
+        q = quat_from_euler(rows[:, 1], rows[:, 0], rows[:, 1], "zyz")
+    elif k == 3:
+        q = quat_from_euler(rows[:, 0], rows[:, 1], rows[:, 2], mode)
+    elif k == 4:
+        q = quat_from_euler(rows[:, 0], rows[:, 1], rows[:, 2], mode)
+        w = rows[:, 3].copy()
+    else:
+        raise ValueError("Invalid orientation row")
+    return q * np.array([1.0, -1.0, -1.0, -1.0]), w
+
+
+def eulrange(N):
+    """N^3 Euler-angle rows with weights sin(b).  utils.py:40-50."""
+    N = int(N)
+    a = np.linspace(0, 2 * np.pi, N)
+    b = np.linspace(0, np.pi, N + 2)[1:-1]
+    c = np.linspace(0, 2 * np.pi, N)
+    a, b, c = np.array(np.meshgrid(a, b, c)).reshape((3, -1))
+    return np.array([a, b, c, np.sin(b)]).T
+
+
+def _vec3_rows(rows):
+    out = []
+    for r in rows:
+        r = np.atleast_1d(np.asarray(r, dtype=float))
+        if len(r) == 1:
+            r = np.array([0.0, 0.0, r[0]])  # scalar field is along z (simconfig.py:571-586)
+        elif len(r) != 3:
+            raise ValueError("Invalid magnetic field value")
+        out.append(r)
+    return np.array(out)
+
+
+class ConfigTable:
+    """All configurations of one simulation as arrays.
+
+    Attributes
+      B, p        [n,3] field / polarisation in the crystallite frame (rotated; intrinsic
+                  field added unrotated, experiment.py:404-411)
+      T, w        [n]   temperature, orientation weight / avg_N
+      slot        [n]   row of the [n_slots, nt] accumulation buffer
+      fast        [n]   bool: the reference's T=inf / B=0 predicate (experiment.py:413-418)
+      times       [nt]  time axis (length 1 and unused for y = integral)
+      results_shape     shape of the reference's results array (simconfig.py:293-297)
+    """
+
+    def __init__(self, spec):
+        s = default_spec()
+        s.update(spec)
+        self.spec = s
+        self.y = s["y_axis"]
+        if self.y not in ("asymmetry", "integral"):
+            raise ValueError("Invalid value '%s', accepts ['asymmetry', 'integral']" % self.y)
+        try:
+            xname = _KEYS[s["x_axis"]]
+            avg = [_KEYS[a] for a in s["average_axes"] if a.lower() != "none"]
+        except KeyError as exc:
+            raise ValueError("Invalid axis name") from exc
+
+        vals = {}
+        pol = np.atleast_2d(np.asarray(s["polarization"], dtype=float))
+        if pol.shape[1] != 3:
+            raise ValueError("Invalid muon polarization direction")
+        vals["mupol"] = pol / np.linalg.norm(pol, axis=1)[:, None]  # simconfig.py:588-594
+        vals["B"] = _vec3_rows(s["field"])
+        vals["intrinsic_B"] = _vec3_rows(s["intrinsic_field"])
+        t = np.asarray(s["time"], dtype=float).reshape(-1)
+        if self.y == "integral":
+            t = np.array([np.inf])  # simconfig.py:145-149
+        vals["t"] = t
+        q, ow = orientation_table(s["orientation"], s["orientation_mode"])
+        if "orient" in avg:
+            ow = ow * (len(ow) / np.sum(ow))  # weights normalised to sum to N (simconfig.py:152-156)
+        else:
+            ow = np.ones(len(ow))
+        vals["orient"] = q
+        vals["T"] = np.asarray(s["temperature"], dtype=float).reshape(-1)
+
+        # classify ranges in the reference's keyword order
+        self.x_name = xname
+        self.file_ranges, self.avg_ranges = OrderedDict(), OrderedDict()
+        x_len = None
+        for cname in _KEYS.values():
+            n = len(vals[cname])
+            if n > 1:
+                if cname == xname:
+                    x_len = n
+                elif cname in avg:
+                    self.avg_ranges[cname] = n
+                else:
+                    self.file_ranges[cname] = n
+        if self.y == "integral" and xname == "t":
+            raise ValueError("Can not use time as X axis when evaluating integral of signal")
+        if x_len is None:
+            raise ValueError("Specified x axis is not a range")
+        self.x_len = x_len
+        self.time_isavg = "t" in avg
+        self.times = t
+        self.x_axis_values = vals[xname]
+        self.results_shape = tuple(self.file_ranges.values()) + (x_len,)
+
+        # enumerate product(file, avg, x) without the time axis (time is the inner dimension
+        # of every evaluation: make_configs uses slice(None) for it, simconfig.py:300-309)
+        axes = []  # (name, length, kind)
+        for k, n in self.file_ranges.items():
+            axes.append((k, n, "f"))
+        for k, n in self.avg_ranges.items():
+            axes.append((k, n, "a"))
+        axes.append((xname, x_len, "x"))
+        loop_axes = [(k, n, kind) for (k, n, kind) in axes if k != "t"]
+        shape = [n for (_, n, _) in loop_axes]
+        n_cfg = int(np.prod(shape)) if shape else 1
+        grids = np.unravel_index(np.arange(n_cfg), shape) if shape else ()
+        idx = {k: np.zeros(n_cfg, dtype=np.int64) for k in _KEYS.values()}
+        for (k, _, _), g in zip(loop_axes, grids):
+            idx[k] = g
+        self.n_cfg = n_cfg
+        self.avg_N = int(np.prod([n for (k, n, kind) in axes if kind == "a" and k != "t"])) if axes else 1
+        # (if time is an averaged axis the reference counts it as ONE average configuration,
+        #  because make_configs gives [slice(None)] for it, and averages the slice instead)
+
+        # slot: index into the non-time dimensions of `results`, in results order
+        slot_dims = [(k, n) for (k, n, kind) in axes if kind in "fx" and k != "t"]
+        self._slot_shape = tuple(n for (_, n) in slot_dims) or (1,)
+        slot = np.zeros(n_cfg, dtype=np.int64)
+        for k, n in slot_dims:
+            slot = slot * n + idx[k]
+        self.slot = slot.astype(np.int32)
+        self.n_slots = int(np.prod(self._slot_shape))
+        # where the time axis sits in `results`
+        names_f = list(self.file_ranges.keys())
+        self._t_pos = names_f.index("t") if "t" in names_f else None
+
+        # rotate lab-frame field and polarisation by the stored (conjugate) quaternion
+        R = quat_rotation_matrices(q)[idx["orient"]]
+        self.B = np.einsum("nij,nj->ni", R, vals["B"][idx["B"]]) + vals["intrinsic_B"][idx["intrinsic_B"]]
+        self.p = np.einsum("nij,nj->ni", R, vals["mupol"][idx["mupol"]])
+        self.T = vals["T"][idx["T"]].astype(float)
+        self.w = ow[idx["orient"]] / self.avg_N
+        Bn = np.linalg.norm(self.B, axis=1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            check = (cnst.e * (cnst.hbar**2) * Bn) / (2 * cnst.m_p * cnst.k * self.T)
+        self.fast = check == 0  # experiment.py:413-418
+
+    def finish(self, out):
+        """[n_slots, nt] accumulation buffer -> the reference's results array layout."""
+        out = np.asarray(out)
+        if self.y == "integral":
+            return out.reshape(self.results_shape)
+        if self.time_isavg:
+            return out.mean(axis=1).reshape(self.results_shape)  # simconfig.py:364-365
+        if self.x_name == "t":
+            return out.reshape(self.results_shape)
+        if self._t_pos is None:
+            # a single time value reaches the solver as a 0-d array (validation.py:19-20)
+            raise ValueError("times must be an array of values in microseconds")
+        full = out.reshape(self._slot_shape + (out.shape[1],))
+        return np.moveaxis(full, -1, self._t_pos).reshape(self.results_shape)

@@ -1,0 +1,590 @@
+// musim.cu -- C ABI (include/musim.h) and host-side orchestration of the sm_100a kernels.
+//
+// The reference evaluates one configuration at a time in Python
+// (/root/reference/muspinsim/experiment.py:358-382, 434-498).  Here a whole table of
+// configurations is processed in launch groups ("chunks") through a short pipeline of batched
+// kernels whose intermediates (eigenvalues, eigenvectors, weights) live in HBM/L2:
+//
+//   eigh (H0 + B.Z built on chip)  ->  O_c = p.M  ->  T = O U  ->  Y = U^H T  [-> rho0, X]  ->
+//   W = rho' .* conj(O')           ->  polarisation / integral accumulation into out[slot, :]
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/musim.h"
+#include "common.cuh"
+#include "eigh_jacobi.cuh"
+#include "eigh_hql.cuh"
+#include "lindblad.cuh"
+#include "peak.cuh"
+#include "polar.cuh"
+#include "rotate.cuh"
+
+using namespace musim;
+
+#define MUSIM_VERSION 1
+#define MAX_SMEM_OPTIN (227 * 1024)
+
+enum Phase { PH_EIGH = 0, PH_ROTATE, PH_RHO0, PH_POLAR, PH_INTEGRAL, PH_LINDBLAD, PH_COUNT };
+static const char *kPhaseNames[PH_COUNT] = {"eigh", "rotate", "rho0", "polar", "integral", "lindblad"};
+
+struct musim_handle {
+  int device = 0;
+  int d = 0;
+  SpinTable tab;
+  int n_diss = 0;
+  std::vector<int> diss_spin;
+  std::vector<double> diss_rate;
+  // device constants
+  cplx *H0 = nullptr, *Z = nullptr, *M = nullptr, *rho0_explicit = nullptr, *Sops = nullptr;
+  PairIdx *pairs = nullptr;
+  int npairs = 0;
+  double *times_dev = nullptr;
+  int times_cap = 0;
+  // workspaces (sized for `ws_cfg` configurations)
+  int64_t ws_cfg = 0;
+  double *lam = nullptr;
+  cplx *U = nullptr, *T1 = nullptr, *Y = nullptr, *X = nullptr, *W = nullptr, *Oc = nullptr, *Vg = nullptr;
+  void *lws = nullptr;  // Lindblad workspace
+  size_t lws_bytes = 0;
+  int *status = nullptr;
+  // host-run staging
+  void *stage = nullptr;
+  size_t stage_bytes = 0;
+  // options
+  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0;
+  // bookkeeping
+  int64_t launches = 0;
+  double phase_ms[PH_COUNT] = {0};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::string err;
+};
+
+static int set_err(musim_handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call,            \
+               cudaGetErrorString(e_));                                                  \
+      return set_err(h, MUSIM_ECUDA, buf_);                                              \
+    }                                                                                    \
+  } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(T **p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
+}
+
+static void free_ws(musim_handle *h) {
+  cudaFree(h->lam);
+  cudaFree(h->U);
+  cudaFree(h->T1);
+  cudaFree(h->Y);
+  cudaFree(h->X);
+  cudaFree(h->W);
+  cudaFree(h->Oc);
+  cudaFree(h->Vg);
+  h->lam = nullptr;
+  h->U = h->T1 = h->Y = h->X = h->W = h->Oc = h->Vg = nullptr;
+  h->ws_cfg = 0;
+}
+
+extern "C" int musim_version(void) { return MUSIM_VERSION; }
+
+extern "C" const char *musim_last_error(musim_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int64_t musim_launch_count(musim_handle *h) { return h ? h->launches : 0; }
+
+extern "C" double musim_phase_ms(musim_handle *h, const char *phase) {
+  if (!h || !phase) return -1.0;
+  for (int i = 0; i < PH_COUNT; ++i)
+    if (!strcmp(phase, kPhaseNames[i])) return h->phase_ms[i];
+  return -1.0;
+}
+
+extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
+  if (!h || !key) return MUSIM_EINVAL;
+  if (!strcmp(key, "eigh"))
+    h->opt_eigh = value;
+  else if (!strcmp(key, "polar"))
+    h->opt_polar = value;
+  else if (!strcmp(key, "chunk"))
+    h->opt_chunk = value;
+  else if (!strcmp(key, "profile"))
+    h->opt_profile = value;
+  else if (!strcmp(key, "gemm"))
+    h->opt_gemm = value;
+  else
+    return set_err(h, MUSIM_EINVAL, std::string("unknown option ") + key);
+  return MUSIM_OK;
+}
+
+extern "C" int musim_create(musim_handle **out, int device, int d, int n_spins, const int *dims,
+                            const double *gammas, int muon_index, const double *H0, const double *Z,
+                            const double *M, int n_diss, const int *diss_spin,
+                            const double *diss_rate) {
+  if (!out) return MUSIM_EINVAL;
+  *out = nullptr;
+  if (d < 1 || d > 4096 || n_spins < 1 || n_spins > MUSIM_MAX_SPINS || !dims || !gammas || !H0 ||
+      !Z || !M || muon_index < 0 || muon_index >= n_spins)
+    return MUSIM_EINVAL;
+  long prod = 1;
+  for (int i = 0; i < n_spins; ++i) {
+    if (dims[i] < 1 || dims[i] > MUSIM_MAX_SDIM) return MUSIM_EINVAL;
+    prod *= dims[i];
+  }
+  if (prod != d) return MUSIM_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MUSIM_ECUDA;
+  musim_handle *h = new musim_handle();
+  *out = h;  // returned even on failure so that musim_last_error works; caller destroys it
+  h->device = device;
+  h->d = d;
+  h->tab.n_spins = n_spins;
+  h->tab.muon_index = muon_index;
+  for (int i = 0; i < n_spins; ++i) {
+    h->tab.dims[i] = dims[i];
+    h->tab.gammas[i] = gammas[i];
+  }
+  h->n_diss = n_diss;
+  for (int i = 0; i < n_diss; ++i) {
+    if (diss_spin[i] < 0 || diss_spin[i] >= n_spins) return set_err(h, MUSIM_EINVAL, "bad dissipation index");
+    h->diss_spin.push_back(diss_spin[i]);
+    h->diss_rate.push_back(diss_rate[i]);
+  }
+  CK(cudaSetDevice(device));
+  const size_t dd = (size_t)d * d;
+  CK(dev_alloc(&h->H0, dd));
+  CK(dev_alloc(&h->Z, 3 * dd));
+  CK(dev_alloc(&h->M, 3 * dd));
+  CK(cudaMemcpy(h->H0, H0, dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->Z, Z, 3 * dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->M, M, 3 * dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  // pair table (i <= j)
+  if (d <= 65535) {
+    std::vector<PairIdx> pt;
+    pt.reserve(dd / 2 + d);
+    for (int i = 0; i < d; ++i)
+      for (int j = i; j < d; ++j) pt.push_back(PairIdx{(unsigned short)i, (unsigned short)j});
+    h->npairs = (int)pt.size();
+    CK(dev_alloc(&h->pairs, pt.size()));
+    CK(cudaMemcpy(h->pairs, pt.data(), pt.size() * sizeof(PairIdx), cudaMemcpyHostToDevice));
+  }
+  CK(dev_alloc(&h->status, 4));
+  CK(cudaMemset(h->status, 0, 4 * sizeof(int)));
+  CK(cudaEventCreate(&h->ev[0]));
+  CK(cudaEventCreate(&h->ev[1]));
+  return MUSIM_OK;
+}
+
+extern "C" int musim_update_system(musim_handle *h, const double *H0, const double *Z) {
+  if (!h) return MUSIM_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const size_t dd = (size_t)h->d * h->d;
+  if (H0) CK(cudaMemcpy(h->H0, H0, dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  if (Z) CK(cudaMemcpy(h->Z, Z, 3 * dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  return MUSIM_OK;
+}
+
+extern "C" int musim_set_rho0(musim_handle *h, const double *rho0) {
+  if (!h) return MUSIM_EINVAL;
+  CK(cudaSetDevice(h->device));
+  const size_t dd = (size_t)h->d * h->d;
+  if (!rho0) {
+    cudaFree(h->rho0_explicit);
+    h->rho0_explicit = nullptr;
+    return MUSIM_OK;
+  }
+  if (!h->rho0_explicit) CK(dev_alloc(&h->rho0_explicit, dd));
+  CK(cudaMemcpy(h->rho0_explicit, rho0, dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  return MUSIM_OK;
+}
+
+extern "C" int musim_destroy(musim_handle *h) {
+  if (!h) return MUSIM_OK;
+  cudaSetDevice(h->device);
+  free_ws(h);
+  cudaFree(h->H0);
+  cudaFree(h->Z);
+  cudaFree(h->M);
+  cudaFree(h->rho0_explicit);
+  cudaFree(h->Sops);
+  cudaFree(h->pairs);
+  cudaFree(h->times_dev);
+  cudaFree(h->status);
+  cudaFree(h->stage);
+  cudaFree(h->lws);
+  if (h->ev[0]) cudaEventDestroy(h->ev[0]);
+  if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+  delete h;
+  return MUSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// eigensolver dispatch
+// ---------------------------------------------------------------------------------------
+static int pick_eigh(long opt, int d) {
+  if (opt == 1 || opt == 2) return (int)opt;
+  return hql_supported(d) ? 2 : 1;
+}
+
+// Ain == nullptr: build H from H0/Z/B.  Returns cudaError_t as int (0 ok) or MUSIM_EUNSUP.
+static int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
+                       const cplx *Ain, double *lam, cplx *U, cplx *Vg, int *status,
+                       cudaStream_t st, int64_t *launches) {
+  if (method == 2 && hql_supported(d)) {
+    int rc = launch_eigh_hql(d, n, H0, Z, B, Ain, lam, U, status, st, launches);
+    return rc;
+  }
+  const bool vglob = eigh_jacobi_smem(d, false) > MAX_SMEM_OPTIN;
+  const size_t smem = eigh_jacobi_smem(d, vglob);
+  if (smem > MAX_SMEM_OPTIN) return MUSIM_EUNSUP;
+  if (vglob && !Vg) return MUSIM_EUNSUP;
+  int nth = 256;
+  if (d * d <= 64) nth = 32;
+  else if (d * d <= 256) nth = 64;
+  else if (d * d <= 1024) nth = 128;
+  cudaError_t e;
+  if (Ain) {
+    e = cudaFuncSetAttribute(eigh_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    eigh_jacobi_kernel<false><<<(unsigned)n, nth, smem, st>>>(d, H0, Z, B, Ain, lam, U, status, 40, vglob ? Vg : nullptr);
+  } else {
+    e = cudaFuncSetAttribute(eigh_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    eigh_jacobi_kernel<true><<<(unsigned)n, nth, smem, st>>>(d, H0, Z, B, Ain, lam, U, status, 40, vglob ? Vg : nullptr);
+  }
+  if (launches) ++*launches;
+  return (int)cudaGetLastError();
+}
+
+extern "C" int musim_eigh(int device, int d, int64_t batch, const double *A, double *evals,
+                          double *evecs, int method, void *cuda_stream) {
+  musim_handle *h = nullptr;
+  if (d < 1 || batch < 0 || !A || !evals || !evecs) return MUSIM_EINVAL;
+  if (batch == 0) return MUSIM_OK;
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int m = pick_eigh(method, d);
+  cplx *Vg = nullptr;
+  int *status = nullptr;
+  CK(dev_alloc(&status, 4));
+  CK(cudaMemsetAsync(status, 0, 4 * sizeof(int), st));
+  const bool vglob = (m == 1) && eigh_jacobi_smem(d, false) > MAX_SMEM_OPTIN;
+  if (vglob) CK(dev_alloc(&Vg, (size_t)batch * d * (d | 1)));
+  int rc = launch_eigh(m, d, batch, nullptr, nullptr, nullptr, reinterpret_cast<const cplx *>(A),
+                       evals, reinterpret_cast<cplx *>(evecs), Vg, status, st, nullptr);
+  int hstat[4] = {0, 0, 0, 0};
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaMemcpy(hstat, status, sizeof hstat, cudaMemcpyDeviceToHost);
+  cudaFree(Vg);
+  cudaFree(status);
+  if (rc == MUSIM_EUNSUP) return MUSIM_EUNSUP;
+  if (rc != 0 || e != cudaSuccess) return MUSIM_ECUDA;
+  if (hstat[0] != 0) return MUSIM_ENOTCONV;
+  return MUSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// the batched run
+// ---------------------------------------------------------------------------------------
+static int ensure_ws(musim_handle *h, int64_t n, bool general, bool vglob) {
+  const size_t dd = (size_t)h->d * h->d;
+  if (h->ws_cfg >= n && (!general || h->X) && (!vglob || h->Vg)) return MUSIM_OK;
+  free_ws(h);
+  CK(dev_alloc(&h->lam, (size_t)n * h->d));
+  CK(dev_alloc(&h->U, n * dd));
+  CK(dev_alloc(&h->T1, n * dd));
+  CK(dev_alloc(&h->W, n * dd));
+  CK(dev_alloc(&h->Oc, n * dd));
+  if (general) {
+    CK(dev_alloc(&h->Y, n * dd));
+    CK(dev_alloc(&h->X, n * dd));
+  }
+  if (vglob) CK(dev_alloc(&h->Vg, (size_t)n * h->d * (h->d | 1)));
+  h->ws_cfg = n;
+  return MUSIM_OK;
+}
+
+struct TimeGrid {
+  bool uniform = false;
+  double t0 = 0, dt = 0;
+};
+
+static TimeGrid analyse_times(int nt, const double *t) {
+  TimeGrid g;
+  if (nt < 2) {
+    g.uniform = true;
+    g.t0 = nt ? t[0] : 0.0;
+    g.dt = 0.0;
+    return g;
+  }
+  g.t0 = t[0];
+  g.dt = (t[nt - 1] - t[0]) / (double)(nt - 1);
+  double tmax = 0, dev = 0;
+  for (int k = 0; k < nt; ++k) {
+    tmax = std::max(tmax, fabs(t[k]));
+    dev = std::max(dev, fabs(t[k] - (g.t0 + k * g.dt)));
+  }
+  g.uniform = dev <= 8.0 * 2.220446049250313e-16 * tmax;
+  return g;
+}
+
+template <bool CONJ_A, int EPI>
+static void launch_gemm(int d, int64_t n, const cplx *A, size_t as, const cplx *B, size_t bs, cplx *C,
+                        double scale, cudaStream_t st, int64_t *launches) {
+  dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);
+  cgemm_batched_kernel<CONJ_A, EPI><<<grid, 256, 0, st>>>(d, A, as, B, bs, C, scale);
+  ++*launches;
+}
+
+struct PhaseTimer {
+  musim_handle *h;
+  cudaStream_t st;
+  int ph;
+  bool on;
+  PhaseTimer(musim_handle *h_, cudaStream_t st_, int ph_) : h(h_), st(st_), ph(ph_), on(h_->opt_profile != 0) {
+    if (on) cudaEventRecord(h->ev[0], st);
+  }
+  ~PhaseTimer() {
+    if (on) {
+      cudaEventRecord(h->ev[1], st);
+      cudaEventSynchronize(h->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+      h->phase_ms[ph] += ms;
+    }
+  }
+};
+
+extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double *B, const double *p,
+                         const double *T, const double *w, const int32_t *slot, int nt,
+                         const double *times, double tau, int n_slots, double *out,
+                         void *cuda_stream) {
+  if (!h) return MUSIM_EINVAL;
+  if (mode < 0 || mode > 5) return set_err(h, MUSIM_EINVAL, "invalid mode");
+  if (n_cfg < 0 || n_slots < 1 || !out) return set_err(h, MUSIM_EINVAL, "invalid sizes");
+  if (n_cfg == 0) return MUSIM_OK;
+  if (!B || !p || !w || !slot) return set_err(h, MUSIM_EINVAL, "null configuration arrays");
+  const bool integral = (mode == MUSIM_MODE_INTEGRAL || mode == MUSIM_MODE_LINDBLAD_INT ||
+                         mode == MUSIM_MODE_INTEGRAL_FAST);
+  const bool lind = (mode == MUSIM_MODE_LINDBLAD || mode == MUSIM_MODE_LINDBLAD_INT);
+  const bool general = (mode != MUSIM_MODE_FAST && mode != MUSIM_MODE_INTEGRAL_FAST);
+  if (general && !T && !h->rho0_explicit) return set_err(h, MUSIM_EINVAL, "temperature array required");
+  if (integral) {
+    if (!(tau > 0.0)) return set_err(h, MUSIM_EINVAL, "'tau' must be a real number > 0");
+    nt = 1;
+  } else {
+    if (nt < 1 || !times) return set_err(h, MUSIM_EINVAL, "times must be an array of values in microseconds");
+  }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int d = h->d;
+  const size_t dd = (size_t)d * d;
+  for (int i = 0; i < PH_COUNT; ++i) h->phase_ms[i] = 0.0;
+
+  TimeGrid tg;
+  if (!integral) {
+    tg = analyse_times(nt, times);
+    if (nt > h->times_cap) {
+      cudaFree(h->times_dev);
+      h->times_dev = nullptr;
+      CK(dev_alloc(&h->times_dev, (size_t)nt));
+      h->times_cap = nt;
+    }
+    CK(cudaMemcpyAsync(h->times_dev, times, nt * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+
+  if (lind) {
+    int rc = lindblad_run(h->d, h->tab, h->n_diss, h->diss_spin.data(), h->diss_rate.data(), h->H0,
+                          h->Z, h->M, h->rho0_explicit, integral, n_cfg, B, p, T, w, slot, nt,
+                          h->times_dev, tg.uniform, tg.t0, tg.dt, tau, out, &h->lws, &h->lws_bytes,
+                          h->opt_chunk, st, &h->launches, h->err);
+    return rc;
+  }
+
+  const int method = pick_eigh(h->opt_eigh, d);
+  const bool vglob = (method == 1) && eigh_jacobi_smem(d, false) > MAX_SMEM_OPTIN;
+  // chunk: bound the workspace to ~1.5 GB
+  const int nbuf = general ? 7 : 5;
+  int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk
+                                   : std::max<int64_t>(148, (int64_t)(1.5e9 / (nbuf * dd * sizeof(cplx))));
+  chunk = std::min<int64_t>(chunk, n_cfg);
+  chunk = std::min<int64_t>(chunk, 65535LL * 8);
+  int rc = ensure_ws(h, chunk, general, vglob);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
+
+  const double d_other = (double)d / h->tab.dims[h->tab.muon_index];
+
+  for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
+    const int64_t n = std::min(chunk, n_cfg - c0);
+    {
+      PhaseTimer pt(h, st, PH_EIGH);
+      rc = launch_eigh(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->Vg, h->status, st,
+                       &h->launches);
+      if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
+      if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
+    }
+    {
+      PhaseTimer pt(h, st, PH_ROTATE);
+      dim3 g1((unsigned)((dd + 255) / 256), (unsigned)n);
+      form_obs_kernel<<<g1, 256, 0, st>>>(d, h->M, p + 3 * c0, h->Oc);
+      ++h->launches;
+      launch_gemm<false, 0>(d, n, h->Oc, dd, h->U, dd, h->T1, 1.0, st, &h->launches);
+      if (!general) {
+        // fast path: W = |U^H O U|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
+        launch_gemm<true, 1>(d, n, h->U, dd, h->T1, dd, h->W, 1.0 / d_other, st, &h->launches);
+      } else {
+        launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->Y, 1.0, st, &h->launches);
+      }
+    }
+    if (general) {
+      const cplx *R = h->rho0_explicit;
+      size_t rs = 0;
+      if (!R) {
+        PhaseTimer pt(h, st, PH_RHO0);
+        rho0_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->tab, B + 3 * c0, p + 3 * c0, T + c0, h->Oc);
+        ++h->launches;
+        R = h->Oc;
+        rs = dd;
+      }
+      PhaseTimer pt(h, st, PH_ROTATE);
+      launch_gemm<false, 0>(d, n, R, rs, h->U, dd, h->T1, 1.0, st, &h->launches);
+      launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->X, 1.0, st, &h->launches);
+      const size_t tot = (size_t)n * dd;
+      weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, h->X, h->Y, h->W);
+      ++h->launches;
+    }
+    if (integral) {
+      PhaseTimer pt(h, st, PH_INTEGRAL);
+      integral_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->W, h->lam, w + c0, slot + c0, tau, out);
+      ++h->launches;
+    } else {
+      PhaseTimer pt(h, st, PH_POLAR);
+      const bool fact = (h->opt_polar == 2) || (h->opt_polar == 0 && tg.uniform);
+      if (h->opt_polar == 2 && !tg.uniform)
+        return set_err(h, MUSIM_EINVAL, "time-factorised polarisation needs a uniform time grid");
+      int groups = (int)std::min<int64_t>(n, 148);
+      int per = (int)((n + groups - 1) / groups);
+      groups = (int)((n + per - 1) / per);
+      if (fact) {
+        int NB = 1;
+        while (NB * NB < nt && NB < 32) ++NB;
+        const int NA_total = (nt + NB - 1) / NB;
+        const size_t smem = polar_fact_smem(d);
+        CK(cudaFuncSetAttribute(polar_fact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(groups, (NA_total + 31) / 32);
+        polar_fact_kernel<<<grid, 256, smem, st>>>(d, h->npairs, h->pairs, (int)n, per, h->W, h->lam, w + c0,
+                                                   slot + c0, nt, tg.t0, tg.dt, NA_total, NB, out);
+      } else {
+        dim3 grid(groups, (nt + 255) / 256);
+        polar_direct_kernel<<<grid, 256, d * sizeof(double), st>>>(d, h->npairs, h->pairs, (int)n, per, h->W,
+                                                                  h->lam, w + c0, slot + c0, nt, h->times_dev, out);
+      }
+      ++h->launches;
+    }
+    CK(cudaGetLastError());
+  }
+  return MUSIM_OK;
+}
+
+extern "C" int musim_run_host(musim_handle *h, int mode, int64_t n_cfg, const double *B, const double *p,
+                              const double *T, const double *w, const int32_t *slot, int nt,
+                              const double *times, double tau, int n_slots, double *out) {
+  if (!h) return MUSIM_EINVAL;
+  if (n_cfg < 0 || n_slots < 1 || !out) return set_err(h, MUSIM_EINVAL, "invalid sizes");
+  if (n_cfg == 0) return MUSIM_OK;
+  if (!B || !p || !w || !slot) return set_err(h, MUSIM_EINVAL, "null configuration arrays");
+  CK(cudaSetDevice(h->device));
+  const bool integral = (mode == MUSIM_MODE_INTEGRAL || mode == MUSIM_MODE_LINDBLAD_INT ||
+                         mode == MUSIM_MODE_INTEGRAL_FAST);
+  const int ntx = integral ? 1 : nt;
+  if (ntx < 1) return set_err(h, MUSIM_EINVAL, "times must be an array of values in microseconds");
+  const size_t n = (size_t)n_cfg;
+  const size_t bB = n * 3 * sizeof(double), bT = n * sizeof(double), bS = n * sizeof(int32_t);
+  const size_t bO = (size_t)n_slots * ntx * sizeof(double);
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t total = 2 * al(bB) + 2 * al(bT) + al(bS) + al(bO);
+  if (total > h->stage_bytes) {
+    cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    CK(cudaMalloc(&h->stage, total));
+    h->stage_bytes = total;
+  }
+  char *base = (char *)h->stage;
+  double *dB = (double *)base;
+  double *dp = (double *)(base + al(bB));
+  double *dT = (double *)(base + 2 * al(bB));
+  double *dw = (double *)(base + 2 * al(bB) + al(bT));
+  int32_t *ds = (int32_t *)(base + 2 * al(bB) + 2 * al(bT));
+  double *dout = (double *)(base + 2 * al(bB) + 2 * al(bT) + al(bS));
+  cudaStream_t st = 0;
+  CK(cudaMemcpyAsync(dB, B, bB, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dp, p, bB, cudaMemcpyHostToDevice, st));
+  if (T) CK(cudaMemcpyAsync(dT, T, bT, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dw, w, bT, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ds, slot, bS, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dout, out, bO, cudaMemcpyHostToDevice, st));
+  int rc = musim_run(h, mode, n_cfg, dB, dp, T ? dT : nullptr, dw, ds, nt, times, tau, n_slots, dout, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, dout, bO, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int hstat[4];
+  CK(cudaMemcpy(hstat, h->status, sizeof hstat, cudaMemcpyDeviceToHost));
+  if (hstat[0] != 0) return set_err(h, MUSIM_ENOTCONV, "eigensolver did not converge");
+  return MUSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 peak micro-benchmarks
+// ---------------------------------------------------------------------------------------
+extern "C" int musim_fp64_peak(int device, int kind, double *tflops) {
+  musim_handle *h = nullptr;
+  if (!tflops || kind < 0 || kind > 1) return MUSIM_EINVAL;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8;
+  const int iters = 4096;
+  double *buf = nullptr;
+  CK(dev_alloc(&buf, (size_t)blocks * 256));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0));
+    if (kind == 0)
+      peak_dfma_kernel<<<blocks, 256>>>(iters, buf);
+    else
+      peak_dmma_kernel<<<blocks, 256>>>(iters, buf);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double flops;
+    if (kind == 0)
+      flops = (double)blocks * 256 * iters * 8.0 * 8.0 * 2.0;
+    else
+      flops = (double)blocks * 8 * iters * 8.0 * (8 * 8 * 4 * 2.0);
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return MUSIM_OK;
+}

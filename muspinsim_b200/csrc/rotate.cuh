@@ -1,0 +1,279 @@
+// rotate.cuh -- per-configuration operators and basis rotations.
+//
+//  * form_obs_kernel      O_c = sum_a p_a M_a            (MuonSpinSystem.muon_operator,
+//                                                        /root/reference/muspinsim/spinsys.py:707-732)
+//  * rho0_kernel          thermal product state          (ExperimentRunner.rho0, experiment.py:170-236)
+//  * cgemm_batched_kernel C = op(A) B, complex FP64      (Operator.basis_change, spinop.py:330-355)
+//  * weights_kernel       w_ij = rho'_ij O'_ji           (hamiltonian.py:77-103; fast path :204-217)
+//  * integral_kernel      sum_ab w_ab/(1/tau+2 pi i(l_a-l_b))/tau   (hamiltonian.py:150-162,
+//                                                        experiment.py:492-496)
+#pragma once
+#include "common.cuh"
+
+namespace musim {
+
+#define MUSIM_MAX_SPINS 16
+#define MUSIM_MAX_SDIM 10  // largest single-spin dimension 2I+1 (I <= 9/2)
+
+struct SpinTable {
+  int n_spins;
+  int muon_index;
+  int dims[MUSIM_MAX_SPINS];
+  double gammas[MUSIM_MAX_SPINS];
+};
+
+// O_c[idx] = px M0 + py M1 + pz M2 ; grid (ceil(d*d/256), n_cfg)
+__global__ void form_obs_kernel(int d, const cplx *__restrict__ M, const double *__restrict__ pf,
+                                cplx *__restrict__ O) {
+  const size_t cfg = blockIdx.y;
+  const size_t dd = (size_t)d * d;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dd) return;
+  const double px = pf[cfg * 3 + 0], py = pf[cfg * 3 + 1], pz = pf[cfg * 3 + 2];
+  const cplx m0 = M[idx], m1 = M[dd + idx], m2 = M[2 * dd + idx];
+  O[cfg * dd + idx] = make_c(px * m0.x + py * m1.x + pz * m2.x, px * m0.y + py * m1.y + pz * m2.y);
+}
+
+// Spin matrices for spin I (n = 2I+1), m from +I to -I  (spinop.py:14-41):
+// h = nx Sx + ny Sy + nz Sz  as an n x n Hermitian matrix.
+__device__ inline void spin_dot(int n, double nx, double ny, double nz, cplx *h /* n*n */) {
+  const double I = 0.5 * (n - 1);
+  for (int i = 0; i < n * n; ++i) h[i] = make_c(0.0, 0.0);
+  for (int a = 0; a < n; ++a) {
+    const double m = I - a;
+    h[a * n + a] = make_c(nz * m, 0.0);
+    if (a + 1 < n) {
+      // <m|S+|m-1> = sqrt(I(I+1) - m(m-1)) ; element (a, a+1) of S+
+      const double mp = I - (a + 1);
+      const double sp = sqrt(I * (I + 1.0) - mp * (mp + 1.0));
+      // Sx = (S+ + S-)/2, Sy = (S+ - S-)/(2i):  (a,a+1): nx*sp/2 - i*ny*sp/2
+      h[a * n + a + 1] = make_c(0.5 * nx * sp, -0.5 * ny * sp);
+      h[(a + 1) * n + a] = make_c(0.5 * nx * sp, 0.5 * ny * sp);
+    }
+  }
+}
+
+// Thermal single-spin density matrix  rho = sum_m p_m P_m(n.S),  p_m ~ exp(-x m)
+// (experiment.py:204-228: eigh of B.S, E = eval*1e6*gamma, Boltzmann weights exp(-hE/kT)).
+// P_m are Lagrange projectors  prod_{m' != m} (h - m')/(m - m').
+__device__ inline void thermal_factor(int n, double gamma, double bx, double by, double bz,
+                                      double T, cplx *rho /* n*n */) {
+  const double I = 0.5 * (n - 1);
+  const double Bn = sqrt(bx * bx + by * by + bz * bz);
+  double pm[MUSIM_MAX_SDIM];
+  bool uniform = false;
+  const double kB = 1.380649e-23, hP = 6.62607015e-34;
+  const double escale = gamma * Bn * 1e6;  // E_m = m * escale  (Hz)
+  if (Bn == 0.0 || escale == 0.0) {
+    uniform = true;
+  } else if (T > 0.0) {
+    if (isinf(T)) {
+      uniform = true;
+    } else {
+      const double x = hP * escale / (kB * T);
+      // subtract the maximum exponent for robustness (the reference does not; same result
+      // wherever the reference does not overflow)
+      double mx = -1e300;
+      for (int a = 0; a < n; ++a) mx = fmax(mx, -x * (I - a));
+      double s = 0.0;
+      for (int a = 0; a < n; ++a) {
+        pm[a] = exp(-x * (I - a) - mx);
+        s += pm[a];
+      }
+      for (int a = 0; a < n; ++a) pm[a] /= s;
+    }
+  } else {  // T == 0: ground state only (experiment.py:218-219)
+    for (int a = 0; a < n; ++a) pm[a] = 0.0;
+    if (escale > 0.0)
+      pm[n - 1] = 1.0;  // m = -I has the lowest E
+    else
+      pm[0] = 1.0;
+  }
+  if (uniform) {
+    for (int i = 0; i < n * n; ++i) rho[i] = make_c(0.0, 0.0);
+    for (int a = 0; a < n; ++a) rho[a * n + a] = make_c(1.0 / n, 0.0);
+    return;
+  }
+  cplx h[MUSIM_MAX_SDIM * MUSIM_MAX_SDIM], P[MUSIM_MAX_SDIM * MUSIM_MAX_SDIM],
+      Q[MUSIM_MAX_SDIM * MUSIM_MAX_SDIM];
+  spin_dot(n, bx / Bn, by / Bn, bz / Bn, h);
+  for (int i = 0; i < n * n; ++i) rho[i] = make_c(0.0, 0.0);
+  for (int a = 0; a < n; ++a) {
+    if (pm[a] == 0.0) continue;
+    const double m = I - a;
+    for (int i = 0; i < n * n; ++i) P[i] = make_c(0.0, 0.0);
+    for (int i = 0; i < n; ++i) P[i * n + i] = make_c(1.0, 0.0);
+    for (int b = 0; b < n; ++b) {
+      if (b == a) continue;
+      const double mb = I - b;
+      const double inv = 1.0 / (m - mb);
+      // Q = P * (h - mb) * inv
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+          cplx acc = make_c(0.0, 0.0);
+          for (int k = 0; k < n; ++k) {
+            cplx hk = h[k * n + j];
+            if (k == j) hk.x -= mb;
+            cfma(acc, P[i * n + k], hk);
+          }
+          Q[i * n + j] = cscale(inv, acc);
+        }
+      for (int i = 0; i < n * n; ++i) P[i] = Q[i];
+    }
+    for (int i = 0; i < n * n; ++i) {
+      rho[i].x += pm[a] * P[i].x;
+      rho[i].y += pm[a] * P[i].y;
+    }
+  }
+}
+
+// One CTA per configuration: factors in shared memory, then the Kronecker product.
+__global__ void rho0_kernel(int d, SpinTable tab, const double *__restrict__ Bf,
+                            const double *__restrict__ pf, const double *__restrict__ Tf,
+                            cplx *__restrict__ R) {
+  __shared__ cplx fac[MUSIM_MAX_SPINS][MUSIM_MAX_SDIM * MUSIM_MAX_SDIM];
+  const size_t cfg = blockIdx.x;
+  const double bx = Bf[cfg * 3], by = Bf[cfg * 3 + 1], bz = Bf[cfg * 3 + 2];
+  const double T = Tf[cfg];
+  if (threadIdx.x < tab.n_spins) {
+    const int s = threadIdx.x;
+    const int n = tab.dims[s];
+    if (s == tab.muon_index) {
+      // pure state along p:  1/2 + p_hat . S   (DensityOperator.from_vectors, spinop.py:455-530)
+      double px = pf[cfg * 3], py = pf[cfg * 3 + 1], pz = pf[cfg * 3 + 2];
+      const double pn = sqrt(px * px + py * py + pz * pz);
+      if (pn > 0.0) {
+        px /= pn;
+        py /= pn;
+        pz /= pn;
+      }
+      spin_dot(2, px, py, pz, fac[s]);
+      fac[s][0].x += 0.5;
+      fac[s][3].x += 0.5;
+    } else {
+      thermal_factor(n, tab.gammas[s], bx, by, bz, T, fac[s]);
+    }
+  }
+  __syncthreads();
+  const size_t dd = (size_t)d * d;
+  for (int idx = threadIdx.x; idx < dd; idx += blockDim.x) {
+    int i = idx / d, j = idx - (idx / d) * d;
+    cplx v = make_c(1.0, 0.0);
+    for (int s = tab.n_spins - 1; s >= 0; --s) {
+      const int n = tab.dims[s];
+      const int is = i % n, js = j % n;
+      i /= n;
+      j /= n;
+      v = cmul(v, fac[s][is * n + js]);
+    }
+    R[cfg * dd + idx] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Batched complex GEMM, C[c] = op(A[c]) * B[c] (all d x d, row-major).  CONJ_A: op = A^H.
+// 32x32 output tile per CTA (256 threads, 2x2 complex outputs each), K staged through
+// shared memory in slabs of 16.  a_stride / b_stride may be 0 (operand shared by the batch).
+// EPI: 0 store C; 1 store (|C|^2 * scale, 0)   [fast-path weights |O'|^2 / d_o]
+// ---------------------------------------------------------------------------------------
+template <bool CONJ_A, int EPI>
+__global__ void __launch_bounds__(256)
+cgemm_batched_kernel(int d, const cplx *__restrict__ A, size_t a_stride,
+                     const cplx *__restrict__ B, size_t b_stride, cplx *__restrict__ C,
+                     double scale) {
+  constexpr int TM = 32, TN = 32, TK = 16;
+  __shared__ cplx sA[TK][TM + 1];  // sA[k][m] = op(A)(m0+m, k0+k)
+  __shared__ cplx sB[TK][TN + 1];  // sB[k][n] = B(k0+k, n0+n)
+  const size_t cfg = blockIdx.z;
+  const size_t dd = (size_t)d * d;
+  const cplx *Ab = A + cfg * a_stride;
+  const cplx *Bb = B + cfg * b_stride;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads
+  cplx acc[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j] = make_c(0.0, 0.0);
+
+  for (int k0 = 0; k0 < d; k0 += TK) {
+    // stage A slab: TK x TM elements, 512 -> 2 per thread
+    for (int e = threadIdx.x; e < TK * TM; e += 256) {
+      int k, m;
+      cplx v = make_c(0.0, 0.0);
+      if (CONJ_A) {
+        // op(A)(m,k) = conj(A(k,m)): read row k0+k of A, consecutive m -> coalesced
+        k = e / TM;
+        m = e - k * TM;
+        if (k0 + k < d && m0 + m < d) v = cconj(Ab[(size_t)(k0 + k) * d + m0 + m]);
+      } else {
+        // op(A)(m,k) = A(m,k): read row m0+m, consecutive k -> coalesced
+        m = e / TK;
+        k = e - m * TK;
+        if (k0 + k < d && m0 + m < d) v = Ab[(size_t)(m0 + m) * d + k0 + k];
+      }
+      sA[k][m] = v;
+    }
+    for (int e = threadIdx.x; e < TK * TN; e += 256) {
+      const int k = e / TN, n = e - k * TN;
+      cplx v = make_c(0.0, 0.0);
+      if (k0 + k < d && n0 + n < d) v = Bb[(size_t)(k0 + k) * d + n0 + n];
+      sB[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const cplx a0 = sA[k][ty], a1 = sA[k][ty + 16];
+      const cplx b0 = sB[k][tx], b1 = sB[k][tx + 16];
+      cfma(acc[0][0], a0, b0);
+      cfma(acc[0][1], a0, b1);
+      cfma(acc[1][0], a1, b0);
+      cfma(acc[1][1], a1, b1);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      if (m < d && n < d) {
+        cplx v = acc[i][j];
+        if (EPI == 1) v = make_c(cnorm2(v) * scale, 0.0);
+        C[cfg * dd + (size_t)m * d + n] = v;
+      }
+    }
+}
+
+// W = X .* conj(Y) elementwise (general weights  w_ij = rho'_ij * O'_ji, O' Hermitian)
+__global__ void weights_kernel(size_t n, const cplx *__restrict__ X, const cplx *__restrict__ Y,
+                               cplx *__restrict__ W) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) W[i] = cmulc(X[i], Y[i]);
+}
+
+// Integral of the decaying signal, one CTA per configuration:
+//   val = (1/tau) Re sum_ab w_ab / (1/tau + 2 pi i (l_a - l_b));   out[slot] += weight * val
+__global__ void integral_kernel(int d, const cplx *__restrict__ W, const double *__restrict__ lam,
+                                const double *__restrict__ wgt, const int *__restrict__ slot,
+                                double tau, double *__restrict__ out) {
+  __shared__ double red[34];
+  const size_t cfg = blockIdx.x;
+  const size_t dd = (size_t)d * d;
+  const cplx *Wc = W + cfg * dd;
+  const double *lc = lam + cfg * d;
+  const double it = 1.0 / tau;
+  const double twopi = 6.283185307179586476925286766559;
+  double acc = 0.0;
+  for (int idx = threadIdx.x; idx < dd; idx += blockDim.x) {
+    const int a = idx / d, b = idx - a * d;
+    const cplx w = Wc[idx];
+    const double om = twopi * (lc[a] - lc[b]);
+    // Re[ w / (it + i om) ] = (w.x*it + w.y*om) / (it^2 + om^2)
+    acc += (w.x * it + w.y * om) / (it * it + om * om);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(&out[slot[cfg]], wgt[cfg] * acc * it);
+}
+
+}  // namespace musim
