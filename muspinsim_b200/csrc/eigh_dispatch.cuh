@@ -1,0 +1,161 @@
+// eigh_dispatch.cuh -- host-side launcher and workspace of the two batched eigensolvers.
+#pragma once
+#include "eigh_hql.cuh"
+#include "eigh_jacobi.cuh"
+#include "rotate.cuh"
+
+namespace musim {
+
+#define MUSIM_MAX_SMEM_OPTIN (227 * 1024)
+
+enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
+
+inline int pick_eigh(long opt, int d) {
+  if (opt == EIGH_JACOBI) return EIGH_JACOBI;
+  if (opt == EIGH_HQL) return hql_supported(d) ? EIGH_HQL : EIGH_JACOBI;
+  return hql_supported(d) ? EIGH_HQL : EIGH_JACOBI;
+}
+
+struct EighWs {
+  int64_t cap = 0;
+  int d = 0, method = 0;
+  cplx *Vg = nullptr;
+  double *dbuf = nullptr, *ebuf = nullptr, *Zt = nullptr;
+  cplx *Q = nullptr;
+  double2 *rot = nullptr;
+  SweepIdx *swp = nullptr;
+  int *nswp = nullptr;
+  unsigned short *perm = nullptr;
+  size_t rot_cap = 0;
+  int swp_cap = 0;
+
+  static bool jacobi_vglobal(int d) { return eigh_jacobi_smem(d, false) > MUSIM_MAX_SMEM_OPTIN; }
+
+  static size_t bytes_per_matrix(int method, int d) {
+    const size_t dd = (size_t)d * d;
+    if (method == EIGH_HQL)
+      return 2 * d * sizeof(double) + dd * sizeof(cplx) + dd * sizeof(double) +
+             (3 * dd + 64) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
+             d * sizeof(unsigned short);
+    return jacobi_vglobal(d) ? (size_t)d * (d | 1) * sizeof(cplx) : 0;
+  }
+
+  void release() {
+    cudaFree(Vg);
+    cudaFree(dbuf);
+    cudaFree(ebuf);
+    cudaFree(Zt);
+    cudaFree(Q);
+    cudaFree(rot);
+    cudaFree(swp);
+    cudaFree(nswp);
+    cudaFree(perm);
+    Vg = nullptr;
+    dbuf = ebuf = Zt = nullptr;
+    Q = nullptr;
+    rot = nullptr;
+    swp = nullptr;
+    nswp = nullptr;
+    perm = nullptr;
+    cap = 0;
+  }
+
+  cudaError_t ensure(int method_, int d_, int64_t n) {
+    if (cap >= n && d == d_ && method == method_) return cudaSuccess;
+    release();
+    d = d_;
+    method = method_;
+    const size_t dd = (size_t)d * d;
+    cudaError_t e = cudaSuccess;
+#define EW_ALLOC(ptr, count)                                              \
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ptr, (count) * sizeof(*ptr));
+    if (method == EIGH_HQL) {
+      rot_cap = 3 * dd + 64;
+      swp_cap = 6 * d + 16;
+      EW_ALLOC(dbuf, (size_t)n * d);
+      EW_ALLOC(ebuf, (size_t)n * d);
+      EW_ALLOC(Q, (size_t)n * dd);
+      EW_ALLOC(Zt, (size_t)n * dd);
+      EW_ALLOC(rot, (size_t)n * rot_cap);
+      EW_ALLOC(swp, (size_t)n * swp_cap);
+      EW_ALLOC(nswp, (size_t)n);
+      EW_ALLOC(perm, (size_t)n * d);
+    } else if (jacobi_vglobal(d)) {
+      EW_ALLOC(Vg, (size_t)n * d * (d | 1));
+    }
+#undef EW_ALLOC
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+};
+
+// Eigen-decompose n matrices: either H0 + B.Z (Ain == nullptr) or Ain[n].  lam ascending,
+// U row-major with eigenvectors in columns.  Returns 0, a cudaError_t (> 0), or -5 (unsupported).
+inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
+                       const cplx *Ain, double *lam, cplx *U, EighWs &ws, int *status, cudaStream_t st,
+                       int64_t *launches) {
+  int64_t dummy = 0;
+  if (!launches) launches = &dummy;
+  cudaError_t e = ws.ensure(method, d, n);
+  if (e != cudaSuccess) return (int)e;
+  if (method == EIGH_HQL) {
+    if (!hql_supported(d)) return -5;
+    const HqlGeom g = hql_geom(d);
+    const size_t smem = hql_tridiag_smem(d, g);
+    if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
+    if (Ain) {
+      e = cudaFuncSetAttribute(hql_tridiag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      hql_tridiag_kernel<false><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf, ws.ebuf, ws.Q);
+    } else {
+      e = cudaFuncSetAttribute(hql_tridiag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      hql_tridiag_kernel<true><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf, ws.ebuf, ws.Q);
+    }
+    ++*launches;
+    const unsigned tb = (unsigned)((n + 127) / 128);
+    if (d <= 8)
+      hql_tql_kernel<8><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
+    else if (d <= 32)
+      hql_tql_kernel<32><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
+    else if (d <= 64)
+      hql_tql_kernel<64><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
+    else
+      hql_tql_kernel<128><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
+    ++*launches;
+    const size_t zsmem = (size_t)d * (d | 1) * sizeof(double);
+    e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
+    if (e != cudaSuccess) return (int)e;
+    const int ath = std::min(128, (d + 31) & ~31);
+    hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
+    ++*launches;
+    dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);
+    cgemm_realB_kernel<<<grid, 256, 0, st>>>(d, ws.Q, ws.Zt, U);
+    ++*launches;
+    return (int)cudaGetLastError();
+  }
+  // Jacobi
+  const bool vglob = EighWs::jacobi_vglobal(d);
+  const size_t smem = eigh_jacobi_smem(d, vglob);
+  if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
+  int nth = 256;
+  if (d * d <= 64)
+    nth = 32;
+  else if (d * d <= 256)
+    nth = 64;
+  else if (d * d <= 1024)
+    nth = 128;
+  if (Ain) {
+    e = cudaFuncSetAttribute(eigh_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    eigh_jacobi_kernel<false><<<(unsigned)n, nth, smem, st>>>(d, H0, Z, B, Ain, lam, U, status, 40, vglob ? ws.Vg : nullptr);
+  } else {
+    e = cudaFuncSetAttribute(eigh_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    eigh_jacobi_kernel<true><<<(unsigned)n, nth, smem, st>>>(d, H0, Z, B, Ain, lam, U, status, 40, vglob ? ws.Vg : nullptr);
+  }
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace musim

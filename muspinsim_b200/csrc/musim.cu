@@ -18,8 +18,7 @@
 
 #include "../../include/musim.h"
 #include "common.cuh"
-#include "eigh_jacobi.cuh"
-#include "eigh_hql.cuh"
+#include "eigh_dispatch.cuh"
 #include "lindblad.cuh"
 #include "peak.cuh"
 #include "polar.cuh"
@@ -28,7 +27,6 @@
 using namespace musim;
 
 #define MUSIM_VERSION 1
-#define MAX_SMEM_OPTIN (227 * 1024)
 
 enum Phase { PH_EIGH = 0, PH_ROTATE, PH_RHO0, PH_POLAR, PH_INTEGRAL, PH_LINDBLAD, PH_COUNT };
 static const char *kPhaseNames[PH_COUNT] = {"eigh", "rotate", "rho0", "polar", "integral", "lindblad"};
@@ -49,7 +47,8 @@ struct musim_handle {
   // workspaces (sized for `ws_cfg` configurations)
   int64_t ws_cfg = 0;
   double *lam = nullptr;
-  cplx *U = nullptr, *T1 = nullptr, *Y = nullptr, *X = nullptr, *W = nullptr, *Oc = nullptr, *Vg = nullptr;
+  cplx *U = nullptr, *T1 = nullptr, *Y = nullptr, *X = nullptr, *W = nullptr, *Oc = nullptr;
+  EighWs ews;
   void *lws = nullptr;  // Lindblad workspace
   size_t lws_bytes = 0;
   int *status = nullptr;
@@ -94,9 +93,9 @@ static void free_ws(musim_handle *h) {
   cudaFree(h->X);
   cudaFree(h->W);
   cudaFree(h->Oc);
-  cudaFree(h->Vg);
+  h->ews.release();
   h->lam = nullptr;
-  h->U = h->T1 = h->Y = h->X = h->W = h->Oc = h->Vg = nullptr;
+  h->U = h->T1 = h->Y = h->X = h->W = h->Oc = nullptr;
   h->ws_cfg = 0;
 }
 
@@ -231,44 +230,6 @@ extern "C" int musim_destroy(musim_handle *h) {
   return MUSIM_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// eigensolver dispatch
-// ---------------------------------------------------------------------------------------
-static int pick_eigh(long opt, int d) {
-  if (opt == 1 || opt == 2) return (int)opt;
-  return hql_supported(d) ? 2 : 1;
-}
-
-// Ain == nullptr: build H from H0/Z/B.  Returns cudaError_t as int (0 ok) or MUSIM_EUNSUP.
-static int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
-                       const cplx *Ain, double *lam, cplx *U, cplx *Vg, int *status,
-                       cudaStream_t st, int64_t *launches) {
-  if (method == 2 && hql_supported(d)) {
-    int rc = launch_eigh_hql(d, n, H0, Z, B, Ain, lam, U, status, st, launches);
-    return rc;
-  }
-  const bool vglob = eigh_jacobi_smem(d, false) > MAX_SMEM_OPTIN;
-  const size_t smem = eigh_jacobi_smem(d, vglob);
-  if (smem > MAX_SMEM_OPTIN) return MUSIM_EUNSUP;
-  if (vglob && !Vg) return MUSIM_EUNSUP;
-  int nth = 256;
-  if (d * d <= 64) nth = 32;
-  else if (d * d <= 256) nth = 64;
-  else if (d * d <= 1024) nth = 128;
-  cudaError_t e;
-  if (Ain) {
-    e = cudaFuncSetAttribute(eigh_jacobi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    eigh_jacobi_kernel<false><<<(unsigned)n, nth, smem, st>>>(d, H0, Z, B, Ain, lam, U, status, 40, vglob ? Vg : nullptr);
-  } else {
-    e = cudaFuncSetAttribute(eigh_jacobi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    eigh_jacobi_kernel<true><<<(unsigned)n, nth, smem, st>>>(d, H0, Z, B, Ain, lam, U, status, 40, vglob ? Vg : nullptr);
-  }
-  if (launches) ++*launches;
-  return (int)cudaGetLastError();
-}
-
 extern "C" int musim_eigh(int device, int d, int64_t batch, const double *A, double *evals,
                           double *evecs, int method, void *cuda_stream) {
   musim_handle *h = nullptr;
@@ -277,18 +238,24 @@ extern "C" int musim_eigh(int device, int d, int64_t batch, const double *A, dou
   CK(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int m = pick_eigh(method, d);
-  cplx *Vg = nullptr;
   int *status = nullptr;
   CK(dev_alloc(&status, 4));
   CK(cudaMemsetAsync(status, 0, 4 * sizeof(int), st));
-  const bool vglob = (m == 1) && eigh_jacobi_smem(d, false) > MAX_SMEM_OPTIN;
-  if (vglob) CK(dev_alloc(&Vg, (size_t)batch * d * (d | 1)));
-  int rc = launch_eigh(m, d, batch, nullptr, nullptr, nullptr, reinterpret_cast<const cplx *>(A),
-                       evals, reinterpret_cast<cplx *>(evecs), Vg, status, st, nullptr);
+  EighWs ws;
+  // bound the workspace: process in slices
+  const size_t per = std::max<size_t>(1, EighWs::bytes_per_matrix(m, d));
+  const int64_t slice = std::max<int64_t>(1, std::min<int64_t>(batch, (int64_t)(1.0e9 / per)));
+  int rc = 0;
+  const size_t dd = (size_t)d * d;
+  for (int64_t b0 = 0; b0 < batch && rc == 0; b0 += slice) {
+    const int64_t n = std::min(slice, batch - b0);
+    rc = launch_eigh(m, d, n, nullptr, nullptr, nullptr, reinterpret_cast<const cplx *>(A) + b0 * dd,
+                     evals + b0 * d, reinterpret_cast<cplx *>(evecs) + b0 * dd, ws, status, st, nullptr);
+  }
   int hstat[4] = {0, 0, 0, 0};
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaMemcpy(hstat, status, sizeof hstat, cudaMemcpyDeviceToHost);
-  cudaFree(Vg);
+  ws.release();
   cudaFree(status);
   if (rc == MUSIM_EUNSUP) return MUSIM_EUNSUP;
   if (rc != 0 || e != cudaSuccess) return MUSIM_ECUDA;
@@ -299,9 +266,9 @@ extern "C" int musim_eigh(int device, int d, int64_t batch, const double *A, dou
 // ---------------------------------------------------------------------------------------
 // the batched run
 // ---------------------------------------------------------------------------------------
-static int ensure_ws(musim_handle *h, int64_t n, bool general, bool vglob) {
+static int ensure_ws(musim_handle *h, int64_t n, bool general) {
   const size_t dd = (size_t)h->d * h->d;
-  if (h->ws_cfg >= n && (!general || h->X) && (!vglob || h->Vg)) return MUSIM_OK;
+  if (h->ws_cfg >= n && (!general || h->X)) return MUSIM_OK;
   free_ws(h);
   CK(dev_alloc(&h->lam, (size_t)n * h->d));
   CK(dev_alloc(&h->U, n * dd));
@@ -312,7 +279,6 @@ static int ensure_ws(musim_handle *h, int64_t n, bool general, bool vglob) {
     CK(dev_alloc(&h->Y, n * dd));
     CK(dev_alloc(&h->X, n * dd));
   }
-  if (vglob) CK(dev_alloc(&h->Vg, (size_t)n * h->d * (h->d | 1)));
   h->ws_cfg = n;
   return MUSIM_OK;
 }
@@ -415,14 +381,13 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   }
 
   const int method = pick_eigh(h->opt_eigh, d);
-  const bool vglob = (method == 1) && eigh_jacobi_smem(d, false) > MAX_SMEM_OPTIN;
-  // chunk: bound the workspace to ~1.5 GB
-  const int nbuf = general ? 7 : 5;
-  int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk
-                                   : std::max<int64_t>(148, (int64_t)(1.5e9 / (nbuf * dd * sizeof(cplx))));
+  // chunk: bound the workspace to ~3 GB
+  const int nbuf = general ? 6 : 4;
+  const size_t per_cfg = nbuf * dd * sizeof(cplx) + EighWs::bytes_per_matrix(method, d) + d * sizeof(double);
+  int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>(148, (int64_t)(3.0e9 / per_cfg));
   chunk = std::min<int64_t>(chunk, n_cfg);
   chunk = std::min<int64_t>(chunk, 65535LL * 8);
-  int rc = ensure_ws(h, chunk, general, vglob);
+  int rc = ensure_ws(h, chunk, general);
   if (rc) return rc;
   CK(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
 
@@ -432,7 +397,7 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
     const int64_t n = std::min(chunk, n_cfg - c0);
     {
       PhaseTimer pt(h, st, PH_EIGH);
-      rc = launch_eigh(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->Vg, h->status, st,
+      rc = launch_eigh(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->ews, h->status, st,
                        &h->launches);
       if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
       if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));

@@ -31,6 +31,7 @@ def eigh_check(d, batch, method, seed=0, degenerate=False):
             q, _ = np.linalg.qr(A[b])
             lam = (np.arange(d) // 4).astype(float)
             A[b] = (q * lam) @ q.conj().T
+    A = np.ascontiguousarray(A)
     At = torch.from_numpy(A).cuda()
     ev = torch.empty(batch, d, dtype=torch.float64, device="cuda")
     U = torch.empty(batch, d, d, dtype=torch.complex128, device="cuda")
@@ -48,7 +49,7 @@ def eigh_check(d, batch, method, seed=0, degenerate=False):
     return e_err, res, orth
 
 
-for d in (2, 3, 4, 8, 12, 24, 32, 64, 96):
+for d in (1, 2, 3, 4, 8, 12, 17, 24, 32, 64, 96, 120):
     for method in (1, 2):
         try:
             eigh_check(d, 64, method)
@@ -70,7 +71,7 @@ specs = [
 for spec in specs:
     try:
         want = mo.run_spec(spec, evolve_fn=mo.evolve_vectorised)
-        for opts in ({}, {"polar": 1}):
+        for opts in ({}, {"polar": 1}, {"eigh": 1}):
             r = ExperimentRunner(spec, device=0)
             for k, v in opts.items():
                 r.set_option(k, v)
