@@ -2,6 +2,7 @@
 #pragma once
 #include "eigh_hql.cuh"
 #include "eigh_jacobi.cuh"
+#include "profiler.cuh"
 #include "rotate.cuh"
 
 namespace musim {
@@ -93,7 +94,7 @@ struct EighWs {
 // U row-major with eigenvectors in columns.  Returns 0, a cudaError_t (> 0), or -5 (unsupported).
 inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
                        const cplx *Ain, double *lam, cplx *U, EighWs &ws, int *status, cudaStream_t st,
-                       int64_t *launches) {
+                       int64_t *launches, Profiler *prof) {
   int64_t dummy = 0;
   if (!launches) launches = &dummy;
   cudaError_t e = ws.ensure(method, d, n);
@@ -103,6 +104,8 @@ inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx 
     const HqlGeom g = hql_geom(d);
     const size_t smem = hql_tridiag_smem(d, g);
     if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
+    {
+    ProfScope ps(prof, st, PH_EIGH_TRIDIAG);
     if (Ain) {
       e = cudaFuncSetAttribute(hql_tridiag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
@@ -112,8 +115,11 @@ inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx 
       if (e != cudaSuccess) return (int)e;
       hql_tridiag_kernel<true><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf, ws.ebuf, ws.Q);
     }
+    }
     ++*launches;
     const unsigned tb = (unsigned)((n + 127) / 128);
+    {
+    ProfScope ps(prof, st, PH_EIGH_TQL);
     if (d <= 8)
       hql_tql_kernel<8><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
     else if (d <= 32)
@@ -122,15 +128,22 @@ inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx 
       hql_tql_kernel<64><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
     else
       hql_tql_kernel<128><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
+    }
     ++*launches;
     const size_t zsmem = (size_t)d * (d | 1) * sizeof(double);
     e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
     if (e != cudaSuccess) return (int)e;
     const int ath = std::min(128, (d + 31) & ~31);
-    hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
+    {
+      ProfScope ps(prof, st, PH_EIGH_APPLY);
+      hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
+    }
     ++*launches;
     dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);
-    cgemm_realB_kernel<<<grid, 256, 0, st>>>(d, ws.Q, ws.Zt, U);
+    {
+      ProfScope ps(prof, st, PH_EIGH_BACK);
+      cgemm_realB_kernel<<<grid, 256, 0, st>>>(d, ws.Q, ws.Zt, U);
+    }
     ++*launches;
     return (int)cudaGetLastError();
   }
@@ -138,6 +151,7 @@ inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx 
   const bool vglob = EighWs::jacobi_vglobal(d);
   const size_t smem = eigh_jacobi_smem(d, vglob);
   if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
+  ProfScope ps(prof, st, PH_EIGH_JACOBI);
   int nth = 256;
   if (d * d <= 64)
     nth = 32;

@@ -24,7 +24,7 @@
 
 namespace musim {
 
-#define HQL_MAX_D 120
+#define HQL_MAX_D 118  // A (d x (d|1) complex) must fit the 227 KB of opt-in shared memory
 
 inline bool hql_supported(int d) { return d >= 1 && d <= HQL_MAX_D; }
 

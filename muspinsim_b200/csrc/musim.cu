@@ -18,6 +18,7 @@
 
 #include "../../include/musim.h"
 #include "common.cuh"
+#include "profiler.cuh"
 #include "eigh_dispatch.cuh"
 #include "lindblad.cuh"
 #include "peak.cuh"
@@ -28,8 +29,6 @@ using namespace musim;
 
 #define MUSIM_VERSION 1
 
-enum Phase { PH_EIGH = 0, PH_ROTATE, PH_RHO0, PH_POLAR, PH_INTEGRAL, PH_LINDBLAD, PH_COUNT };
-static const char *kPhaseNames[PH_COUNT] = {"eigh", "rotate", "rho0", "polar", "integral", "lindblad"};
 
 struct musim_handle {
   int device = 0;
@@ -59,8 +58,7 @@ struct musim_handle {
   long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0;
   // bookkeeping
   int64_t launches = 0;
-  double phase_ms[PH_COUNT] = {0};
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  Profiler prof;
   std::string err;
 };
 
@@ -107,8 +105,9 @@ extern "C" int64_t musim_launch_count(musim_handle *h) { return h ? h->launches 
 
 extern "C" double musim_phase_ms(musim_handle *h, const char *phase) {
   if (!h || !phase) return -1.0;
+  h->prof.resolve();
   for (int i = 0; i < PH_COUNT; ++i)
-    if (!strcmp(phase, kPhaseNames[i])) return h->phase_ms[i];
+    if (!strcmp(phase, kPhaseNames[i])) return h->prof.ms[i];
   return -1.0;
 }
 
@@ -120,8 +119,11 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->opt_polar = value;
   else if (!strcmp(key, "chunk"))
     h->opt_chunk = value;
-  else if (!strcmp(key, "profile"))
+  else if (!strcmp(key, "profile")) {  // 1: enable and reset the accumulators, 0: disable
     h->opt_profile = value;
+    h->prof.on = value != 0;
+    if (value) h->prof.reset();
+  }
   else if (!strcmp(key, "gemm"))
     h->opt_gemm = value;
   else
@@ -182,8 +184,6 @@ extern "C" int musim_create(musim_handle **out, int device, int d, int n_spins, 
   }
   CK(dev_alloc(&h->status, 4));
   CK(cudaMemset(h->status, 0, 4 * sizeof(int)));
-  CK(cudaEventCreate(&h->ev[0]));
-  CK(cudaEventCreate(&h->ev[1]));
   return MUSIM_OK;
 }
 
@@ -224,8 +224,7 @@ extern "C" int musim_destroy(musim_handle *h) {
   cudaFree(h->status);
   cudaFree(h->stage);
   cudaFree(h->lws);
-  if (h->ev[0]) cudaEventDestroy(h->ev[0]);
-  if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+  h->prof.destroy();
   delete h;
   return MUSIM_OK;
 }
@@ -250,7 +249,7 @@ extern "C" int musim_eigh(int device, int d, int64_t batch, const double *A, dou
   for (int64_t b0 = 0; b0 < batch && rc == 0; b0 += slice) {
     const int64_t n = std::min(slice, batch - b0);
     rc = launch_eigh(m, d, n, nullptr, nullptr, nullptr, reinterpret_cast<const cplx *>(A) + b0 * dd,
-                     evals + b0 * d, reinterpret_cast<cplx *>(evecs) + b0 * dd, ws, status, st, nullptr);
+                     evals + b0 * d, reinterpret_cast<cplx *>(evecs) + b0 * dd, ws, status, st, nullptr, nullptr);
   }
   int hstat[4] = {0, 0, 0, 0};
   cudaError_t e = cudaStreamSynchronize(st);
@@ -315,25 +314,6 @@ static void launch_gemm(int d, int64_t n, const cplx *A, size_t as, const cplx *
   ++*launches;
 }
 
-struct PhaseTimer {
-  musim_handle *h;
-  cudaStream_t st;
-  int ph;
-  bool on;
-  PhaseTimer(musim_handle *h_, cudaStream_t st_, int ph_) : h(h_), st(st_), ph(ph_), on(h_->opt_profile != 0) {
-    if (on) cudaEventRecord(h->ev[0], st);
-  }
-  ~PhaseTimer() {
-    if (on) {
-      cudaEventRecord(h->ev[1], st);
-      cudaEventSynchronize(h->ev[1]);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-      h->phase_ms[ph] += ms;
-    }
-  }
-};
-
 extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double *B, const double *p,
                          const double *T, const double *w, const int32_t *slot, int nt,
                          const double *times, double tau, int n_slots, double *out,
@@ -358,7 +338,6 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int d = h->d;
   const size_t dd = (size_t)d * d;
-  for (int i = 0; i < PH_COUNT; ++i) h->phase_ms[i] = 0.0;
 
   TimeGrid tg;
   if (!integral) {
@@ -396,14 +375,13 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
     const int64_t n = std::min(chunk, n_cfg - c0);
     {
-      PhaseTimer pt(h, st, PH_EIGH);
       rc = launch_eigh(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->ews, h->status, st,
-                       &h->launches);
+                       &h->launches, &h->prof);
       if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
       if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
     }
     {
-      PhaseTimer pt(h, st, PH_ROTATE);
+      ProfScope pt(&h->prof, st, PH_ROTATE);
       dim3 g1((unsigned)((dd + 255) / 256), (unsigned)n);
       form_obs_kernel<<<g1, 256, 0, st>>>(d, h->M, p + 3 * c0, h->Oc);
       ++h->launches;
@@ -419,13 +397,13 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       const cplx *R = h->rho0_explicit;
       size_t rs = 0;
       if (!R) {
-        PhaseTimer pt(h, st, PH_RHO0);
+        ProfScope pt(&h->prof, st, PH_RHO0);
         rho0_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->tab, B + 3 * c0, p + 3 * c0, T + c0, h->Oc);
         ++h->launches;
         R = h->Oc;
         rs = dd;
       }
-      PhaseTimer pt(h, st, PH_ROTATE);
+      ProfScope pt(&h->prof, st, PH_ROTATE);
       launch_gemm<false, 0>(d, n, R, rs, h->U, dd, h->T1, 1.0, st, &h->launches);
       launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->X, 1.0, st, &h->launches);
       const size_t tot = (size_t)n * dd;
@@ -433,11 +411,11 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       ++h->launches;
     }
     if (integral) {
-      PhaseTimer pt(h, st, PH_INTEGRAL);
+      ProfScope pt(&h->prof, st, PH_INTEGRAL);
       integral_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->W, h->lam, w + c0, slot + c0, tau, out);
       ++h->launches;
     } else {
-      PhaseTimer pt(h, st, PH_POLAR);
+      ProfScope pt(&h->prof, st, PH_POLAR);
       const bool fact = (h->opt_polar == 2) || (h->opt_polar == 0 && tg.uniform);
       if (h->opt_polar == 2 && !tg.uniform)
         return set_err(h, MUSIM_EINVAL, "time-factorised polarisation needs a uniform time grid");
