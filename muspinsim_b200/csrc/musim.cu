@@ -35,6 +35,7 @@ struct musim_handle {
   int d = 0;
   SpinTable tab;
   int n_diss = 0;
+  bool thermal_ok = true;
   std::vector<int> diss_spin;
   std::vector<double> diss_rate;
   // device constants
@@ -142,7 +143,7 @@ extern "C" int musim_create(musim_handle **out, int device, int d, int n_spins, 
     return MUSIM_EINVAL;
   long prod = 1;
   for (int i = 0; i < n_spins; ++i) {
-    if (dims[i] < 1 || dims[i] > MUSIM_MAX_SDIM) return MUSIM_EINVAL;
+    if (dims[i] < 1) return MUSIM_EINVAL;
     prod *= dims[i];
   }
   if (prod != d) return MUSIM_EINVAL;
@@ -154,9 +155,11 @@ extern "C" int musim_create(musim_handle **out, int device, int d, int n_spins, 
   h->d = d;
   h->tab.n_spins = n_spins;
   h->tab.muon_index = muon_index;
+  h->thermal_ok = dims[muon_index] == 2;
   for (int i = 0; i < n_spins; ++i) {
     h->tab.dims[i] = dims[i];
     h->tab.gammas[i] = gammas[i];
+    if (dims[i] > MUSIM_MAX_SDIM) h->thermal_ok = false;  // thermal rho0 needs real spins (2I+1 <= 10)
   }
   h->n_diss = n_diss;
   for (int i = 0; i < n_diss; ++i) {
@@ -328,6 +331,8 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   const bool lind = (mode == MUSIM_MODE_LINDBLAD || mode == MUSIM_MODE_LINDBLAD_INT);
   const bool general = (mode != MUSIM_MODE_FAST && mode != MUSIM_MODE_INTEGRAL_FAST);
   if (general && !T && !h->rho0_explicit) return set_err(h, MUSIM_EINVAL, "temperature array required");
+  if (general && !h->rho0_explicit && !h->thermal_ok)
+    return set_err(h, MUSIM_EINVAL, "thermal rho0 needs a muon (dimension 2) and spins with 2I+1 <= 10; pass rho0");
   if (integral) {
     if (!(tau > 0.0)) return set_err(h, MUSIM_EINVAL, "'tau' must be a real number > 0");
     nt = 1;

@@ -1,0 +1,87 @@
+"""Batched eigensolvers (musim_eigh through the C ABI) against numpy.linalg.eigh.
+Eigenvectors are never compared directly (degeneracy): residual ||A U - U diag(l)||,
+orthonormality and eigenvalues are."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _eigh(A, method):
+    import torch
+
+    from muspinsim_b200 import _lib
+
+    A = np.ascontiguousarray(A, dtype=np.complex128)
+    b, d, _ = A.shape
+    At = torch.from_numpy(A).cuda()
+    ev = torch.zeros(b, d, dtype=torch.float64, device="cuda")
+    U = torch.zeros(b, d, d, dtype=torch.complex128, device="cuda")
+    _lib.eigh_device(0, d, b, At.data_ptr(), ev.data_ptr(), U.data_ptr(), method)
+    torch.cuda.synchronize()
+    return ev.cpu().numpy(), U.cpu().numpy()
+
+
+def _check(A, method, tol=5e-13):
+    ev, U = _eigh(A, method)
+    d = A.shape[-1]
+    ref = np.linalg.eigvalsh(A)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.all(np.diff(ev, axis=1) >= 0), "eigenvalues must be ascending"
+    assert np.abs(ev - ref).max() / scale < tol
+    assert np.abs(A @ U - U * ev[:, None, :]).max() / scale < tol
+    assert np.abs(np.conj(np.transpose(U, (0, 2, 1))) @ U - np.eye(d)).max() < tol
+
+
+def _rand_herm(rng, b, d):
+    A = rng.normal(size=(b, d, d)) + 1j * rng.normal(size=(b, d, d))
+    return np.ascontiguousarray(A + np.conj(np.transpose(A, (0, 2, 1))))
+
+
+@pytest.mark.parametrize("method", [1, 2])
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 7, 8, 12, 16, 17, 24, 31, 32, 33, 48, 64, 83, 96])
+def test_random_hermitian(method, d):
+    if method == 1 and d > 96:
+        pytest.skip("Jacobi limited by shared memory")
+    rng = np.random.default_rng(d)
+    _check(_rand_herm(rng, 24 if d < 64 else 6, d), method)
+
+
+@pytest.mark.parametrize("method", [1, 2])
+@pytest.mark.parametrize("d", [4, 12, 32, 96])
+def test_degenerate_and_structured(method, d):
+    rng = np.random.default_rng(100 + d)
+    mats = []
+    q, _ = np.linalg.qr(_rand_herm(rng, 1, d)[0])
+    lam = (np.arange(d) // 4).astype(float)  # 4-fold degenerate levels
+    mats.append((q * lam) @ q.conj().T)
+    mats.append(np.zeros((d, d), dtype=complex))  # zero matrix (empty spin system)
+    mats.append(np.eye(d, dtype=complex) * 3.0)  # multiple of identity
+    mats.append(np.diag(rng.normal(size=d)).astype(complex))  # already diagonal
+    T = np.diag(rng.normal(size=d)).astype(complex)  # real tridiagonal
+    T += np.diag(np.ones(d - 1), 1) + np.diag(np.ones(d - 1), -1)
+    mats.append(T)
+    big = _rand_herm(rng, 1, d)[0] * 7e4  # ALC-scale norm (gamma_e * 2.6 T)
+    mats.append(big)
+    A = np.array([0.5 * (m + m.conj().T) for m in mats])
+    _check(A, method)
+
+
+@pytest.mark.parametrize("method", [1, 2])
+def test_physical_hamiltonians(method):
+    from muspinsim_b200 import workloads
+    from muspinsim_b200.spinsys import system_from_spec
+
+    for spec in (workloads.c5_large(2, 2), workloads.c3_alc(2, 2), workloads.c2_hfine_powder(2, 2)):
+        s, _ = system_from_spec(spec)
+        Z = s.zeeman_operators()
+        rng = np.random.default_rng(5)
+        A = np.array([s.hamiltonian + np.tensordot(rng.normal(size=3) * 2.0, Z, 1) for _ in range(4)])
+        A[0] = s.hamiltonian  # zero field: massively degenerate
+        _check(A, method)
+
+
+def test_large_batch_all_matrices_processed():
+    rng = np.random.default_rng(9)
+    A = _rand_herm(rng, 3000, 12)
+    _check(A, 2)

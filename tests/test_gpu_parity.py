@@ -1,0 +1,111 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the golden vectors
+generated from the unmodified reference.  Tolerance: 1e-9 absolute on the polarisation
+(BASELINE.json north_star), FP64."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _run(spec, **opts):
+    from muspinsim_b200 import ExperimentRunner
+
+    r = ExperimentRunner(spec, device=0)
+    for k, v in opts.items():
+        r.set_option(k, v)
+    return r.run(), r
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name):
+    spec, want = load_golden(name)
+    got, _ = _run(spec)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) < TOL
+
+
+@pytest.mark.parametrize("opts", [{"polar": 1}, {"eigh": 1}, {"eigh": 2, "polar": 2}, {"chunk": 3}])
+@pytest.mark.parametrize("name", ["c2_fast_d16", "c2_general_d8_T0p3", "c3_alc_d12", "c5_fast_d96",
+                                  "polarization_filerange", "ground_state_T0"])
+def test_golden_all_kernel_variants(name, opts):
+    spec, want = load_golden(name)
+    got, _ = _run(spec, **opts)
+    assert np.max(np.abs(got - want)) < TOL
+
+
+def test_nonuniform_times_take_direct_path_and_match():
+    spec, want = load_golden("nonuniform_times")
+    got, _ = _run(spec)
+    assert np.max(np.abs(got - want)) < TOL
+    with pytest.raises(ValueError):
+        _run(spec, polar=2)  # the factorised kernel refuses non-uniform grids
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_seeded_against_oracle(seed):
+    """Fresh seeded inputs (not in the golden set) against the oracle."""
+    from muspinsim_b200 import workloads
+    from oracle import muspin_oracle as mo
+
+    rng = np.random.default_rng(seed)
+    nt = int(rng.integers(1, 300))
+    spec = workloads.c2_hfine_powder(n_orient=int(rng.integers(1, 40)), nt=nt, n_h=int(rng.integers(0, 3)),
+                                     temperature=[np.inf, 0.5, 20.0, 0.0][seed], seed=100 + seed)
+    spec["field"] = [[0.001 * seed, 0.0, 0.02]]
+    want = mo.run_spec(spec, evolve_fn=mo.evolve_vectorised)
+    got, _ = _run(spec)
+    assert np.max(np.abs(got - want)) < TOL
+
+
+def test_edge_cases():
+    from oracle import muspin_oracle as mo
+
+    t = np.linspace(0, 10, 100)
+    # empty system: constant 0.5 (tests/test_experiment.py:117-133)
+    got, _ = _run({"spins": ["e", "mu"], "time": t})
+    assert np.max(np.abs(got - 0.5)) < 1e-14
+    # single spin, single time point ... and 1025 time points (two a-blocks in the factorised kernel)
+    zee = [{"type": "zeeman", "i": 2, "value": [0, 0, 1.0 / mo.MU_GAMMA]}]
+    for n in (2, 33, 1025, 2500):
+        tt = np.linspace(0, 10, n)
+        got, _ = _run({"spins": ["e", "mu"], "time": tt, "couplings": zee})
+        assert np.max(np.abs(got - 0.5 * np.cos(2 * np.pi * tt))) < TOL
+    # integral known answer (tests/test_experiment.py:135-202)
+    got, _ = _run({"spins": ["e", "mu"], "couplings": zee, "y_axis": "integral", "x_axis": "field",
+                   "field": [[0.0], [1.0]]})
+    assert abs(got[0] - 0.5 / (1.0 + 4 * np.pi**2 * mo.MU_TAU**2)) < 1e-12
+
+
+def test_device_pointer_entry_matches_host_entry():
+    import torch
+
+    from muspinsim_b200 import ExperimentRunner, _lib
+    from muspinsim_b200.constants import MU_TAU
+
+    spec, want = load_golden("c2_fast_d16")
+    r = ExperimentRunner(spec, device=0)
+    tab = r.config
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(getattr(tab, k))).to(dev) for k in ("B", "p", "T", "w")}
+    slot = torch.from_numpy(tab.slot).to(dev)
+    out = torch.zeros(tab.n_slots, len(tab.times), dtype=torch.float64, device=dev)
+    r.handle.run_device(_lib.MODE_FAST, tab.n_cfg, t["B"].data_ptr(), t["p"].data_ptr(), t["T"].data_ptr(),
+                        t["w"].data_ptr(), slot.data_ptr(), tab.times, MU_TAU, tab.n_slots, out.data_ptr(),
+                        torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.max(np.abs(tab.finish(out.cpu().numpy()) - want)) < TOL
+    assert r.handle.launches > 0
+
+
+def test_accumulate_semantics_and_rank_shards():
+    """out is accumulated into (+=); the round-robin shards of two ranks sum to the total."""
+    from muspinsim_b200 import ExperimentRunner
+
+    spec, want = load_golden("c2_fast_d16")
+    r = ExperimentRunner(spec, device=0)
+    a = r.run_partial(0, 2)
+    b = r.run_partial(1, 2)
+    assert np.max(np.abs(r.config.finish(a + b) - want)) < TOL

@@ -1,0 +1,132 @@
+"""Host-side logic without a GPU: spin system builder, vectorised configuration table,
+mode selection and result layout of ExperimentRunner, checked against the oracle / golden
+vectors with the CPU stand-in handle of tests/helpers.py."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from helpers import OracleHandle
+from muspinsim_b200 import ExperimentRunner, MuonSpinSystem, _lib, configs
+from muspinsim_b200.spinsys import spin_operators, system_from_spec
+from oracle import muspin_oracle as mo
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_runner_host_logic_matches_golden(name):
+    spec, want = load_golden(name)
+    r = ExperimentRunner(spec)
+    r._handle = OracleHandle(spec)
+    got = r.run()
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["c2_fast_d16", "c5_fast_d96", "c3_alc_d24", "ground_state_T0", "c4_dissip_tf"])
+def test_system_operators_match_oracle(name):
+    spec, _ = load_golden(name)
+    a = mo.build_system(spec)
+    b, dis = system_from_spec(spec)
+    assert np.allclose(a.H0, b.hamiltonian, atol=1e-12, rtol=0)
+    v = np.array([0.3, -0.2, 0.9])
+    assert np.allclose(a.muon_operator(v), b.muon_operator(v), atol=1e-15)
+    assert np.allclose(mo.zeeman_matrix(a, v), np.tensordot(v, b.zeeman_operators(), 1), atol=1e-9, rtol=1e-15)
+    assert np.allclose(a.sigma_mu(v), b.sigma_mu(v))
+    assert dict(a.dissipation) == dis
+
+
+def test_spin_operator_algebra():
+    for I in (0.5, 1.0, 1.5, 3.5):
+        sx, sy, sz = spin_operators(I)
+        assert np.allclose(sx @ sy - sy @ sx, 1j * sz)
+        assert np.allclose(sx @ sx + sy @ sy + sz @ sz, I * (I + 1) * np.eye(int(2 * I + 1)))
+        ox, oy, oz = mo.spin_matrices(I)
+        assert np.allclose(sx, ox) and np.allclose(sy, oy) and np.allclose(sz, oz)
+
+
+def test_spinsys_errors_mirror_reference():
+    with pytest.raises(ValueError):
+        MuonSpinSystem(["e", "e"])  # exactly one muon (spinsys.py:646-649)
+    s = MuonSpinSystem(["mu", "e", "e"])
+    with pytest.raises(ValueError):
+        s.add_hyperfine_term(0, np.eye(3))  # must name the electron (spinsys.py:684-689)
+    with pytest.raises(ValueError):
+        s.add_hyperfine_term(1, np.eye(3), 2)  # first index must not be an electron
+    with pytest.raises(ValueError):
+        s.add_dipolar_term(0, 0, [0, 0, 1])
+    with pytest.raises(ValueError):
+        s.add_quadrupolar_term(0, np.eye(3))  # spin 1/2
+    with pytest.raises(ValueError):
+        s.muon_operator([1, 0])
+    with pytest.raises(ValueError):
+        s.add_linear_term(5, [0, 0, 1])
+
+
+def test_quaternion_conventions():
+    # tests/test_config.py:231-233 and tests/test_utils.py:43-65 of the reference
+    q, w = configs.orientation_table([[0.0, 0, 0, 1.0], [0.5 * np.pi, 0, 0, 2.0]])
+    assert np.allclose(q[1], [2**-0.5, 0, 0, -(2**-0.5)]) and np.allclose(w, [1, 2])
+    theta, phi = 0.6 * np.pi, 0.4 * np.pi
+    qc, _ = configs.orientation_table([[theta, phi]])
+    st, ct, sp, cp = np.sin(theta), np.cos(theta), np.sin(phi), np.cos(phi)
+    R = configs.quat_rotation_matrices(qc)[0]
+    assert np.allclose(R @ [0, 0, 1], [-st * cp, st * sp, ct])
+    rng = np.random.default_rng(0)
+    rows = rng.uniform(0, np.pi, size=(20, 3))
+    for mode in ("zyz", "zxz"):
+        qq, _ = configs.orientation_table(rows, mode)
+        for k in range(20):
+            q1, _ = mo.orientation_row(rows[k], mode)
+            assert np.allclose(qq[k], q1, atol=1e-15)
+    assert np.allclose(configs.eulrange(4), mo.eulrange(4))
+
+
+def test_config_table_matches_oracle_enumeration():
+    for name in ("alc_T_filerange", "intrinsic_scan_zxz", "time_averaged_vs_field", "polarization_filerange"):
+        spec, want = load_golden(name)
+        tab = configs.ConfigTable(spec)
+        oc = mo.OracleConfig(spec)
+        assert tab.n_cfg == len(oc.configurations)
+        assert tab.results_shape == oc.results.shape
+        assert tab.avg_N == oc.avg_N
+        for idx in range(tab.n_cfg):
+            snap = oc.snapshot(idx)
+            q, w = snap["orient"]
+            R = mo.quat_rotmat(q)
+            B = R @ np.asarray(snap["B"]) + np.asarray(snap["intrinsic_B"])
+            assert np.allclose(tab.B[idx], B, atol=1e-15)
+            assert np.allclose(tab.p[idx], R @ np.asarray(snap["mupol"]), atol=1e-15)
+            assert tab.T[idx] == snap["T"]
+            assert np.isclose(tab.w[idx], w / oc.avg_N)
+
+
+def test_config_errors():
+    with pytest.raises(ValueError):
+        configs.ConfigTable({"y_axis": "integral"})  # time as x axis with integral (simconfig.py:173-178)
+    with pytest.raises(ValueError):
+        configs.ConfigTable({"x_axis": "field"})  # x axis is not a range (simconfig.py:236-238)
+    with pytest.raises(ValueError):
+        configs.ConfigTable({"orientation": [[1.0]]})
+    with pytest.raises(ValueError):
+        configs.ConfigTable({"field": [[1.0, 2.0]]})
+
+
+def test_weights_normalised_only_when_averaged():
+    spec = {"orientation": [[0, 0, 0, 1.0], [1, 1, 1, 3.0]]}
+    t = configs.ConfigTable(spec)
+    assert np.allclose(t.w * t.avg_N, [0.5, 1.5])  # sum to N (simconfig.py:152-156)
+    t = configs.ConfigTable(dict(spec, average_axes=["none"]))
+    assert np.allclose(t.w, 1.0) and t.results_shape == (2, 101)
+
+
+def test_fast_predicate():
+    t = configs.ConfigTable({"temperature": [np.inf, 1.0], "field": [[0, 0, 0.1]], "average_axes": ["none"]})
+    assert list(t.fast) == [True, False]
+    t = configs.ConfigTable({"temperature": [1.0], "field": [[0, 0, 0.0]]})
+    assert list(t.fast) == [True]  # B = 0 (experiment.py:413-418)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.MusimError):
+        _lib.load()
