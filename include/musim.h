@@ -75,6 +75,12 @@ int musim_update_system(musim_handle *h, const double *H0, const double *Z);
  * restores the thermal construction. */
 int musim_set_rho0(musim_handle *h, const double *rho0);
 
+/* Explicit, configuration-independent dissipators for the Lindbladian modes: n operators
+ * A[n,d,d] (complex, HOST) with rates gamma[n], added to the field/temperature dependent ones
+ * built from `diss_spin`.  This is the per-call boundary Lindbladian.from_hamiltonian(H,
+ * dissipators=[(A, gamma), ...]) (lindbladian.py:18-41).  n = 0 clears them. */
+int musim_set_dissipators(musim_handle *h, int n, const double *A, const double *gamma);
+
 /* Tunables: "eigh" (0 auto, 1 Jacobi, 2 Householder+QL), "polar" (0 auto, 1 direct sincos,
  * 2 time-factorised), "chunk" (configurations per launch group, 0 auto). */
 int musim_set_option(musim_handle *h, const char *key, long value);

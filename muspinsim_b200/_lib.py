@@ -22,6 +22,7 @@ EXPORTS = [
     "musim_create",
     "musim_update_system",
     "musim_set_rho0",
+    "musim_set_dissipators",
     "musim_set_option",
     "musim_run",
     "musim_run_host",
@@ -60,6 +61,8 @@ def load():
     lib.musim_update_system.restype = i32
     lib.musim_set_rho0.argtypes = [vp, vp]
     lib.musim_set_rho0.restype = i32
+    lib.musim_set_dissipators.argtypes = [vp, i32, vp, vp]
+    lib.musim_set_dissipators.restype = i32
     lib.musim_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_long]
     lib.musim_set_option.restype = i32
     lib.musim_run.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32, vp, dbl, i32, vp, vp]
@@ -151,6 +154,17 @@ class Handle:
             if r.shape != (self.d, self.d):
                 raise ValueError("rho0 must be (d,d)")
             self._check(self._lib.musim_set_rho0(self._h, _ptr(r)))
+
+    def set_dissipators(self, ops, rates):
+        """Explicit jump operators [(d,d) complex] with rates (Lindbladian.from_hamiltonian)."""
+        if len(ops) == 0:
+            self._check(self._lib.musim_set_dissipators(self._h, 0, None, None))
+            return
+        A = _c128(np.array([np.asarray(o) for o in ops]))
+        g = _f64(rates)
+        if A.shape != (len(g), self.d, self.d):
+            raise ValueError("Invalid dissipation operator for this Lindbladian")
+        self._check(self._lib.musim_set_dissipators(self._h, len(g), _ptr(A), _ptr(g)))
 
     def update_system(self, H0=None, Z=None):
         H0 = _c128(H0) if H0 is not None else None

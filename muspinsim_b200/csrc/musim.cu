@@ -49,8 +49,10 @@ struct musim_handle {
   double *lam = nullptr;
   cplx *U = nullptr, *T1 = nullptr, *Y = nullptr, *X = nullptr, *W = nullptr, *Oc = nullptr;
   EighWs ews;
-  void *lws = nullptr;  // Lindblad workspace
-  size_t lws_bytes = 0;
+  LindWs lws;
+  cplx *exA = nullptr;
+  double *exg = nullptr;
+  int n_explicit = 0;
   int *status = nullptr;
   // host-run staging
   void *stage = nullptr;
@@ -213,6 +215,24 @@ extern "C" int musim_set_rho0(musim_handle *h, const double *rho0) {
   return MUSIM_OK;
 }
 
+extern "C" int musim_set_dissipators(musim_handle *h, int n, const double *A, const double *gamma) {
+  if (!h || n < 0 || (n > 0 && (!A || !gamma))) return MUSIM_EINVAL;
+  CK(cudaSetDevice(h->device));
+  cudaFree(h->exA);
+  cudaFree(h->exg);
+  h->exA = nullptr;
+  h->exg = nullptr;
+  h->n_explicit = 0;
+  if (n == 0) return MUSIM_OK;
+  const size_t dd = (size_t)h->d * h->d;
+  CK(dev_alloc(&h->exA, n * dd));
+  CK(dev_alloc(&h->exg, (size_t)n));
+  CK(cudaMemcpy(h->exA, A, n * dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->exg, gamma, n * sizeof(double), cudaMemcpyHostToDevice));
+  h->n_explicit = n;
+  return MUSIM_OK;
+}
+
 extern "C" int musim_destroy(musim_handle *h) {
   if (!h) return MUSIM_OK;
   cudaSetDevice(h->device);
@@ -226,7 +246,9 @@ extern "C" int musim_destroy(musim_handle *h) {
   cudaFree(h->times_dev);
   cudaFree(h->status);
   cudaFree(h->stage);
-  cudaFree(h->lws);
+  h->lws.release();
+  cudaFree(h->exA);
+  cudaFree(h->exg);
   h->prof.destroy();
   delete h;
   return MUSIM_OK;
@@ -313,7 +335,7 @@ template <bool CONJ_A, int EPI>
 static void launch_gemm(int d, int64_t n, const cplx *A, size_t as, const cplx *B, size_t bs, cplx *C,
                         double scale, cudaStream_t st, int64_t *launches) {
   dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);
-  cgemm_batched_kernel<CONJ_A, EPI><<<grid, 256, 0, st>>>(d, A, as, B, bs, C, scale);
+  cgemm_batched_kernel<CONJ_A, EPI><<<grid, 256, 0, st>>>(d, A, as, B, bs, C, scale, nullptr);
   ++*launches;
 }
 
@@ -357,10 +379,26 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   }
 
   if (lind) {
-    int rc = lindblad_run(h->d, h->tab, h->n_diss, h->diss_spin.data(), h->diss_rate.data(), h->H0,
-                          h->Z, h->M, h->rho0_explicit, integral, n_cfg, B, p, T, w, slot, nt,
-                          h->times_dev, tg.uniform, tg.t0, tg.dt, tau, out, &h->lws, &h->lws_bytes,
-                          h->opt_chunk, st, &h->launches, h->err);
+    LindCtx ctx;
+    ctx.P.d = d;
+    ctx.P.tab = h->tab;
+    ctx.P.n_diss = h->n_diss;
+    for (int i = 0; i < h->n_diss; ++i) {
+      ctx.P.diss_spin[i] = h->diss_spin[i];
+      ctx.P.diss_rate[i] = h->diss_rate[i];
+    }
+    ctx.P.n_explicit = h->n_explicit;
+    ctx.H0 = h->H0;
+    ctx.Z = h->Z;
+    ctx.M = h->M;
+    ctx.rho0_explicit = h->rho0_explicit;
+    ctx.exA = h->exA;
+    ctx.exg = h->exg;
+    if (!h->rho0_explicit && !h->thermal_ok)
+      return set_err(h, MUSIM_EINVAL, "thermal rho0 needs a muon (dimension 2) and spins with 2I+1 <= 10; pass rho0");
+    CK(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
+    int rc = lindblad_run(ctx, integral, n_cfg, B, p, T, w, slot, nt, tg.uniform, tg.t0, tg.dt, tau, out, h->lws,
+                          h->opt_chunk, h->status, st, &h->launches, &h->prof, h->err);
     return rc;
   }
 

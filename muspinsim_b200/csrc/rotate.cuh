@@ -174,13 +174,14 @@ __global__ void rho0_kernel(int d, SpinTable tab, const double *__restrict__ Bf,
 // Batched complex GEMM, C[c] = op(A[c]) * B[c] (all d x d, row-major).  CONJ_A: op = A^H.
 // 32x32 output tile per CTA (256 threads, 2x2 complex outputs each), K staged through
 // shared memory in slabs of 16.  a_stride / b_stride may be 0 (operand shared by the batch).
-// EPI: 0 store C; 1 store (|C|^2 * scale, 0)   [fast-path weights |O'|^2 / d_o]
+// EPI: 0 store C; 1 store (|C|^2 * scale, 0)   [fast-path weights |O'|^2 / d_o];
+//      2 store C + D (D may alias C)           [Horner steps of the matrix exponential]
 // ---------------------------------------------------------------------------------------
 template <bool CONJ_A, int EPI>
 __global__ void __launch_bounds__(256)
 cgemm_batched_kernel(int d, const cplx *__restrict__ A, size_t a_stride,
-                     const cplx *__restrict__ B, size_t b_stride, cplx *__restrict__ C,
-                     double scale) {
+                     const cplx *__restrict__ B, size_t b_stride, cplx *C, double scale,
+                     const cplx *D) {
   constexpr int TM = 32, TN = 32, TK = 16;
   __shared__ cplx sA[TK][TM + 1];  // sA[k][m] = op(A)(m0+m, k0+k)
   __shared__ cplx sB[TK][TN + 1];  // sB[k][n] = B(k0+k, n0+n)
@@ -240,6 +241,7 @@ cgemm_batched_kernel(int d, const cplx *__restrict__ A, size_t a_stride,
       if (m < d && n < d) {
         cplx v = acc[i][j];
         if (EPI == 1) v = make_c(cnorm2(v) * scale, 0.0);
+        if (EPI == 2) v = cadd(v, D[cfg * dd + (size_t)m * d + n]);
         C[cfg * dd + (size_t)m * d + n] = v;
       }
     }

@@ -1,0 +1,82 @@
+"""Per-call boundary for open-system dynamics: `Lindbladian` with the reference's signatures
+(/root/reference/muspinsim/lindbladian.py:17-173), computed on the GPU without an
+eigen-decomposition of the super-operator (see csrc/lindblad.cuh)."""
+
+from numbers import Number
+
+import numpy as np
+
+from . import _lib
+from .hamiltonian import Hamiltonian, _dense, validate_times
+
+
+class Lindbladian:
+    def __init__(self, H, dissipators=(), device=0):
+        self._H = H
+        self._dops = [(_dense(A), float(g)) for A, g in dissipators]
+        self._device = device
+
+    @classmethod
+    def from_hamiltonian(cls, H, dissipators=()):
+        """lindbladian.py:18-33."""
+        if not isinstance(H, Hamiltonian):
+            raise ValueError("Must use Hamiltonian to create Lindbladian")
+        L = cls(H, [], H._device)
+        for A, gamma in dissipators:
+            L.add_dissipative_term(A, gamma)
+        return L
+
+    def add_dissipative_term(self, A, gamma=1.0):
+        """lindbladian.py:35-41."""
+        A = _dense(A)
+        if A.shape != self._H.matrix.shape:
+            raise ValueError("Invalid dissipation operator for this Lindbladian")
+        self._dops.append((A, float(gamma)))
+
+    @property
+    def dimension(self):
+        return self._H.dimension * 2
+
+    def _run(self, mode, rho0, times, tau, op):
+        d = self._H.matrix.shape[0]
+        zeros = np.zeros((3, d, d), dtype=complex)
+        M = zeros.copy()
+        M[0] = _dense(op)
+        h = _lib.Handle(self._device, [d], [0.0], 0, self._H.matrix, zeros, M)
+        try:
+            h.set_rho0(rho0)
+            h.set_dissipators([a for a, _ in self._dops], [g for _, g in self._dops])
+            nt = len(times) if times is not None else 1
+            out = np.zeros((1, nt))
+            h.run_host(mode, np.zeros((1, 3)), np.array([[1.0, 0.0, 0.0]]), np.array([np.inf]), np.array([1.0]),
+                       np.array([0]), times, tau, out)
+            return out[0]
+        finally:
+            h.close()
+
+    def evolve(self, rho0, times, operators=()):
+        """lindbladian.py:43-111: expectation values [nt, n_ops]."""
+        times = np.array(times)
+        if not isinstance(operators, (list, tuple)):
+            operators = [operators]
+        validate_times(times)
+        r = _dense(rho0)
+        if r.shape != self._H.matrix.shape:
+            raise ValueError("Incompatible rho0 dimension")
+        if any(_dense(o).shape != r.shape for o in operators):
+            raise ValueError("Incompatible measure operator dimension")
+        if len(operators) == 0:
+            raise NotImplementedError("density-matrix output (operators=[]) is outside the hot path")
+        cols = [self._run(_lib.MODE_LINDBLAD, r, times.astype(float), 1.0, o) for o in operators]
+        return np.array(cols).T.astype(complex)
+
+    def integrate_decaying(self, rho0, tau, operators):
+        """lindbladian.py:113-173."""
+        if not isinstance(operators, (list, tuple)):
+            operators = [operators]
+        if not (isinstance(tau, Number) and np.isreal(tau) and tau > 0):
+            raise ValueError("'tau' must be a real number > 0")
+        if not operators:
+            raise ValueError("At least one SpinOperator must be present in 'operators'")
+        r = _dense(rho0)
+        return np.array([self._run(_lib.MODE_LINDBLAD_INT, r, None, float(tau), o)[0] * tau for o in operators]).astype(complex)

@@ -63,3 +63,37 @@ def test_validation_errors():
         H.integrate_decaying(rho0, 1.0, [])
     with pytest.raises(ValueError):
         H.evolve(np.eye(3), np.linspace(0, 1, 3), [sz])  # incompatible rho0
+
+
+def test_lindbladian_closed_forms():
+    """tests/test_lindbladian.py:40-80 and :130-159 of the reference, through the GPU path."""
+    from muspinsim_b200.hamiltonian import Hamiltonian
+    from muspinsim_b200.lindbladian import Lindbladian
+    from muspinsim_b200.spinsys import spin_operators
+
+    sx, sy, sz = spin_operators(0.5)
+    sp, sm = sx + 1j * sy, sx - 1j * sy
+    H = Hamiltonian(sz)
+    rho0 = 0.5 * np.eye(2) + sx
+    t = np.linspace(0, 1, 100)
+    L = Lindbladian.from_hamiltonian(H)
+    assert np.allclose(L.evolve(rho0, t, sx)[:, 0], 0.5 * np.cos(2 * np.pi * t), atol=1e-11)
+    tau = 2.0
+    assert abs(L.integrate_decaying(rho0, tau, sx)[0] - 0.5 * tau / (1 + 4 * np.pi**2 * tau**2)) < 1e-12
+    for g in [1.0, 2.0, 5.0, 10.0]:
+        L = Lindbladian.from_hamiltonian(H, [(sx, g)])
+        ap = -0.5 * np.pi * g + ((0.5 * np.pi * g) ** 2 - 4 * np.pi**2 + 0j) ** 0.5
+        am = -0.5 * np.pi * g - ((0.5 * np.pi * g) ** 2 - 4 * np.pi**2 + 0j) ** 0.5
+        A = ap * am / (am - ap)
+        solx = np.real(0.5 * A * (np.exp(ap * t) / ap - np.exp(am * t) / am))
+        assert np.allclose(L.evolve(rho0, t, sx)[:, 0], solx, atol=1e-10)
+        sol = np.real(0.5 * A * tau * (1 / ((1 - ap * tau) * ap) - 1 / ((1 - am * tau) * am)))
+        assert abs(L.integrate_decaying(rho0, tau, sx)[0] - sol) < 1e-11
+        L = Lindbladian.from_hamiltonian(H, [(sp, 1.5 * g), (sm, 0.5 * g)])
+        ev = L.evolve(rho0, t, [sx, sz])
+        assert np.allclose(ev[:, 0], 0.5 * np.cos(2 * np.pi * t) * np.exp(-2 * np.pi * g * t), atol=1e-10)
+        assert np.allclose(ev[:, 1], 0.25 * (1 - np.exp(-4 * np.pi * g * t)), atol=1e-10)
+    with pytest.raises(ValueError):
+        Lindbladian.from_hamiltonian(sz)
+    with pytest.raises(ValueError):
+        L.evolve(np.eye(3), t, sx)
