@@ -1,0 +1,96 @@
+"""Drop-in adapter: run the reference's own `ExperimentRunner` objects on the GPU path.
+
+`runner_from_reference(ref_runner)` reads the (already parsed and validated) system and
+configuration ranges out of a reference `muspinsim.ExperimentRunner` and returns the
+equivalent `muspinsim_b200.ExperimentRunner`; `patch_reference()` replaces
+`muspinsim.ExperimentRunner.run` so that the CLI, `FittingRunner` and library users call the GPU
+path unchanged.  Nothing here imports the reference: it only duck-types the
+objects it is handed.
+"""
+
+import numpy as np
+
+from .configs import ConfigTable
+from .experiment import ExperimentRunner
+from .spinsys import MuonSpinSystem
+
+
+class _ReferenceSystemView(MuonSpinSystem):
+    """MuonSpinSystem whose operators are taken from a reference MuonSpinSystem."""
+
+    def __init__(self, ref_runner):
+        sysr = ref_runner.system
+        self._spins = list(sysr.spins)
+        self._gammas = np.array(sysr.gammas, dtype=float)
+        self._Qs = np.array(sysr.Qs, dtype=float)
+        self._Is = np.array(sysr.Is, dtype=float)
+        self._dim = tuple(int(x) for x in sysr.dimension)
+        self._mu_i = int(sysr.muon_index)
+        self._e_i = set(sysr.elec_indices)
+        self._terms = []
+        H = ref_runner.Hsys.matrix  # spinsys.py:613-626 via experiment.py:119
+        self._H = np.asarray(H.toarray() if hasattr(H, "toarray") else H, dtype=complex)
+        self._ref = sysr
+        from .spinsys import spin_operators
+
+        self._local = [spin_operators(I) for I in self._Is]
+
+
+def system_from_reference(ref_runner):
+    return _ReferenceSystemView(ref_runner)
+
+
+def table_from_reference(cfg):
+    """MuSpinConfig (simconfig.py:82-321) -> ConfigTable, reusing its classified ranges."""
+    def get(name):
+        for od in (cfg._file_ranges, cfg._avg_ranges, cfg._x_range):
+            if name in od and od[name] is not None:
+                return list(od[name])
+        return [cfg._constants[name]]
+
+    orient = get("orient")
+    vals = {
+        "mupol": np.array(get("mupol"), dtype=float).reshape(-1, 3),
+        "B": np.array(get("B"), dtype=float).reshape(-1, 3),
+        "intrinsic_B": np.array(get("intrinsic_B"), dtype=float).reshape(-1, 3),
+        "t": np.array(get("t"), dtype=float).reshape(-1),
+        "orient": np.array([np.asarray(q.q, dtype=float) for (q, w) in orient]),
+        "T": np.array(get("T"), dtype=float).reshape(-1),
+    }
+    ow = np.array([w for (q, w) in orient], dtype=float)  # already normalised (simconfig.py:152-159)
+    x_name = list(cfg._x_range.keys())[0]
+    avg = list(cfg._avg_ranges.keys()) + (["t"] if cfg._time_isavg and "t" not in cfg._avg_ranges else [])
+    return ConfigTable.from_values(vals, ow, x_name, avg, cfg._y_axis)
+
+
+def runner_from_reference(ref_runner, device=None, comm=None):
+    if getattr(ref_runner.config, "celio_k", 0):
+        raise NotImplementedError("Celio's method stays on the reference path")
+    dissip = {int(i): float(a) for i, a in ref_runner.config.dissipation_terms.items()}
+    return ExperimentRunner(system=system_from_reference(ref_runner), table=table_from_reference(ref_runner.config),
+                            dissipation=dissip, device=device, comm=comm)
+
+
+def run_reference_runner(ref_runner, device=None, comm=None):
+    """What the patched `ExperimentRunner.run` does: GPU evaluation, then the reference's own
+    post-processing (experiment.py:373-382)."""
+    results = runner_from_reference(ref_runner, device, comm).run()
+    if not ref_runner._variables:
+        results = ref_runner.apply_results_function(results, {})
+    ref_runner._config.results = results
+    return results
+
+
+def patch_reference():
+    """Monkey-patch muspinsim.ExperimentRunner.run (experiment.py:358-382) with the GPU path."""
+    import muspinsim.experiment as mexp
+
+    original = mexp.ExperimentRunner.run
+
+    def run(self):
+        if getattr(self.config, "celio_k", 0):
+            return original(self)
+        return run_reference_runner(self)
+
+    mexp.ExperimentRunner.run = run
+    return original

@@ -179,7 +179,23 @@ class ConfigTable:
             ow = np.ones(len(ow))
         vals["orient"] = q
         vals["T"] = np.asarray(s["temperature"], dtype=float).reshape(-1)
+        self._build(vals, ow, xname, avg)
 
+    @classmethod
+    def from_values(cls, vals, orient_weights, x_name, avg_names, y_axis):
+        """Build from already validated values: vals = {"mupol": [n,3] unit vectors, "B": [n,3],
+        "intrinsic_B": [n,3], "t": [nt], "orient": [n,4] conjugate quaternions, "T": [n]},
+        weights already normalised (used by adapter.table_from_reference)."""
+        self = cls.__new__(cls)
+        self.spec = None
+        self.y = y_axis
+        self._build({k: np.asarray(v, dtype=float) for k, v in vals.items()}, np.asarray(orient_weights, float),
+                    x_name, list(avg_names))
+        return self
+
+    def _build(self, vals, ow, xname, avg):
+        q = vals["orient"]
+        t = vals["t"]
         # classify ranges in the reference's keyword order
         self.x_name = xname
         self.file_ranges, self.avg_ranges = OrderedDict(), OrderedDict()

@@ -130,3 +130,25 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.MusimError):
         _lib.load()
+
+
+@pytest.mark.parametrize("name", ["c2_fast_d16", "alc_T_filerange", "time_averaged_vs_field", "c4_dissip_tf",
+                                  "polarization_filerange", "hfine_powder_eulrange3"])
+def test_adapter_from_reference_runner(name):
+    """The drop-in adapter on the reference's own parsed objects (needs oracle/_ref: build
+    container only; skipped where the reference install did not travel)."""
+    from oracle import ref_driver
+
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref not present")
+    from muspinsim_b200 import adapter
+
+    spec, want = load_golden(name)
+    ref_runner = ref_driver.make_runner(spec)
+    r = adapter.runner_from_reference(ref_runner)
+    r._handle = OracleHandle(spec)
+    got = r.run()
+    assert got.shape == want.shape and np.max(np.abs(got - want)) < 1e-10
+    ours = system_from_spec(spec)[0]
+    assert np.allclose(r.system.hamiltonian, ours.hamiltonian, atol=1e-12)
+    assert np.allclose(r.system.zeeman_operators(), ours.zeeman_operators(), atol=1e-9, rtol=1e-15)
