@@ -36,7 +36,7 @@ struct EighWs {
     const size_t dd = (size_t)d * d;
     if (method == EIGH_HQL)
       return 2 * d * sizeof(double) + dd * sizeof(cplx) + dd * sizeof(double) +
-             (3 * dd + 64) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
+             (2 * dd + 64) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
              d * sizeof(unsigned short);
     return jacobi_vglobal(d) ? (size_t)d * (d | 1) * sizeof(cplx) : 0;
   }
@@ -71,7 +71,7 @@ struct EighWs {
 #define EW_ALLOC(ptr, count)                                              \
   if (e == cudaSuccess) e = cudaMalloc((void **)&ptr, (count) * sizeof(*ptr));
     if (method == EIGH_HQL) {
-      rot_cap = 3 * dd + 64;
+      rot_cap = 2 * dd + 64;  // ~1.2 d^2 rotations observed; overflow is reported as ENOTCONV
       swp_cap = 6 * d + 16;
       EW_ALLOC(dbuf, (size_t)n * d);
       EW_ALLOC(ebuf, (size_t)n * d);
@@ -94,7 +94,7 @@ struct EighWs {
 // U row-major with eigenvectors in columns.  Returns 0, a cudaError_t (> 0), or -5 (unsupported).
 inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
                        const cplx *Ain, double *lam, cplx *U, EighWs &ws, int *status, cudaStream_t st,
-                       int64_t *launches, Profiler *prof) {
+                       int64_t *launches, Profiler *prof, bool sorted = true) {
   int64_t dummy = 0;
   if (!launches) launches = &dummy;
   cudaError_t e = ws.ensure(method, d, n);
@@ -117,24 +117,34 @@ inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx 
     }
     }
     ++*launches;
-    const unsigned tb = (unsigned)((n + 127) / 128);
+    const unsigned tb = (unsigned)((n + HQL_TQL_THREADS - 1) / HQL_TQL_THREADS);
+    e = cudaFuncSetAttribute(hql_tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hql_tql_smem(d));
+    if (e != cudaSuccess) return (int)e;
     {
-    ProfScope ps(prof, st, PH_EIGH_TQL);
-    if (d <= 8)
-      hql_tql_kernel<8><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
-    else if (d <= 32)
-      hql_tql_kernel<32><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
-    else if (d <= 64)
-      hql_tql_kernel<64><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
-    else
-      hql_tql_kernel<128><<<tb, 128, 0, st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status);
+      ProfScope ps(prof, st, PH_EIGH_TQL);
+      hql_tql_kernel<<<tb, HQL_TQL_THREADS, hql_tql_smem(d), st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot,
+                                                                  ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status, sorted ? 1 : 0);
     }
     ++*launches;
-    const size_t zsmem = (size_t)d * (d | 1) * sizeof(double);
+    const size_t zsmem = hql_apply_smem(d, ws.swp_cap);
     e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
     if (e != cudaSuccess) return (int)e;
     const int ath = std::min(128, (d + 31) & ~31);
-    {
+    if (!sorted && d <= 96) {
+      // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
+      const size_t rsmem = hql_apply_reg_smem(ws.swp_cap);
+      ProfScope ps(prof, st, PH_EIGH_APPLY);
+      if (d <= 32) {
+        cudaFuncSetAttribute(hql_apply_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        hql_apply_reg_kernel<32><<<(unsigned)n, 32, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
+      } else if (d <= 64) {
+        cudaFuncSetAttribute(hql_apply_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        hql_apply_reg_kernel<64><<<(unsigned)n, 64, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
+      } else {
+        cudaFuncSetAttribute(hql_apply_reg_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        hql_apply_reg_kernel<96><<<(unsigned)n, 96, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
+      }
+    } else {
       ProfScope ps(prof, st, PH_EIGH_APPLY);
       hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
     }

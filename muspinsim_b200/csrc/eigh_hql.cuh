@@ -328,20 +328,29 @@ __device__ __forceinline__ void dlaev2_dev(double a, double b, double c, double 
   }
 }
 
-template <int MAXD>
-__global__ void __launch_bounds__(128)
+// (d, e) live in shared memory, laid out [i][thread] so that the threads of a warp (different
+// matrices, nearly the same i) hit different banks; the next (d, e) pair is prefetched one step
+// ahead so that shared-memory latency is off the serial chain.
+#define HQL_TQL_THREADS 32
+
+__global__ void __launch_bounds__(HQL_TQL_THREADS)
 hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *__restrict__ ein,
                double *__restrict__ lam, unsigned short *__restrict__ perm, double2 *__restrict__ rot,
                size_t rot_cap, SweepIdx *__restrict__ swp, int swp_cap, int *__restrict__ nswp,
-               int *__restrict__ status) {
-  const int64_t mat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+               int *__restrict__ status, int sorted) {
+  extern __shared__ double tql_smem[];
+  constexpr int NT = HQL_TQL_THREADS;
+  double *dl = tql_smem + threadIdx.x;  // dl[i*NT]
+  double *el = tql_smem + (size_t)d * NT + threadIdx.x;
+#define DL(i) dl[(i) * NT]
+#define EL(i) el[(i) * NT]
+  const int64_t mat = (int64_t)blockIdx.x * NT + threadIdx.x;
   if (mat >= n) return;
-  double dl[MAXD], el[MAXD];
   for (int i = 0; i < d; ++i) {
-    dl[i] = din[mat * d + i];
-    el[i] = ein[mat * d + i];
+    DL(i) = din[mat * d + i];
+    EL(i) = ein[mat * d + i];
   }
-  el[d - 1] = 0.0;
+  EL(d - 1) = 0.0;
   double2 *myrot = rot + mat * rot_cap;
   SweepIdx *myswp = swp + mat * swp_cap;
   size_t nrot = 0;
@@ -354,11 +363,11 @@ hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *_
   while (l < d) {
     int m = l;
     while (m < d - 1) {
-      const double tst = el[m] * el[m];
-      if (tst <= (eps2 * fabs(dl[m])) * fabs(dl[m + 1]) + safmin) break;
+      const double em = EL(m);
+      if (em * em <= (eps2 * fabs(DL(m))) * fabs(DL(m + 1)) + safmin) break;
       ++m;
     }
-    if (m < d - 1) el[m] = 0.0;
+    if (m < d - 1) EL(m) = 0.0;
     if (m == l) {
       ++l;
       continue;
@@ -369,105 +378,325 @@ hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *_
     }
     if (m == l + 1) {
       double rt1, rt2, c, s;
-      dlaev2_dev(dl[l], el[l], dl[l + 1], rt1, rt2, c, s);
+      dlaev2_dev(DL(l), EL(l), DL(l + 1), rt1, rt2, c, s);
       myrot[nrot++] = make_double2(c, s);
       myswp[ns++] = SweepIdx{(unsigned short)l, (unsigned short)(l + 1)};
-      dl[l] = rt1;
-      dl[l + 1] = rt2;
-      el[l] = 0.0;
+      DL(l) = rt1;
+      DL(l + 1) = rt2;
+      EL(l) = 0.0;
       l += 2;
       continue;
     }
     ++nit;
-    double p = dl[l];
-    double g = (dl[l + 1] - p) / (2.0 * el[l]);
+    double p = DL(l);
+    const double el_l = EL(l);
+    double g = (DL(l + 1) - p) / (2.0 * el_l);
     double r = sqrt(fma(g, g, 1.0));
-    g = dl[m] - p + el[l] / (g + copysign(r, g));
+    g = DL(m) - p + el_l / (g + copysign(r, g));
     double s = 1.0, c = 1.0;
     p = 0.0;
+    // carried / prefetched values: d_ip1 = d[i+1] (untouched so far in this sweep), e_i, d_i
+    double d_ip1 = DL(m);
+    double e_i = EL(m - 1), d_i = DL(m - 1);
+    double2 *rp = myrot + nrot;
     for (int i = m - 1; i >= l; --i) {
-      const double f = s * el[i];
-      const double b = c * el[i];
-      r = sqrt(fma(g, g, f * f));
-      if (r == 0.0) {
+      double e_nx = 0.0, d_nx = 0.0;
+      if (i > l) {
+        e_nx = EL(i - 1);
+        d_nx = DL(i - 1);
+      }
+      const double f = s * e_i;
+      const double b = c * e_i;
+      const double q = fma(g, g, f * f);
+      if (q == 0.0) {
         c = 1.0;
         s = 0.0;
+        r = 0.0;
       } else {
-        const double ri = 1.0 / r;
+        const double ri = rsqrt(q);
+        r = q * ri;
         c = g * ri;
         s = f * ri;
       }
-      if (i != m - 1) el[i + 1] = r;
-      g = dl[i + 1] - p;
-      r = (dl[i] - g) * s + 2.0 * c * b;
+      if (i != m - 1) EL(i + 1) = r;
+      g = d_ip1 - p;
+      r = fma(d_i - g, s, 2.0 * c * b);
       p = s * r;
-      dl[i + 1] = g + p;
-      g = c * r - b;
-      myrot[nrot++] = make_double2(c, -s);
+      DL(i + 1) = g + p;
+      g = fma(c, r, -b);
+      *rp++ = make_double2(c, -s);
+      d_ip1 = d_i;
+      e_i = e_nx;
+      d_i = d_nx;
     }
-    dl[l] -= p;
-    el[l] = g;
+    nrot += (size_t)(m - l);
+    DL(l) = DL(l) - p;
+    EL(l) = g;
     myswp[ns++] = SweepIdx{(unsigned short)l, (unsigned short)m};
   }
   nswp[mat] = ns;
   if (fail) atomicMax(status, 1);
-  // ascending order: insertion sort of indices
   unsigned short *pm = perm + mat * d;
+  if (!sorted) {  // pipeline use: eigenpairs stay in the order the iteration leaves them
+    for (int i = 0; i < d; ++i) {
+      pm[i] = (unsigned short)i;
+      lam[mat * d + i] = DL(i);
+    }
+    return;
+  }
+  // ascending order: insertion sort of indices
   for (int i = 0; i < d; ++i) {
-    const double v = dl[i];
+    const double v = DL(i);
     int j = i - 1;
-    while (j >= 0 && dl[pm[j]] > v) {
+    while (j >= 0 && DL(pm[j]) > v) {
       pm[j + 1] = pm[j];
       --j;
     }
     pm[j + 1] = (unsigned short)i;
   }
-  for (int i = 0; i < d; ++i) lam[mat * d + i] = dl[pm[i]];
+  for (int i = 0; i < d; ++i) lam[mat * d + i] = DL(pm[i]);
+#undef DL
+#undef EL
 }
 
+inline size_t hql_tql_smem(int d) { return 2 * (size_t)d * HQL_TQL_THREADS * sizeof(double); }
+
 // ---------------------------------------------------------------------------------------
-// K3: replay the rotations on Zt (real, starts as identity), one thread per row.
+// K3: replay the rotations on Zt (real, starts as identity), one thread per row.  The
+// rotation stream is staged through a shared-memory ring with cp.async (deep prefetch: the
+// stream comes from HBM and is read exactly once); each thread processes rotations in groups
+// of 8 with all loads issued before the dependent chain  x <- s x + c a.
 // ---------------------------------------------------------------------------------------
+#define HQL_TILE 256  // rotations per staging tile (4 KB)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
 __global__ void __launch_bounds__(128)
 hql_apply_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
                  const SweepIdx *__restrict__ swp, int swp_cap, const int *__restrict__ nswp,
                  const unsigned short *__restrict__ perm, double *__restrict__ Zt) {
-  extern __shared__ double sZ[];  // (r,c) at [c*ld + r]
+  extern __shared__ __align__(16) unsigned char apply_smem[];
+  double2 *ring = reinterpret_cast<double2 *>(apply_smem);           // [2][HQL_TILE]
+  double *sZ = reinterpret_cast<double *>(ring + 2 * HQL_TILE);      // (r,c) at [c*ld + r]
   const int ld = d | 1;
+  SweepIdx *sswp = reinterpret_cast<SweepIdx *>(sZ + (size_t)d * ld);  // [swp_cap]
   const int tid = threadIdx.x, nth = blockDim.x;
   const size_t mat = blockIdx.x;
+  const double2 *myrot = rot + mat * rot_cap;
+  const int ns = nswp[mat];
+  size_t total = 0;
+  for (int i = tid; i < ns; i += nth) sswp[i] = swp[mat * swp_cap + i];
   for (int idx = tid; idx < d * ld; idx += nth) sZ[idx] = 0.0;
   __syncthreads();
-  for (int i = tid; i < d; i += nth) sZ[i * ld + i] = 1.0;
-  __syncthreads();
-  const double2 *myrot = rot + mat * rot_cap;
-  const SweepIdx *myswp = swp + mat * swp_cap;
-  const int ns = nswp[mat];
-  for (int r = tid; r < d; r += nth) {
-    size_t off = 0;
-    for (int sidx = 0; sidx < ns; ++sidx) {
-      const SweepIdx lm = myswp[sidx];
-      const int l = lm.l, m = lm.m;
-      double x = sZ[m * ld + r];
-      const double2 *rs = myrot + off;
-#pragma unroll 4
-      for (int j = m - 1; j >= l; --j) {
-        const double2 cs = rs[m - 1 - j];
-        const double a = sZ[j * ld + r];
-        sZ[(j + 1) * ld + r] = cs.x * x - cs.y * a;
-        x = cs.y * x + cs.x * a;
-      }
-      sZ[l * ld + r] = x;
-      off += (size_t)(m - l);
+  for (int i = 0; i < ns; ++i) total += (size_t)(sswp[i].m - sswp[i].l);
+  const int ntiles = (int)((total + HQL_TILE - 1) / HQL_TILE);
+  auto stage = [&](int t) {  // issue tile t into ring slot t & 1
+    if (t < ntiles) {
+      const size_t base = (size_t)t * HQL_TILE;
+      for (int e = tid; e < HQL_TILE; e += nth)
+        if (base + e < total) cp_async16(&ring[(t & 1) * HQL_TILE + e], &myrot[base + e]);
     }
+    cp_async_commit();
+  };
+  stage(0);
+  stage(1);
+  for (int i = tid; i < d; i += nth) sZ[i * ld + i] = 1.0;
+  cp_async_wait<1>();
+  __syncthreads();
+
+  const int r = tid;  // one row per thread (d <= 128 = blockDim bound)
+  const bool active = r < d;
+  size_t g = 0;  // global rotation index
+  int tile = 0;
+  for (int sidx = 0; sidx < ns; ++sidx) {
+    const int l = sswp[sidx].l, m = sswp[sidx].m;
+    double x = active ? sZ[m * ld + r] : 0.0;
+    int j = m - 1;
+    while (j >= l) {
+      // rotations [g, g+cnt) stay inside the current tile
+      const int in_tile = (int)(g - (size_t)tile * HQL_TILE);
+      int cnt = min(j - l + 1, HQL_TILE - in_tile);
+      const double2 *rs = ring + (tile & 1) * HQL_TILE + in_tile;
+      int k = 0;
+      if (active) {
+        for (; k + 8 <= cnt; k += 8) {
+          double a[8];
+          double2 cs[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            a[u] = sZ[(j - k - u) * ld + r];
+            cs[u] = rs[k + u];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            sZ[(j - k - u + 1) * ld + r] = cs[u].x * x - cs[u].y * a[u];
+            x = fma(cs[u].y, x, cs[u].x * a[u]);
+          }
+        }
+        for (; k < cnt; ++k) {
+          const double a = sZ[(j - k) * ld + r];
+          const double2 cs = rs[k];
+          sZ[(j - k + 1) * ld + r] = cs.x * x - cs.y * a;
+          x = fma(cs.y, x, cs.x * a);
+        }
+      }
+      g += cnt;
+      j -= cnt;
+      if (g == (size_t)(tile + 1) * HQL_TILE && g < total) {
+        // tile consumed by everyone -> refill its slot with tile+2, wait for tile+1
+        __syncthreads();
+        stage(tile + 2);
+        cp_async_wait<1>();
+        __syncthreads();
+        ++tile;
+      }
+    }
+    if (active) sZ[l * ld + r] = x;
   }
+  cp_async_wait<0>();
   __syncthreads();
   const unsigned short *pm = perm + mat * d;
   const size_t dd = (size_t)d * d;
   for (int idx = tid; idx < d * d; idx += nth) {
-    const int rr = idx / d, j = idx - rr * d;
-    Zt[mat * dd + idx] = sZ[pm[j] * ld + rr];
+    const int rr = idx / d, jj = idx - rr * d;
+    Zt[mat * dd + idx] = sZ[pm[jj] * ld + rr];
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 (register-resident variant, d <= 96): thread r keeps row r of Zt in REGISTERS (D doubles).
+// The column loop is fully unrolled so every register index is static; a rotation is executed
+// when its column lies in the current sweep [l, m) (a uniform branch).  No shared-memory
+// traffic for Zt at all -- the shared-memory version above is LSU-bound (ncu: 65 % LSU, 21 %
+// FP64) -- only the broadcast read of (c, s) from the cp.async ring remains.
+// ---------------------------------------------------------------------------------------
+#define HQL_RTILE 512
+#define HQL_RTILES 4
+#define HQL_RPAD 96  // guard entries in front of the ring and mirrored entries behind it
+
+template <int D>
+__global__ void __maxnreg__(224)
+hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
+                     const SweepIdx *__restrict__ swp, int swp_cap, const int *__restrict__ nswp,
+                     double *__restrict__ Zt) {
+  extern __shared__ __align__(16) unsigned char apply_smem[];
+  constexpr int RING = HQL_RTILE * HQL_RTILES;
+  // [RPAD guard][RING][RPAD mirror of the first entries]: a sweep's <= 95 rotations starting
+  // anywhere in the ring are contiguous, so every (c, s) load is base + immediate offset
+  double2 *ring = reinterpret_cast<double2 *>(apply_smem) + HQL_RPAD;
+  SweepIdx *sswp = reinterpret_cast<SweepIdx *>(ring + RING + HQL_RPAD);
+  const int tid = threadIdx.x;
+  const size_t mat = blockIdx.x;
+  const double2 *myrot = rot + mat * rot_cap;
+  const int ns = nswp[mat];
+  for (int i = tid; i < ns; i += D) sswp[i] = swp[mat * swp_cap + i];
+  __syncthreads();
+  size_t total = 0;
+  for (int i = 0; i < ns; ++i) total += (size_t)(sswp[i].m - sswp[i].l);
+  const int ntiles = (int)((total + HQL_RTILE - 1) / HQL_RTILE);
+  int t_issued = 0, t_landed = 0;
+  auto issue = [&]() {  // issue tile t_issued into its ring slot (+ mirror if it is slot 0)
+    const size_t base = (size_t)t_issued * HQL_RTILE;
+    const int slot0 = (t_issued % HQL_RTILES) * HQL_RTILE;
+    for (int e = tid; e < HQL_RTILE; e += D)
+      if (base + e < total) {
+        cp_async16(&ring[slot0 + e], &myrot[base + e]);
+        if (slot0 == 0 && e < HQL_RPAD) cp_async16(&ring[RING + e], &myrot[base + e]);
+      }
+    cp_async_commit();
+    ++t_issued;
+  };
+  while (t_issued < ntiles && t_issued < HQL_RTILES) issue();
+
+  double z[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) z[j] = (j == tid) ? 1.0 : 0.0;
+
+  size_t g = 0;
+  for (int sidx = 0; sidx < ns; ++sidx) {
+    const int l = sswp[sidx].l, m = sswp[sidx].m;
+    const size_t need = g + (size_t)(m - l);
+    while ((size_t)t_landed * HQL_RTILE < need && t_landed < ntiles) {
+      cp_async_wait<0>();
+      __syncthreads();
+      t_landed = t_issued;
+      const int consumed = (int)(g / HQL_RTILE);  // tiles < consumed are dead for every thread
+      // (the mirror of slot 0 is rewritten together with slot 0; a sweep that still reads the
+      //  old mirror would start in the last tile, which is then not yet consumed)
+      while (t_issued < ntiles && t_issued - consumed < HQL_RTILES - 1) issue();
+    }
+    // rotation for column j sits at base[-j]
+    const double2 *base = ring + (int)(g % RING) + (m - 1);
+#pragma unroll
+    for (int b = (D - 2) / 8; b >= 0; --b) {
+      const int jlo = 8 * b;
+      const int jhi = (8 * b + 7 < D - 2) ? 8 * b + 7 : D - 2;
+      if (jlo >= l && jhi < m) {
+        // interior block: all steps active, loads first, then the dependent chain
+        double2 cs[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (jhi - u >= jlo) cs[u] = base[-(jhi - u)];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = jhi - u;
+          if (j >= jlo) {
+            const double t = z[j + 1];
+            z[j + 1] = cs[u].x * t - cs[u].y * z[j];
+            z[j] = fma(cs[u].y, t, cs[u].x * z[j]);
+          }
+        }
+      } else if (jlo < m && jhi >= l) {
+        // edge block
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = jhi - u;
+          if (j >= jlo) {
+            if (j < m && j >= l) {
+              const double2 c1 = base[-j];
+              const double t = z[j + 1];
+              z[j + 1] = c1.x * t - c1.y * z[j];
+              z[j] = fma(c1.y, t, c1.x * z[j]);
+            }
+          }
+        }
+      }
+    }
+    g = need;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // write Zt (unpermuted) through shared memory, 32 columns at a time, for coalescing
+  double *sbuf = reinterpret_cast<double *>(ring);  // [D][33]
+  const size_t dd = (size_t)d * d;
+  for (int c0 = 0; c0 < d; c0 += 32) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (j >= c0 && j < c0 + 32) sbuf[tid * 33 + (j - c0)] = z[j];
+    __syncthreads();
+    const int w = min(32, d - c0);
+    for (int idx = tid; idx < d * 32; idx += D) {
+      const int rr = idx >> 5, jj = idx & 31;
+      if (jj < w) Zt[mat * dd + (size_t)rr * d + c0 + jj] = sbuf[rr * 33 + jj];
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t hql_apply_reg_smem(int swp_cap) {
+  return (HQL_RTILE * HQL_RTILES + 2 * HQL_RPAD) * sizeof(double2) + (size_t)swp_cap * sizeof(SweepIdx) + 16;
+}
+
+inline size_t hql_apply_smem(int d, int swp_cap) {
+  return 2 * HQL_TILE * sizeof(double2) + (size_t)d * (d | 1) * sizeof(double) + (size_t)swp_cap * sizeof(SweepIdx) + 16;
 }
 
 }  // namespace musim

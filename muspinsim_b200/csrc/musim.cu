@@ -58,7 +58,7 @@ struct musim_handle {
   void *stage = nullptr;
   size_t stage_bytes = 0;
   // options
-  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0;
+  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1;
   // bookkeeping
   int64_t launches = 0;
   Profiler prof;
@@ -129,6 +129,10 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
   }
   else if (!strcmp(key, "gemm"))
     h->opt_gemm = value;
+  else if (!strcmp(key, "polar_mma"))  // 1 (default): DMMA polarisation kernel, 0: vector-FMA version
+    h->opt_polar_mma = value;
+  else if (!strcmp(key, "sorted"))  // 1: keep eigenpairs sorted inside the pipeline (slower replay kernel)
+    h->opt_sorted = value;
   else
     return set_err(h, MUSIM_EINVAL, std::string("unknown option ") + key);
   return MUSIM_OK;
@@ -403,12 +407,13 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   }
 
   const int method = pick_eigh(h->opt_eigh, d);
-  // chunk: bound the workspace to ~3 GB
+  // chunk: bound the workspace to ~24 GB of the 180 GB (big launch groups keep the
+  // latency-bound QL stage at full occupancy)
   const int nbuf = general ? 6 : 4;
   const size_t per_cfg = nbuf * dd * sizeof(cplx) + EighWs::bytes_per_matrix(method, d) + d * sizeof(double);
-  int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>(148, (int64_t)(3.0e9 / per_cfg));
+  int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>(148, (int64_t)(24.0e9 / per_cfg));
   chunk = std::min<int64_t>(chunk, n_cfg);
-  chunk = std::min<int64_t>(chunk, 65535LL * 8);
+  chunk = std::min<int64_t>(chunk, 65535);  // grid.y / grid.z limit of the batched kernels
   int rc = ensure_ws(h, chunk, general);
   if (rc) return rc;
   CK(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
@@ -419,7 +424,7 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
     const int64_t n = std::min(chunk, n_cfg - c0);
     {
       rc = launch_eigh(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->ews, h->status, st,
-                       &h->launches, &h->prof);
+                       &h->launches, &h->prof, h->opt_sorted != 0);
       if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
       if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
     }
@@ -469,11 +474,23 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
         int NB = 1;
         while (NB * NB < nt && NB < 32) ++NB;
         const int NA_total = (nt + NB - 1) / NB;
-        const size_t smem = polar_fact_smem(d);
-        CK(cudaFuncSetAttribute(polar_fact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(groups, (NA_total + 31) / 32);
-        polar_fact_kernel<<<grid, 256, smem, st>>>(d, h->npairs, h->pairs, (int)n, per, h->W, h->lam, w + c0,
-                                                   slot + c0, nt, tg.t0, tg.dt, NA_total, NB, out);
+        if (h->opt_polar_mma != 0) {
+          // FP64 tensor-pipe version: 128-thread CTAs, 3 per SM
+          int g2 = (int)std::min<int64_t>(n, 148 * 3);
+          int per2 = (int)((n + g2 - 1) / g2);
+          g2 = (int)((n + per2 - 1) / per2);
+          const size_t smem = polar_dmma_smem(d);
+          CK(cudaFuncSetAttribute(polar_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          dim3 grid(g2, (NA_total + 31) / 32);
+          polar_dmma_kernel<<<grid, 128, smem, st>>>(d, h->npairs, h->pairs, (int)n, per2, h->W, h->lam, w + c0,
+                                                     slot + c0, nt, tg.t0, tg.dt, NA_total, NB, out);
+        } else {
+          const size_t smem = polar_fact_smem(d);
+          CK(cudaFuncSetAttribute(polar_fact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          dim3 grid(groups, (NA_total + 31) / 32);
+          polar_fact_kernel<<<grid, 256, smem, st>>>(d, h->npairs, h->pairs, (int)n, per, h->W, h->lam, w + c0,
+                                                     slot + c0, nt, tg.t0, tg.dt, NA_total, NB, out);
+        }
       } else {
         dim3 grid(groups, (nt + 255) / 256);
         polar_direct_kernel<<<grid, 256, d * sizeof(double), st>>>(d, h->npairs, h->pairs, (int)n, per, h->W,
