@@ -2,6 +2,7 @@
 #pragma once
 #include "eigh_hql.cuh"
 #include "eigh_jacobi.cuh"
+#include "eigh_tridiag_reg.cuh"
 #include "profiler.cuh"
 #include "rotate.cuh"
 
@@ -10,6 +11,8 @@ namespace musim {
 #define MUSIM_MAX_SMEM_OPTIN (227 * 1024)
 
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
+static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
+static bool g_tridiag_reg = false;  // option "tridiag_reg": register-resident tridiagonalisation (slower)
 
 inline int pick_eigh(long opt, int d) {
   if (opt == EIGH_JACOBI) return EIGH_JACOBI;
@@ -17,12 +20,17 @@ inline int pick_eigh(long opt, int d) {
   return hql_supported(d) ? EIGH_HQL : EIGH_JACOBI;
 }
 
+inline bool use_reflect(int d) { return g_reflect && !g_tridiag_reg && d >= 3 && d <= 96; }
+
 struct EighWs {
   int64_t cap = 0;
   int d = 0, method = 0;
   cplx *Vg = nullptr;
-  double *dbuf = nullptr, *ebuf = nullptr, *Zt = nullptr;
-  cplx *Q = nullptr;
+  double *dbuf[2] = {nullptr, nullptr}, *ebuf[2] = {nullptr, nullptr}, *Zt = nullptr;
+  cplx *Q[2] = {nullptr, nullptr};  // [2]: stage A (tridiagonalisation) of the next launch group overlaps stage B
+  bool dbl = false;
+  cplx *Vp[2] = {nullptr, nullptr}, *tauv[2] = {nullptr, nullptr};  // packed reflectors + tau (d <= 96 path)
+  size_t vcap = 0;
   double2 *rot = nullptr;
   SweepIdx *swp = nullptr;
   int *nswp = nullptr;
@@ -35,7 +43,7 @@ struct EighWs {
   static size_t bytes_per_matrix(int method, int d) {
     const size_t dd = (size_t)d * d;
     if (method == EIGH_HQL)
-      return 2 * d * sizeof(double) + dd * sizeof(cplx) + dd * sizeof(double) +
+      return 2 * (2 * d * sizeof(double) + dd * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
              (2 * dd + 64) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
              d * sizeof(unsigned short);
     return jacobi_vglobal(d) ? (size_t)d * (d | 1) * sizeof(cplx) : 0;
@@ -43,17 +51,23 @@ struct EighWs {
 
   void release() {
     cudaFree(Vg);
-    cudaFree(dbuf);
-    cudaFree(ebuf);
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(dbuf[i]);
+      cudaFree(ebuf[i]);
+      cudaFree(Q[i]);
+      cudaFree(Vp[i]);
+      cudaFree(tauv[i]);
+      dbuf[i] = ebuf[i] = nullptr;
+      Q[i] = nullptr;
+      Vp[i] = tauv[i] = nullptr;
+    }
     cudaFree(Zt);
-    cudaFree(Q);
     cudaFree(rot);
     cudaFree(swp);
     cudaFree(nswp);
     cudaFree(perm);
     Vg = nullptr;
-    dbuf = ebuf = Zt = nullptr;
-    Q = nullptr;
+    Zt = nullptr;
     rot = nullptr;
     swp = nullptr;
     nswp = nullptr;
@@ -61,11 +75,12 @@ struct EighWs {
     cap = 0;
   }
 
-  cudaError_t ensure(int method_, int d_, int64_t n) {
-    if (cap >= n && d == d_ && method == method_) return cudaSuccess;
+  cudaError_t ensure(int method_, int d_, int64_t n, bool dbl_ = false) {
+    if (cap >= n && d == d_ && method == method_ && (dbl || !dbl_)) return cudaSuccess;
     release();
     d = d_;
     method = method_;
+    dbl = dbl_;
     const size_t dd = (size_t)d * d;
     cudaError_t e = cudaSuccess;
 #define EW_ALLOC(ptr, count)                                              \
@@ -73,9 +88,14 @@ struct EighWs {
     if (method == EIGH_HQL) {
       rot_cap = 2 * dd + 64;  // ~1.2 d^2 rotations observed; overflow is reported as ENOTCONV
       swp_cap = 6 * d + 16;
-      EW_ALLOC(dbuf, (size_t)n * d);
-      EW_ALLOC(ebuf, (size_t)n * d);
-      EW_ALLOC(Q, (size_t)n * dd);
+      vcap = (size_t)(d - 1) * (d - 2) / 2 + 8;
+      for (int i = 0; i < (dbl ? 2 : 1); ++i) {
+        EW_ALLOC(dbuf[i], (size_t)n * d);
+        EW_ALLOC(ebuf[i], (size_t)n * d);
+        EW_ALLOC(Q[i], (size_t)n * dd);
+        EW_ALLOC(Vp[i], (size_t)n * vcap);
+        EW_ALLOC(tauv[i], (size_t)n * d);
+      }
       EW_ALLOC(Zt, (size_t)n * dd);
       EW_ALLOC(rot, (size_t)n * rot_cap);
       EW_ALLOC(swp, (size_t)n * swp_cap);
@@ -90,69 +110,43 @@ struct EighWs {
   }
 };
 
-// Eigen-decompose n matrices: either H0 + B.Z (Ain == nullptr) or Ain[n].  lam ascending,
-// U row-major with eigenvectors in columns.  Returns 0, a cudaError_t (> 0), or -5 (unsupported).
-inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
-                       const cplx *Ain, double *lam, cplx *U, EighWs &ws, int *status, cudaStream_t st,
-                       int64_t *launches, Profiler *prof, bool sorted = true) {
-  int64_t dummy = 0;
-  if (!launches) launches = &dummy;
-  cudaError_t e = ws.ensure(method, d, n);
-  if (e != cudaSuccess) return (int)e;
+// Stage A of the Householder+QL solver: tridiagonalise + form Q into buffer set `buf`.
+// (For Jacobi, stage A is the whole solver.)  Returns 0, a cudaError_t (> 0), or -5.
+inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
+                              const cplx *Ain, double *lam, cplx *U, EighWs &ws, int buf, int *status,
+                              cudaStream_t st, int64_t *launches, Profiler *prof) {
+  cudaError_t e;
   if (method == EIGH_HQL) {
     if (!hql_supported(d)) return -5;
     const HqlGeom g = hql_geom(d);
     const size_t smem = hql_tridiag_smem(d, g);
     if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
-    {
     ProfScope ps(prof, st, PH_EIGH_TRIDIAG);
-    if (Ain) {
+    if (d <= 96 && g_tridiag_reg) {
+      // register-resident A (eigh_tridiag_reg.cuh): R = d rounded up to 32 / 64 / 96
+      if (d <= 32) {
+        const size_t sm = hql_tridiag_reg_smem<32>();
+        cudaFuncSetAttribute(hql_tridiag_reg_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_tridiag_reg_kernel<32, 8><<<(unsigned)n, 128, sm, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf]);
+      } else if (d <= 64) {
+        const size_t sm = hql_tridiag_reg_smem<64>();
+        cudaFuncSetAttribute(hql_tridiag_reg_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_tridiag_reg_kernel<64, 16><<<(unsigned)n, 256, sm, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf]);
+      } else {
+        const size_t sm = hql_tridiag_reg_smem<96>();
+        cudaFuncSetAttribute(hql_tridiag_reg_kernel<96, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_tridiag_reg_kernel<96, 24><<<(unsigned)n, 384, sm, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf]);
+      }
+    } else if (Ain) {
       e = cudaFuncSetAttribute(hql_tridiag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      hql_tridiag_kernel<false><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf, ws.ebuf, ws.Q);
+      hql_tridiag_kernel<false><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf],
+                                                                  use_reflect(d) ? ws.Vp[buf] : nullptr, ws.vcap, ws.tauv[buf]);
     } else {
       e = cudaFuncSetAttribute(hql_tridiag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      hql_tridiag_kernel<true><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf, ws.ebuf, ws.Q);
-    }
-    }
-    ++*launches;
-    const unsigned tb = (unsigned)((n + HQL_TQL_THREADS - 1) / HQL_TQL_THREADS);
-    e = cudaFuncSetAttribute(hql_tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hql_tql_smem(d));
-    if (e != cudaSuccess) return (int)e;
-    {
-      ProfScope ps(prof, st, PH_EIGH_TQL);
-      hql_tql_kernel<<<tb, HQL_TQL_THREADS, hql_tql_smem(d), st>>>(d, n, ws.dbuf, ws.ebuf, lam, ws.perm, ws.rot,
-                                                                  ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status, sorted ? 1 : 0);
-    }
-    ++*launches;
-    const size_t zsmem = hql_apply_smem(d, ws.swp_cap);
-    e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
-    if (e != cudaSuccess) return (int)e;
-    const int ath = std::min(128, (d + 31) & ~31);
-    if (!sorted && d <= 96) {
-      // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
-      const size_t rsmem = hql_apply_reg_smem(ws.swp_cap);
-      ProfScope ps(prof, st, PH_EIGH_APPLY);
-      if (d <= 32) {
-        cudaFuncSetAttribute(hql_apply_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-        hql_apply_reg_kernel<32><<<(unsigned)n, 32, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
-      } else if (d <= 64) {
-        cudaFuncSetAttribute(hql_apply_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-        hql_apply_reg_kernel<64><<<(unsigned)n, 64, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
-      } else {
-        cudaFuncSetAttribute(hql_apply_reg_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-        hql_apply_reg_kernel<96><<<(unsigned)n, 96, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
-      }
-    } else {
-      ProfScope ps(prof, st, PH_EIGH_APPLY);
-      hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
-    }
-    ++*launches;
-    dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);
-    {
-      ProfScope ps(prof, st, PH_EIGH_BACK);
-      cgemm_realB_kernel<<<grid, 256, 0, st>>>(d, ws.Q, ws.Zt, U);
+      hql_tridiag_kernel<true><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf],
+                                                                 use_reflect(d) ? ws.Vp[buf] : nullptr, ws.vcap, ws.tauv[buf]);
     }
     ++*launches;
     return (int)cudaGetLastError();
@@ -180,6 +174,83 @@ inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx 
   }
   ++*launches;
   return (int)cudaGetLastError();
+}
+
+// Stage B (Householder+QL only): QL on (d, e), rotation replay, back-transformation U = Q Zt.
+inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U, EighWs &ws, int buf, int *status,
+                              cudaStream_t st, int64_t *launches, Profiler *prof, bool sorted) {
+  if (method != EIGH_HQL) return 0;
+  cudaError_t e;
+  const unsigned tb = (unsigned)((n + HQL_TQL_THREADS - 1) / HQL_TQL_THREADS);
+  e = cudaFuncSetAttribute(hql_tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hql_tql_smem(d));
+  if (e != cudaSuccess) return (int)e;
+  {
+    ProfScope ps(prof, st, PH_EIGH_TQL);
+    hql_tql_kernel<<<tb, HQL_TQL_THREADS, hql_tql_smem(d), st>>>(d, n, ws.dbuf[buf], ws.ebuf[buf], lam, ws.perm, ws.rot,
+                                                                ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status,
+                                                                sorted ? 1 : 0);
+  }
+  ++*launches;
+  const size_t zsmem = hql_apply_smem(d, ws.swp_cap);
+  e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
+  if (e != cudaSuccess) return (int)e;
+  const int ath = std::min(128, (d + 31) & ~31);
+  if (!sorted && d <= 96) {
+    // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
+    const size_t rsmem = hql_apply_reg_smem(ws.swp_cap);
+    ProfScope ps(prof, st, PH_EIGH_APPLY);
+    if (d <= 32) {
+      cudaFuncSetAttribute(hql_apply_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      hql_apply_reg_kernel<32><<<(unsigned)n, 32, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
+    } else if (d <= 64) {
+      cudaFuncSetAttribute(hql_apply_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      hql_apply_reg_kernel<64><<<(unsigned)n, 64, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
+    } else {
+      cudaFuncSetAttribute(hql_apply_reg_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      hql_apply_reg_kernel<96><<<(unsigned)n, 96, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
+    }
+  } else {
+    ProfScope ps(prof, st, PH_EIGH_APPLY);
+    hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
+  }
+  ++*launches;
+  {
+    ProfScope ps(prof, st, PH_EIGH_BACK);
+    if (use_reflect(d)) {
+      if (d <= 32) {
+        const size_t sm = hql_reflect_smem(32);
+        cudaFuncSetAttribute(hql_reflect_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_reflect_kernel<32><<<(unsigned)n, 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+      } else if (d <= 64) {
+        const size_t sm = hql_reflect_smem(64);
+        cudaFuncSetAttribute(hql_reflect_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_reflect_kernel<64><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+      } else {
+        const size_t sm = hql_reflect_smem(96);
+        cudaFuncSetAttribute(hql_reflect_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_reflect_kernel<96><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+      }
+    } else {
+      dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);
+      cgemm_realB_kernel<<<grid, 256, 0, st>>>(d, ws.Q[buf], ws.Zt, U);
+    }
+  }
+  ++*launches;
+  return (int)cudaGetLastError();
+}
+
+// Eigen-decompose n matrices: either H0 + B.Z (Ain == nullptr) or Ain[n].  lam ascending when
+// `sorted`, U row-major with eigenvectors in columns.  Returns 0, a cudaError_t (> 0), or -5.
+inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
+                       const cplx *Ain, double *lam, cplx *U, EighWs &ws, int *status, cudaStream_t st,
+                       int64_t *launches, Profiler *prof, bool sorted = true) {
+  int64_t dummy = 0;
+  if (!launches) launches = &dummy;
+  cudaError_t e = ws.ensure(method, d, n);
+  if (e != cudaSuccess) return (int)e;
+  int rc = launch_eigh_stageA(method, d, n, H0, Z, B, Ain, lam, U, ws, 0, status, st, launches, prof);
+  if (rc) return rc;
+  return launch_eigh_stageB(method, d, n, lam, U, ws, 0, status, st, launches, prof, sorted);
 }
 
 }  // namespace musim

@@ -76,7 +76,8 @@ template <bool BUILD_H>
 __global__ void __launch_bounds__(512)
 hql_tridiag_kernel(int d, int R, int G, const cplx *__restrict__ H0, const cplx *__restrict__ Z,
                    const double *__restrict__ Bf, const cplx *__restrict__ Ain,
-                   double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Qout) {
+                   double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Qout,
+                   cplx *__restrict__ Vp, size_t vcap, cplx *__restrict__ tauout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ld = d | 1;
   cplx *sA = reinterpret_cast<cplx *>(smem_raw);  // (r,c) at [c*ld + r]
@@ -200,6 +201,20 @@ hql_tridiag_kernel(int d, int R, int G, const cplx *__restrict__ H0, const cplx 
   }
   __syncthreads();
 
+  if (Vp) {
+    // reflector output for hql_reflect_kernel: v_k[2:] packed in the order the backward
+    // application consumes them (k = d-2 first), plus tau; Q is not formed here.
+    for (int idx = tid; idx < d * d; idx += nth) {
+      const int k = idx / d, i = idx - k * d;  // column k, row i
+      if (k < d - 2 && i >= k + 2) {
+        const int mk = d - k - 2;  // entries of v_k
+        const size_t off = (size_t)mk * (mk - 1) / 2;  // sum of the entry counts of all k' > k
+        Vp[cfg * vcap + off + (i - k - 2)] = sA[k * ld + i];
+      }
+    }
+    for (int k = tid; k < d; k += nth) tauout[cfg * d + k] = (k < d - 1) ? stau[k] : make_c(0.0, 0.0);
+    return;
+  }
   // ---- zung2r, in place: Q = H_0 H_1 ... H_{d-2} ----
   for (int k = d - 2; k >= 0; --k) {
     const int m1 = d - k - 2;  // length of v[1:]
@@ -689,6 +704,150 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 (d <= 96): back-transformation U = H_0 H_1 ... H_{d-2} Zt by applying the Householder
+// reflectors directly to the columns of Zt.  Thread c keeps column c (D complex numbers) in
+// REGISTERS; every reflector is a dot product and an axpy on that column, so there is no
+// inter-thread communication and no barrier in the main loop -- unlike forming Q inside the
+// tridiagonalisation kernel (a barrier-separated chain that held the whole SM) followed by a
+// GEMM.  The reflector stream (v_k packed in consumption order, 71 KB at d = 96) is staged
+// through the same mirrored cp.async ring as the rotation stream; rows enter through a
+// fall-through switch at row k+1 so the work shrinks with the reflector length.
+// ---------------------------------------------------------------------------------------
+#define HQL_ROWS(X)                                                                           \
+  X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
+      X(17) X(18) X(19) X(20) X(21) X(22) X(23)
+
+// Thread (c, h) = (tid / 4, tid % 4) holds rows i = 4 jj + h of column c (D/4 complex numbers =
+// D registers); the four partial dot products of a column are combined with two shuffles.
+template <int D>
+__global__ void __launch_bounds__(4 * D)
+hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__ Vp, size_t vcap,
+                   const cplx *__restrict__ tau, cplx *__restrict__ U) {
+  constexpr int RPT = D / 4;  // rows per thread
+  static_assert(RPT % 4 == 0 || RPT == 8, "rows per thread in blocks of 4");
+  constexpr int NT = 4 * D;
+  extern __shared__ __align__(16) unsigned char refl_smem[];
+  constexpr int RING = HQL_RTILE * HQL_RTILES;
+  cplx *ring = reinterpret_cast<cplx *>(refl_smem) + HQL_RPAD;
+  cplx *stau = ring + RING + HQL_RPAD;  // [D]
+  const int tid = threadIdx.x;
+  const int c = tid >> 2, hh = tid & 3;
+  const size_t mat = blockIdx.x;
+  const size_t dd = (size_t)d * d;
+  const cplx *myv = Vp + mat * vcap;
+  const size_t total = (size_t)(d - 1) * (d - 2) / 2;
+  const int ntiles = (int)((total + HQL_RTILE - 1) / HQL_RTILE);
+  int t_issued = 0, t_landed = 0;
+  auto issue = [&]() {
+    const size_t base = (size_t)t_issued * HQL_RTILE;
+    const int slot0 = (t_issued % HQL_RTILES) * HQL_RTILE;
+    for (int e = tid; e < HQL_RTILE; e += NT)
+      if (base + e < total) {
+        cp_async16(&ring[slot0 + e], &myv[base + e]);
+        if (slot0 == 0 && e < HQL_RPAD) cp_async16(&ring[RING + e], &myv[base + e]);
+      }
+    cp_async_commit();
+    ++t_issued;
+  };
+  while (t_issued < ntiles && t_issued < HQL_RTILES) issue();
+  for (int k = tid; k < d; k += NT) stau[k] = tau[mat * d + k];
+
+  cplx x[RPT];
+#pragma unroll
+  for (int jj = 0; jj < RPT; ++jj) {
+    const int i = 4 * jj + hh;
+    x[jj] = make_c((i < d && c < d) ? Zt[mat * dd + (size_t)i * d + c] : 0.0, 0.0);
+  }
+  __syncthreads();
+
+  size_t g = 0;  // stream position of v_k[2:]
+  for (int k = d - 2; k >= 0; --k) {
+    const int mk = d - k - 2;  // explicit entries (rows k+2 .. d-1)
+    const size_t need = g + (size_t)mk;
+    while ((size_t)t_landed * HQL_RTILE < need && t_landed < ntiles) {
+      cp_async_wait<0>();
+      __syncthreads();
+      t_landed = t_issued;
+      const int consumed = (int)(g / HQL_RTILE);
+      while (t_issued < ntiles && t_issued - consumed < HQL_RTILES - 1) issue();
+    }
+    const cplx t = stau[k];
+    // v for row i (i >= k+2) sits at vb[i]; this thread's rows are i = 4 jj + hh
+    const cplx *vb = ring + (int)(g % RING) - (k + 2) + hh;
+    // rows in blocks of 4 jj (16 rows): one uniform branch per block; blocks that lie
+    // entirely inside (k+1, d) run without per-row predicates
+    cplx u0 = make_c(0.0, 0.0), u1 = u0;
+#pragma unroll
+    for (int b = 0; b < RPT / 4; ++b) {
+      if (16 * b + 15 >= k + 1 && 16 * b < d) {
+        if (16 * b > k + 1 && 16 * b + 15 < d) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int J = 4 * b + q;
+            ccfma((q & 1) ? u1 : u0, vb[4 * J], x[J]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int J = 4 * b + q;
+            const int i = 4 * J + hh;
+            if (i > k + 1 && i < d)
+              ccfma((q & 1) ? u1 : u0, vb[4 * J], x[J]);
+            else if (i == k + 1)
+              u0 = cadd(u0, x[J]);
+          }
+        }
+      }
+    }
+    cplx u = cadd(u0, u1);
+    u.x += __shfl_xor_sync(0xffffffffu, u.x, 1);
+    u.y += __shfl_xor_sync(0xffffffffu, u.y, 1);
+    u.x += __shfl_xor_sync(0xffffffffu, u.x, 2);
+    u.y += __shfl_xor_sync(0xffffffffu, u.y, 2);
+    const cplx tu = cmul(t, u);
+#pragma unroll
+    for (int b = 0; b < RPT / 4; ++b) {
+      if (16 * b + 15 >= k + 1 && 16 * b < d) {
+        if (16 * b > k + 1 && 16 * b + 15 < d) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int J = 4 * b + q;
+            const cplx v = vb[4 * J];
+            x[J].x -= v.x * tu.x - v.y * tu.y;
+            x[J].y -= v.x * tu.y + v.y * tu.x;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int J = 4 * b + q;
+            const int i = 4 * J + hh;
+            if (i > k + 1 && i < d) {
+              const cplx v = vb[4 * J];
+              x[J].x -= v.x * tu.x - v.y * tu.y;
+              x[J].y -= v.x * tu.y + v.y * tu.x;
+            } else if (i == k + 1) {
+              x[J] = csub(x[J], tu);
+            }
+          }
+        }
+      }
+    }
+    g = need;
+  }
+  if (c < d) {
+#pragma unroll
+    for (int jj = 0; jj < RPT; ++jj) {
+      const int i = 4 * jj + hh;
+      if (i < d) U[mat * dd + (size_t)i * d + c] = x[jj];
+    }
+  }
+}
+
+inline size_t hql_reflect_smem(int D) {
+  return (HQL_RTILE * HQL_RTILES + 2 * HQL_RPAD + D) * sizeof(cplx) + 16;
 }
 
 inline size_t hql_apply_reg_smem(int swp_cap) {

@@ -58,7 +58,9 @@ struct musim_handle {
   void *stage = nullptr;
   size_t stage_bytes = 0;
   // options
-  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1;
+  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_overlap = 0;
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}, evIn = nullptr;
   // bookkeeping
   int64_t launches = 0;
   Profiler prof;
@@ -129,6 +131,12 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
   }
   else if (!strcmp(key, "gemm"))
     h->opt_gemm = value;
+  else if (!strcmp(key, "tridiag_reg"))  // 1: register-resident tridiagonalisation (d <= 96)
+    g_tridiag_reg = value != 0;
+  else if (!strcmp(key, "reflect"))  // 0: form Q in the tridiagonalisation kernel + GEMM back-transformation
+    g_reflect = value != 0;
+  else if (!strcmp(key, "overlap"))  // 0: single stream, no stage overlap
+    h->opt_overlap = value;
   else if (!strcmp(key, "polar_mma"))  // 1 (default): DMMA polarisation kernel, 0: vector-FMA version
     h->opt_polar_mma = value;
   else if (!strcmp(key, "sorted"))  // 1: keep eigenpairs sorted inside the pipeline (slower replay kernel)
@@ -254,6 +262,12 @@ extern "C" int musim_destroy(musim_handle *h) {
   cudaFree(h->exA);
   cudaFree(h->exg);
   h->prof.destroy();
+  if (h->st2) cudaStreamDestroy(h->st2);
+  for (int i = 0; i < 2; ++i) {
+    if (h->evA[i]) cudaEventDestroy(h->evA[i]);
+    if (h->evB[i]) cudaEventDestroy(h->evB[i]);
+  }
+  if (h->evIn) cudaEventDestroy(h->evIn);
   delete h;
   return MUSIM_OK;
 }
@@ -414,17 +428,69 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>(148, (int64_t)(24.0e9 / per_cfg));
   chunk = std::min<int64_t>(chunk, n_cfg);
   chunk = std::min<int64_t>(chunk, 65535);  // grid.y / grid.z limit of the batched kernels
+  // Two-stage software pipeline over launch groups: the tridiagonalisation (stage A) is a
+  // long chain of barrier-separated steps that leaves most of the SM idle (ncu: 22 % FP64,
+  // 64 registers/thread), so stage A of group i+1 runs on a second stream while the
+  // throughput-bound kernels of group i (QL replay, GEMMs, polarisation) fill the same SMs.
+  const bool overlap = h->opt_overlap != 0 && method == EIGH_HQL && n_cfg >= 4 * 148;
+  if (overlap && h->opt_chunk <= 0) chunk = std::min<int64_t>(chunk, (n_cfg + 3) / 4);
   int rc = ensure_ws(h, chunk, general);
   if (rc) return rc;
+  {
+    cudaError_t e = h->ews.ensure(method, d, chunk, overlap);
+    if (e != cudaSuccess) return set_err(h, MUSIM_ECUDA, std::string("eigh workspace: ") + cudaGetErrorString(e));
+  }
   CK(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
+  if (overlap && !h->st2) {
+    CK(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&h->evA[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->evB[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->evIn, cudaEventDisableTiming));
+  }
+  cudaStream_t stA = overlap ? h->st2 : st;
+  if (overlap) {
+    CK(cudaEventRecord(h->evIn, st));  // inputs (and the status reset) are ordered before stage A
+    CK(cudaStreamWaitEvent(stA, h->evIn, 0));
+  }
 
   const double d_other = (double)d / h->tab.dims[h->tab.muon_index];
-
-  for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
+  const int64_t nchunks = (n_cfg + chunk - 1) / chunk;
+  auto stageA = [&](int64_t ci) -> int {
+    const int64_t c0 = ci * chunk;
     const int64_t n = std::min(chunk, n_cfg - c0);
+    const int buf = overlap ? (int)(ci & 1) : 0;
+    if (overlap && ci >= 2) cudaStreamWaitEvent(stA, h->evB[buf], 0);  // buffer set free again
+    int r = launch_eigh_stageA(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->ews, buf, h->status,
+                               stA, &h->launches, &h->prof);
+    if (overlap) cudaEventRecord(h->evA[buf], stA);
+    return r;
+  };
+  if (overlap) {
+    rc = stageA(0);
+    if (rc == 0 && nchunks > 1) rc = stageA(1);
+    if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
+    if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
+  }
+
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int64_t c0 = ci * chunk;
+    const int64_t n = std::min(chunk, n_cfg - c0);
+    const int buf = overlap ? (int)(ci & 1) : 0;
     {
-      rc = launch_eigh(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->ews, h->status, st,
-                       &h->launches, &h->prof, h->opt_sorted != 0);
+      if (!overlap)
+        rc = stageA(ci);
+      else
+        rc = (int)cudaStreamWaitEvent(st, h->evA[buf], 0);
+      if (rc == 0)
+        rc = launch_eigh_stageB(method, d, n, h->lam, h->U, h->ews, buf, h->status, st, &h->launches, &h->prof,
+                                h->opt_sorted != 0);
+      if (overlap) {
+        // U is complete: the (d, e, Q) buffer set may be overwritten by stage A of group ci + 2
+        cudaEventRecord(h->evB[buf], st);
+        if (rc == 0 && ci + 2 < nchunks) rc = stageA(ci + 2);
+      }
       if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
       if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
     }
