@@ -3,6 +3,7 @@
 #include "eigh_hql.cuh"
 #include "eigh_jacobi.cuh"
 #include "eigh_tridiag_reg.cuh"
+#include "eigh_tridiag_rw.cuh"
 #include "profiler.cuh"
 #include "rotate.cuh"
 
@@ -12,6 +13,7 @@ namespace musim {
 
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
+static bool g_tridiag_rw = true;   // option "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96)
 static bool g_tridiag_reg = false;  // option "tridiag_reg": register-resident tridiagonalisation (slower)
 
 inline int pick_eigh(long opt, int d) {
@@ -122,7 +124,14 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
     const size_t smem = hql_tridiag_smem(d, g);
     if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
     ProfScope ps(prof, st, PH_EIGH_TRIDIAG);
-    if (d <= 96 && g_tridiag_reg) {
+    if (use_reflect(d) && g_tridiag_rw) {
+      if (d <= 32)
+        hql_tridiag_rw_kernel<32><<<(unsigned)n, 128, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+      else if (d <= 64)
+        hql_tridiag_rw_kernel<64><<<(unsigned)n, 256, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+      else
+        hql_tridiag_rw_kernel<96><<<(unsigned)n, 384, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+    } else if (d <= 96 && g_tridiag_reg) {
       // register-resident A (eigh_tridiag_reg.cuh): R = d rounded up to 32 / 64 / 96
       if (d <= 32) {
         const size_t sm = hql_tridiag_reg_smem<32>();
