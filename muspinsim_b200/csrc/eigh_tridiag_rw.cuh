@@ -80,24 +80,30 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
   // come from ALL warps in parallel (no serial owner section).
   auto publish_col = [&](int kc) {
     double xn = 0.0;
-    if (l16 == (kc & 15)) {
-      const int j1 = kc >> 4;
+    const int j1 = kc >> 4;  // column block (uniform)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        cplx v = a[i][0];
+    for (int jj = 0; jj < CJ; ++jj) {
+      if (jj == j1 && l16 == (kc & 15)) {
 #pragma unroll
-        for (int jj = 1; jj < CJ; ++jj)
-          if (jj == j1) v = a[i][jj];
-        const int r = r0 + i;
-        sx[kc & 1][r] = v;
-        if (r >= kc + 2 && r < d) xn += cnorm2(v);
-        if (r == kc) dout[cfg * d + kc] = v.x;
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + i;
+          const cplx v = a[i][jj];
+          // rows <= kc are dead: publish zeros there so the mat-vec needs no masks
+          // (row kc+1 carries alpha, the only entry the mat-vec replaces)
+          sx[kc & 1][r] = (r > kc) ? v : make_c(0.0, 0.0);
+          if (r >= kc + 2 && r < d) xn += cnorm2(v);
+          if (r == kc) dout[cfg * d + kc] = v.x;
+        }
       }
     }
     xn += __shfl_xor_sync(0xffffffffu, xn, 16);
     if (lane == (kc & 15)) sxn[kc & 1][w] = xn;
   };
 
+  for (int i = tid; i < D; i += 4 * D) {
+    sv[i] = make_c(0.0, 0.0);
+    sp[i] = make_c(0.0, 0.0);
+  }
   publish_col(0);
   for (int k = 0; k < d - 1; ++k) {
     __syncthreads();  // #1: column k and its partial norms are visible
@@ -144,9 +150,8 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
       for (int jj = 0; jj < CJ; ++jj) {
         if (16 * jj + 15 > k && 16 * jj < d) {  // block has columns > k (uniform)
           const int c = l16 + 16 * jj;
-          cplx xv = x[c];
-          if (c == k + 1) xv = xp0;  // the only term that needs the scalar chain
-          if (c <= k) xv = make_c(0.0, 0.0);
+          cplx xv = x[c];  // zero for c <= k (publish_col)
+          if (jj == ((k + 1) >> 4) && c == k + 1) xv = xp0;  // the only term that needs the scalar chain
 #pragma unroll
           for (int i = 0; i < 4; ++i) cfma(y[i], a[i][jj], xv);
         }
@@ -192,20 +197,17 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
       cplx vr[4], wr[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = r0 + i;
-        const bool act = r > k;
-        vr[i] = act ? sv[r] : make_c(0.0, 0.0);
-        const cplx pr = act ? sp[r] : make_c(0.0, 0.0);
-        wr[i] = cadd(pr, cmul(a2, vr[i]));
+        // rows / columns <= k are dead (never read again): they may take the stale, bounded
+        // v / p values without masking
+        vr[i] = sv[r0 + i];
+        wr[i] = cadd(sp[r0 + i], cmul(a2, vr[i]));
       }
 #pragma unroll
       for (int jj = 0; jj < CJ; ++jj) {
         if (16 * jj + 15 > k && 16 * jj < d) {
           const int c = l16 + 16 * jj;
-          const bool act = c > k;
-          const cplx vc = act ? sv[c] : make_c(0.0, 0.0);
-          const cplx pc = act ? sp[c] : make_c(0.0, 0.0);
-          const cplx wc = cadd(pc, cmul(a2, vc));
+          const cplx vc = sv[c];
+          const cplx wc = cadd(sp[c], cmul(a2, vc));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             cplx &e = a[i][jj];
