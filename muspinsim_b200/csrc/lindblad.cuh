@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "profiler.cuh"
 #include "rotate.cuh"
+#include "zgemm_dmma.cuh"
 
 namespace musim {
 
@@ -517,9 +518,11 @@ template <int EPI>
 inline void lind_gemm(int n, int64_t cnt, const cplx *A, const cplx *B, const cplx *D, cplx *C, cudaStream_t st,
                       int64_t *launches) {
   const size_t nn = (size_t)n * n;
+  ++*launches;
+  MuonObs none = {1, 0};
+  if (launch_zgemm_dmma<false, EPI, false>(n, cnt, A, nn, B, nn, C, 1.0, D, none, nullptr, st)) return;
   dim3 grid((n + 31) / 32, (n + 31) / 32, (unsigned)cnt);
   cgemm_batched_kernel<false, EPI><<<grid, 256, 0, st>>>(n, A, nn, B, nn, C, 1.0, D);
-  ++*launches;
 }
 
 // exp(scale * L) for a batch: result pointer returned (one of the workspace buffers, not X..X4).

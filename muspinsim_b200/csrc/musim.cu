@@ -24,6 +24,7 @@
 #include "peak.cuh"
 #include "polar.cuh"
 #include "rotate.cuh"
+#include "zgemm_dmma.cuh"
 
 using namespace musim;
 
@@ -36,6 +37,7 @@ struct musim_handle {
   SpinTable tab;
   int n_diss = 0;
   bool thermal_ok = true;
+  MuonObs mu = {1, 0};
   std::vector<int> diss_spin;
   std::vector<double> diss_rate;
   // device constants
@@ -191,6 +193,34 @@ extern "C" int musim_create(musim_handle **out, int device, int d, int n_spins, 
   CK(cudaMemcpy(h->H0, H0, dd * sizeof(cplx), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->Z, Z, 3 * dd * sizeof(cplx), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->M, M, 3 * dd * sizeof(cplx), cudaMemcpyHostToDevice));
+  // Is the observable the muon operator S_mu^a (x) 1 (MuonSpinSystem.muon_operator)?  Then O U
+  // has two non-zeros per row and is formed on the fly inside the GEMM (zgemm_dmma.cuh).
+  if (dims[muon_index] == 2) {
+    int stride = 1;
+    for (int i = muon_index + 1; i < n_spins; ++i) stride *= dims[i];
+    bool ok = true;
+    const cplx *Mc = reinterpret_cast<const cplx *>(M);
+    for (int r = 0; r < d && ok; ++r)
+      for (int c = 0; c < d && ok; ++c) {
+        const int mr = (r / stride) & 1, mc = (c / stride) & 1;
+        const bool same_rest = (r - mr * stride) == (c - mc * stride);
+        cplx e[3] = {make_c(0, 0), make_c(0, 0), make_c(0, 0)};
+        if (same_rest) {
+          if (mr != mc) {
+            e[0] = make_c(0.5, 0.0);                       // Sx
+            e[1] = make_c(0.0, mr == 0 ? -0.5 : 0.5);      // Sy: (0,1) = -i/2, (1,0) = +i/2
+          } else {
+            e[2] = make_c(mr == 0 ? 0.5 : -0.5, 0.0);      // Sz
+          }
+        }
+        for (int a = 0; a < 3; ++a) {
+          const cplx v = Mc[(size_t)a * dd + (size_t)r * d + c];
+          if (fabs(v.x - e[a].x) > 1e-14 || fabs(v.y - e[a].y) > 1e-14) ok = false;
+        }
+      }
+    h->mu.stride = stride;
+    h->mu.enabled = ok ? 1 : 0;
+  }
   // pair table (i <= j)
   if (d <= 65535) {
     std::vector<PairIdx> pt;
@@ -496,17 +526,35 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
       if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
     }
+    const bool mma = (h->opt_gemm != 1) && d <= 96;  // FP64 tensor-pipe GEMMs (option "gemm" = 1: vector-FMA kernels)
     {
       ProfScope pt(&h->prof, st, PH_ROTATE);
-      dim3 g1((unsigned)((dd + 255) / 256), (unsigned)n);
-      form_obs_kernel<<<g1, 256, 0, st>>>(d, h->M, p + 3 * c0, h->Oc);
-      ++h->launches;
-      launch_gemm<false, 0>(d, n, h->Oc, dd, h->U, dd, h->T1, 1.0, st, &h->launches);
-      if (!general) {
-        // fast path: W = |U^H O U|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
-        launch_gemm<true, 1>(d, n, h->U, dd, h->T1, dd, h->W, 1.0 / d_other, st, &h->launches);
+      const double sc = 1.0 / d_other;
+      if (mma && h->mu.enabled) {
+        // O' = U^H (O U) with O U formed on the fly from the muon operator's two non-zeros per row
+        if (!general)  // fast path: W = |O'|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
+          launch_zgemm_dmma<true, 1, true>(d, n, h->U, dd, h->U, dd, h->W, sc, nullptr, h->mu, p + 3 * c0, st);
+        else
+          launch_zgemm_dmma<true, 0, true>(d, n, h->U, dd, h->U, dd, h->Y, 1.0, nullptr, h->mu, p + 3 * c0, st);
+        ++h->launches;
       } else {
-        launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->Y, 1.0, st, &h->launches);
+        dim3 g1((unsigned)((dd + 255) / 256), (unsigned)n);
+        form_obs_kernel<<<g1, 256, 0, st>>>(d, h->M, p + 3 * c0, h->Oc);
+        ++h->launches;
+        if (mma) {
+          launch_zgemm_dmma<false, 0, false>(d, n, h->Oc, dd, h->U, dd, h->T1, 1.0, nullptr, h->mu, nullptr, st);
+          if (!general)
+            launch_zgemm_dmma<true, 1, false>(d, n, h->U, dd, h->T1, dd, h->W, sc, nullptr, h->mu, nullptr, st);
+          else
+            launch_zgemm_dmma<true, 0, false>(d, n, h->U, dd, h->T1, dd, h->Y, 1.0, nullptr, h->mu, nullptr, st);
+          h->launches += 2;
+        } else {
+          launch_gemm<false, 0>(d, n, h->Oc, dd, h->U, dd, h->T1, 1.0, st, &h->launches);
+          if (!general)
+            launch_gemm<true, 1>(d, n, h->U, dd, h->T1, dd, h->W, sc, st, &h->launches);
+          else
+            launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->Y, 1.0, st, &h->launches);
+        }
       }
     }
     if (general) {
@@ -520,11 +568,18 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
         rs = dd;
       }
       ProfScope pt(&h->prof, st, PH_ROTATE);
-      launch_gemm<false, 0>(d, n, R, rs, h->U, dd, h->T1, 1.0, st, &h->launches);
-      launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->X, 1.0, st, &h->launches);
-      const size_t tot = (size_t)n * dd;
-      weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, h->X, h->Y, h->W);
-      ++h->launches;
+      if (mma) {
+        // rho' = U^H (rho0 U);  W = rho' .* conj(O')  in the epilogue
+        launch_zgemm_dmma<false, 0, false>(d, n, R, rs, h->U, dd, h->T1, 1.0, nullptr, h->mu, nullptr, st);
+        launch_zgemm_dmma<true, 3, false>(d, n, h->U, dd, h->T1, dd, h->W, 1.0, h->Y, h->mu, nullptr, st);
+        h->launches += 2;
+      } else {
+        launch_gemm<false, 0>(d, n, R, rs, h->U, dd, h->T1, 1.0, st, &h->launches);
+        launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->X, 1.0, st, &h->launches);
+        const size_t tot = (size_t)n * dd;
+        weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, h->X, h->Y, h->W);
+        ++h->launches;
+      }
     }
     if (integral) {
       ProfScope pt(&h->prof, st, PH_INTEGRAL);

@@ -1,0 +1,186 @@
+// zgemm_dmma.cuh -- batched complex FP64 GEMM on the FP64 tensor pipe (mma.sync m8n8k4 f64).
+//
+//   C[c] = op(A[c]) * B[c]      all d x d row-major complex128, op = identity or conj-transpose
+//
+// Replaces the dense `@` products of Operator.basis_change (/root/reference/muspinsim/
+// spinop.py:349-350) and of Hamiltonian.fast_evolve (hamiltonian.py:207).  ncu on the
+// vector-FMA version (rotate.cuh, cgemm_batched_kernel): 81 % LSU, 50 % FP64 -- a 2x2 register
+// tile moves 4 B of shared memory per FMA.  Here a warp owns a 32 x 16 complex output tile as
+// 8 DMMA accumulator fragments x (re, im) = 64 registers; one k4-step loads 8 A- and 4
+// B-fragments (12 LDS.64) for 32 DMMAs = 8192 FMAs.  Operands are staged as separate re / im planes with a leading
+// dimension = 4 (mod 16) so that every fragment load is bank-conflict free.
+//
+// B_MUON: B is not read from memory but formed on the fly as O U with the muon observable
+// O = sum_a p_a S_mu^a (x) 1 (two non-zeros per row: spinsys.py:707-732), which removes the
+// T = O U product and its HBM round trip from the fast path.
+// EPI: 0 store C; 1 store (|C|^2 scale, 0); 2 store C + D; 3 store C .* conj(D).
+#pragma once
+#include "common.cuh"
+#include "polar.cuh"  // dmma884
+
+namespace musim {
+
+#define ZG_KS 16
+
+struct MuonObs {   // O = [[pz/2, (px - i py)/2], [(px + i py)/2, -pz/2]] on the muon index
+  int stride;      // product of the dimensions of the spins after the muon
+  int enabled;
+};
+
+template <int T, bool CONJ_A, int EPI, bool B_MUON>
+__global__ void __launch_bounds__(64 * T * T, (T == 3 ? 1 : (T == 2 ? 2 : 8)))
+zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx *__restrict__ B,
+                  size_t b_stride, cplx *C, double scale, const cplx *D, MuonObs mu,
+                  const double *__restrict__ pvec) {
+  constexpr int DP = 32 * T;     // padded dimension
+  constexpr int LD = DP + 4;     // = 4 (mod 16)
+  constexpr int LDK = ZG_KS + 4; // for the non-transposed A slab [m][k]
+  constexpr int NT = 64 * T * T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sAr = reinterpret_cast<double *>(smem_raw);
+  double *sAi = sAr + (CONJ_A ? ZG_KS * LD : DP * LDK);
+  double *sBr = sAi + (CONJ_A ? ZG_KS * LD : DP * LDK);
+  double *sBi = sBr + ZG_KS * LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / (2 * T), wn = warp % (2 * T);  // this warp's 32 (rows) x 16 (columns) tile
+  const int fr = lane >> 2, fk = lane & 3;
+  const size_t cfg = blockIdx.x;
+  const size_t dd = (size_t)d * d;
+  const cplx *Ab = A + cfg * a_stride;
+  const cplx *Bb = B + cfg * b_stride;
+  double px = 0, py = 0, pz = 0;
+  if (B_MUON) {
+    px = 0.5 * pvec[cfg * 3];
+    py = 0.5 * pvec[cfg * 3 + 1];
+    pz = 0.5 * pvec[cfg * 3 + 2];
+  }
+  double cr[4][2][2], ci[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+
+  for (int k0 = 0; k0 < d; k0 += ZG_KS) {
+    // ---- stage the K slab (planar re / im) ----
+    if (CONJ_A) {
+      for (int e = tid; e < ZG_KS * DP; e += NT) {
+        const int k = e / DP, m = e - k * DP;
+        cplx v = make_c(0.0, 0.0);
+        if (k0 + k < d && m < d) v = Ab[(size_t)(k0 + k) * d + m];
+        sAr[k * LD + m] = v.x;
+        sAi[k * LD + m] = v.y;
+      }
+    } else {
+      for (int e = tid; e < ZG_KS * DP; e += NT) {
+        const int m = e / ZG_KS, k = e - m * ZG_KS;
+        cplx v = make_c(0.0, 0.0);
+        if (k0 + k < d && m < d) v = Ab[(size_t)m * d + k0 + k];
+        sAr[m * LDK + k] = v.x;
+        sAi[m * LDK + k] = v.y;
+      }
+    }
+    for (int e = tid; e < ZG_KS * DP; e += NT) {
+      const int k = e / DP, n = e - k * DP;
+      cplx v = make_c(0.0, 0.0);
+      const int kk = k0 + k;
+      if (kk < d && n < d) {
+        if (B_MUON) {
+          // (O U)[kk][n] = o_diag U[kk][n] + o_off U[kk ^ muon][n]
+          const int m = (kk / mu.stride) & 1;
+          const cplx u0 = Bb[(size_t)kk * d + n];
+          const cplx u1 = Bb[(size_t)(m ? kk - mu.stride : kk + mu.stride) * d + n];
+          const double dg = m ? -pz : pz;
+          const double oy = m ? py : -py;  // o_off = px -/+ i py
+          v.x = dg * u0.x + px * u1.x - oy * u1.y;
+          v.y = dg * u0.y + px * u1.y + oy * u1.x;
+        } else {
+          v = Bb[(size_t)kk * d + n];
+        }
+      }
+      sBr[k * LD + n] = v.x;
+      sBi[k * LD + n] = v.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < ZG_KS; ks += 4) {
+      double ar[4], ai[4], br[2], bi[2], nb[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = wm * 32 + i * 8 + fr;
+        if (CONJ_A) {
+          ar[i] = sAr[(ks + fk) * LD + m];
+          ai[i] = -sAi[(ks + fk) * LD + m];  // conj
+        } else {
+          ar[i] = sAr[m * LDK + ks + fk];
+          ai[i] = sAi[m * LDK + ks + fk];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = wn * 16 + j * 8 + fr;
+        br[j] = sBr[(ks + fk) * LD + n];
+        bi[j] = sBi[(ks + fk) * LD + n];
+        nb[j] = -bi[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);  // + Ar Br
+          dmma884(cr[i][j][0], cr[i][j][1], ai[i], nb[j]);  // - Ai Bi
+          dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);  // + Ar Bi
+          dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);  // + Ai Br
+        }
+    }
+    __syncthreads();
+  }
+  // ---- epilogue ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = wm * 32 + i * 8 + fr;
+      const int n = wn * 16 + j * 8 + fk * 2;
+      if (m < d) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (n + e < d) {
+            cplx v = make_c(cr[i][j][e], ci[i][j][e]);
+            const size_t idx = cfg * dd + (size_t)m * d + n + e;
+            if (EPI == 1) v = make_c(cnorm2(v) * scale, 0.0);
+            if (EPI == 2) v = cadd(v, D[idx]);
+            if (EPI == 3) v = cmulc(v, D[idx]);
+            C[idx] = v;
+          }
+        }
+      }
+    }
+}
+
+template <int T, bool CONJ_A>
+inline size_t zgemm_dmma_smem() {
+  constexpr int DP = 32 * T, LD = DP + 4, LDK = ZG_KS + 4;
+  return (2 * (CONJ_A ? ZG_KS * LD : DP * LDK) + 2 * ZG_KS * LD) * sizeof(double);
+}
+
+// host launcher; returns false if d is outside the tensor-pipe kernel's range (d <= 96)
+template <bool CONJ_A, int EPI, bool B_MUON>
+inline bool launch_zgemm_dmma(int d, int64_t n, const cplx *A, size_t as, const cplx *B, size_t bs, cplx *C,
+                              double scale, const cplx *D, MuonObs mu, const double *pvec, cudaStream_t st) {
+  if (d > 96) return false;
+  if (d <= 32) {
+    const size_t sm = zgemm_dmma_smem<1, CONJ_A>();
+    zgemm_dmma_kernel<1, CONJ_A, EPI, B_MUON><<<(unsigned)n, 64, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec);
+  } else if (d <= 64) {
+    const size_t sm = zgemm_dmma_smem<2, CONJ_A>();
+    cudaFuncSetAttribute(zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON><<<(unsigned)n, 256, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec);
+  } else {
+    const size_t sm = zgemm_dmma_smem<3, CONJ_A>();
+    cudaFuncSetAttribute(zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON><<<(unsigned)n, 576, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec);
+  }
+  return true;
+}
+
+}  // namespace musim
