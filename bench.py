@@ -376,6 +376,8 @@ def main():
     d2h = out_host.nbytes
 
     if rank != 0:
+        if comm is not None:
+            comm.close()
         return
     # ---- roofline of the dominant kernel ----
     peak_dfma = _lib.fp64_peak(local, 0)
@@ -419,6 +421,8 @@ def main():
         "cpu_baseline": cb,
     }
     print(json.dumps(line))
+    if comm is not None:
+        comm.close()
 
 
 if __name__ == "__main__":

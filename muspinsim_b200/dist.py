@@ -23,11 +23,18 @@ class Communicator:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29512")
+            kw = {}
+            if backend == "nccl":
+                local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
+                torch.cuda.set_device(local)
+                kw["device_id"] = torch.device("cuda", local)
             dist.init_process_group(
                 backend=backend,
                 rank=int(os.environ.get("RANK", "0")),
                 world_size=int(os.environ.get("WORLD_SIZE", "1")),
+                **kw,
             )
+            self._owns_group = True
         self.backend = dist.get_backend()
         self.rank = dist.get_rank()
         self.size = dist.get_world_size()
@@ -35,6 +42,11 @@ class Communicator:
             device = int(os.environ.get("LOCAL_RANK", "0"))
             torch.cuda.set_device(device)
         self.device = device
+
+    def close(self):
+        if getattr(self, "_owns_group", False) and self._dist.is_initialized():
+            self._dist.destroy_process_group()
+            self._owns_group = False
 
     @property
     def is_root(self):
