@@ -77,12 +77,12 @@ def algorithmic_flops(d, nt, mode):
 def kernel_flops(name, d, nt):
     npairs = d * (d - 1) / 2
     return {
-        "eigh_tridiag": (16.0 / 3 + 16.0 / 3) * d**3,  # zhetrd + zungtr
+        "eigh_tridiag": (16.0 / 3) * d**3,  # zhetrd
         "eigh_tql": 30.0 * 1.2 * d * d,
         "eigh_apply": 6.0 * 1.2 * d**3,  # real Givens on d rows, ~1.2 d^2 rotations
-        "eigh_back": 4.0 * d**3,  # complex x real GEMM
+        "eigh_back": (16.0 / 3) * d**3,  # zunmtr: reflectors applied to the real eigenvector matrix
         "eigh_jacobi": 16.0 * d**3,
-        "rotate": 2 * 8.0 * d**3,  # two complex GEMMs (fast path)
+        "rotate": 8.0 * d**3,  # one complex GEMM (fast path; O U is formed on the fly)
         "polar": 10.0 * nt * npairs,
     }.get(name, 0.0)
 
