@@ -228,16 +228,16 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     if (use_reflect(d)) {
       if (d <= 32) {
         const size_t sm = hql_reflect_smem(32);
-        cudaFuncSetAttribute(hql_reflect_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_reflect_kernel<32><<<(unsigned)n, 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        cudaFuncSetAttribute(hql_reflect_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_reflect_kernel<32, 4><<<(unsigned)n, 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
       } else if (d <= 64) {
         const size_t sm = hql_reflect_smem(64);
-        cudaFuncSetAttribute(hql_reflect_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_reflect_kernel<64><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        cudaFuncSetAttribute(hql_reflect_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_reflect_kernel<64, 4><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
       } else {
         const size_t sm = hql_reflect_smem(96);
-        cudaFuncSetAttribute(hql_reflect_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_reflect_kernel<96><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        cudaFuncSetAttribute(hql_reflect_kernel<96, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_reflect_kernel<96, 8><<<(unsigned)n, 768, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
       }
     } else {
       dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);

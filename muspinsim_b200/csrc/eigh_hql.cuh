@@ -720,21 +720,23 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
   X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
       X(17) X(18) X(19) X(20) X(21) X(22) X(23)
 
-// Thread (c, h) = (tid / 4, tid % 4) holds rows i = 4 jj + h of column c (D/4 complex numbers =
-// D registers); the four partial dot products of a column are combined with two shuffles.
-template <int D>
-__global__ void __launch_bounds__(4 * D)
+// Thread (c, h) = (tid / TPC, tid % TPC) holds rows i = TPC jj + h of column c (D/TPC complex
+// numbers); the TPC partial dot products of a column are combined with log2(TPC) shuffles.
+// TPC = 8 at D = 96: 768 threads = 24 warps per SM instead of 12 -- the kernel is latency bound.
+template <int D, int TPC>
+__global__ void __launch_bounds__(TPC *D)
 hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__ Vp, size_t vcap,
                    const cplx *__restrict__ tau, cplx *__restrict__ U) {
-  constexpr int RPT = D / 4;  // rows per thread
-  static_assert(RPT % 4 == 0 || RPT == 8, "rows per thread in blocks of 4");
-  constexpr int NT = 4 * D;
+  constexpr int RPT = D / TPC;  // rows per thread
+  static_assert(RPT % 4 == 0, "rows per thread in blocks of 4");
+  constexpr int NT = TPC * D;
+  constexpr int BR = 4 * TPC;  // rows covered by a block of 4 jj
   extern __shared__ __align__(16) unsigned char refl_smem[];
   constexpr int RING = HQL_RTILE * HQL_RTILES;
   cplx *ring = reinterpret_cast<cplx *>(refl_smem) + HQL_RPAD;
   cplx *stau = ring + RING + HQL_RPAD;  // [D]
   const int tid = threadIdx.x;
-  const int c = tid >> 2, hh = tid & 3;
+  const int c = tid / TPC, hh = tid % TPC;
   const size_t mat = blockIdx.x;
   const size_t dd = (size_t)d * d;
   const cplx *myv = Vp + mat * vcap;
@@ -758,7 +760,7 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
   cplx x[RPT];
 #pragma unroll
   for (int jj = 0; jj < RPT; ++jj) {
-    const int i = 4 * jj + hh;
+    const int i = TPC * jj + hh;
     x[jj] = make_c((i < d && c < d) ? Zt[mat * dd + (size_t)i * d + c] : 0.0, 0.0);
   }
   __syncthreads();
@@ -775,27 +777,27 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
       while (t_issued < ntiles && t_issued - consumed < HQL_RTILES - 1) issue();
     }
     const cplx t = stau[k];
-    // v for row i (i >= k+2) sits at vb[i]; this thread's rows are i = 4 jj + hh
+    // v for row i (i >= k+2) sits at vb0[i]; this thread's rows are i = TPC jj + hh
     const cplx *vb = ring + (int)(g % RING) - (k + 2) + hh;
-    // rows in blocks of 4 jj (16 rows): one uniform branch per block; blocks that lie
-    // entirely inside (k+1, d) run without per-row predicates
+    // rows in blocks of 4 jj: one uniform branch per block; blocks that lie entirely inside
+    // (k+1, d) run without per-row predicates
     cplx u0 = make_c(0.0, 0.0), u1 = u0;
 #pragma unroll
     for (int b = 0; b < RPT / 4; ++b) {
-      if (16 * b + 15 >= k + 1 && 16 * b < d) {
-        if (16 * b > k + 1 && 16 * b + 15 < d) {
+      if (BR * b + BR - 1 >= k + 1 && BR * b < d) {
+        if (BR * b > k + 1 && BR * b + BR - 1 < d) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int J = 4 * b + q;
-            ccfma((q & 1) ? u1 : u0, vb[4 * J], x[J]);
+            ccfma((q & 1) ? u1 : u0, vb[TPC * J], x[J]);
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int J = 4 * b + q;
-            const int i = 4 * J + hh;
+            const int i = TPC * J + hh;
             if (i > k + 1 && i < d)
-              ccfma((q & 1) ? u1 : u0, vb[4 * J], x[J]);
+              ccfma((q & 1) ? u1 : u0, vb[TPC * J], x[J]);
             else if (i == k + 1)
               u0 = cadd(u0, x[J]);
           }
@@ -803,19 +805,20 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
       }
     }
     cplx u = cadd(u0, u1);
-    u.x += __shfl_xor_sync(0xffffffffu, u.x, 1);
-    u.y += __shfl_xor_sync(0xffffffffu, u.y, 1);
-    u.x += __shfl_xor_sync(0xffffffffu, u.x, 2);
-    u.y += __shfl_xor_sync(0xffffffffu, u.y, 2);
+#pragma unroll
+    for (int o = 1; o < TPC; o <<= 1) {
+      u.x += __shfl_xor_sync(0xffffffffu, u.x, o);
+      u.y += __shfl_xor_sync(0xffffffffu, u.y, o);
+    }
     const cplx tu = cmul(t, u);
 #pragma unroll
     for (int b = 0; b < RPT / 4; ++b) {
-      if (16 * b + 15 >= k + 1 && 16 * b < d) {
-        if (16 * b > k + 1 && 16 * b + 15 < d) {
+      if (BR * b + BR - 1 >= k + 1 && BR * b < d) {
+        if (BR * b > k + 1 && BR * b + BR - 1 < d) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int J = 4 * b + q;
-            const cplx v = vb[4 * J];
+            const cplx v = vb[TPC * J];
             x[J].x -= v.x * tu.x - v.y * tu.y;
             x[J].y -= v.x * tu.y + v.y * tu.x;
           }
@@ -823,9 +826,9 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int J = 4 * b + q;
-            const int i = 4 * J + hh;
+            const int i = TPC * J + hh;
             if (i > k + 1 && i < d) {
-              const cplx v = vb[4 * J];
+              const cplx v = vb[TPC * J];
               x[J].x -= v.x * tu.x - v.y * tu.y;
               x[J].y -= v.x * tu.y + v.y * tu.x;
             } else if (i == k + 1) {
@@ -840,7 +843,7 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
   if (c < d) {
 #pragma unroll
     for (int jj = 0; jj < RPT; ++jj) {
-      const int i = 4 * jj + hh;
+      const int i = TPC * jj + hh;
       if (i < d) U[mat * dd + (size_t)i * d + c] = x[jj];
     }
   }
