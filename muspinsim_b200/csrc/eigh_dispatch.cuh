@@ -4,6 +4,7 @@
 #include "eigh_jacobi.cuh"
 #include "eigh_tridiag_reg.cuh"
 #include "eigh_tridiag_rw.cuh"
+#include "eigh_tridiag_warp.cuh"
 #include "profiler.cuh"
 #include "rotate.cuh"
 
@@ -13,6 +14,7 @@ namespace musim {
 
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
+static bool g_tridiag_warp = true; // option "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
 static bool g_tridiag_rw = true;   // option "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96)
 static bool g_tridiag_reg = false;  // option "tridiag_reg": register-resident tridiagonalisation (slower)
 
@@ -124,7 +126,12 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
     const size_t smem = hql_tridiag_smem(d, g);
     if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
     ProfScope ps(prof, st, PH_EIGH_TRIDIAG);
-    if (use_reflect(d) && g_tridiag_rw) {
+    if (use_reflect(d) && g_tridiag_warp && d <= 32) {
+      const size_t sm = hql_tridiag_warp_smem(d);
+      cudaFuncSetAttribute(hql_tridiag_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      hql_tridiag_warp_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
+          d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+    } else if (use_reflect(d) && g_tridiag_rw) {
       if (d <= 32)
         hql_tridiag_rw_kernel<32><<<(unsigned)n, 128, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
       else if (d <= 64)
@@ -206,7 +213,7 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   const int ath = std::min(128, (d + 31) & ~31);
   if (!sorted && d <= 96) {
     // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
-    const size_t rsmem = hql_apply_reg_smem(ws.swp_cap);
+    const size_t rsmem = hql_apply_reg_smem(d <= 32 ? 32 : (d <= 64 ? 64 : 96), ws.swp_cap);
     ProfScope ps(prof, st, PH_EIGH_APPLY);
     if (d <= 32) {
       cudaFuncSetAttribute(hql_apply_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
@@ -228,8 +235,13 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     if (use_reflect(d)) {
       if (d <= 32) {
         const size_t sm = hql_reflect_smem(32);
-        cudaFuncSetAttribute(hql_reflect_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_reflect_kernel<32, 4><<<(unsigned)n, 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        if (d <= 24) {  // one thread per column (warp per matrix): the dot products are thread-local
+          cudaFuncSetAttribute(hql_reflect_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          hql_reflect_kernel<32, 1><<<(unsigned)n, 32, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        } else {
+          cudaFuncSetAttribute(hql_reflect_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          hql_reflect_kernel<32, 4><<<(unsigned)n, 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        }
       } else if (d <= 64) {
         const size_t sm = hql_reflect_smem(64);
         cudaFuncSetAttribute(hql_reflect_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

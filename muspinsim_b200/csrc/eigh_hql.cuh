@@ -593,9 +593,10 @@ hql_apply_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
 // traffic for Zt at all -- the shared-memory version above is LSU-bound (ncu: 65 % LSU, 21 %
 // FP64) -- only the broadcast read of (c, s) from the cp.async ring remains.
 // ---------------------------------------------------------------------------------------
-#define HQL_RTILE 512
+// ring geometry: 4 tiles of 512 (d > 32) or 128 (d <= 32) entries; D guard entries in front of
+// the ring and D mirrored entries behind it (a sweep / reflector has < D entries)
+#define HQL_RTILE_OF(D) ((D) <= 32 ? 128 : 512)
 #define HQL_RTILES 4
-#define HQL_RPAD 96  // guard entries in front of the ring and mirrored entries behind it
 
 template <int D>
 __global__ void __maxnreg__(224)
@@ -603,6 +604,7 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
                      const SweepIdx *__restrict__ swp, int swp_cap, const int *__restrict__ nswp,
                      double *__restrict__ Zt) {
   extern __shared__ __align__(16) unsigned char apply_smem[];
+  constexpr int HQL_RTILE = HQL_RTILE_OF(D), HQL_RPAD = D;
   constexpr int RING = HQL_RTILE * HQL_RTILES;
   // [RPAD guard][RING][RPAD mirror of the first entries]: a sweep's <= 95 rotations starting
   // anywhere in the ring are contiguous, so every (c, s) load is base + immediate offset
@@ -732,6 +734,7 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
   constexpr int NT = TPC * D;
   constexpr int BR = 4 * TPC;  // rows covered by a block of 4 jj
   extern __shared__ __align__(16) unsigned char refl_smem[];
+  constexpr int HQL_RTILE = HQL_RTILE_OF(D), HQL_RPAD = D;
   constexpr int RING = HQL_RTILE * HQL_RTILES;
   cplx *ring = reinterpret_cast<cplx *>(refl_smem) + HQL_RPAD;
   cplx *stau = ring + RING + HQL_RPAD;  // [D]
@@ -850,11 +853,11 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
 }
 
 inline size_t hql_reflect_smem(int D) {
-  return (HQL_RTILE * HQL_RTILES + 2 * HQL_RPAD + D) * sizeof(cplx) + 16;
+  return (HQL_RTILE_OF(D) * HQL_RTILES + 2 * D + D) * sizeof(cplx) + 16;
 }
 
-inline size_t hql_apply_reg_smem(int swp_cap) {
-  return (HQL_RTILE * HQL_RTILES + 2 * HQL_RPAD) * sizeof(double2) + (size_t)swp_cap * sizeof(SweepIdx) + 16;
+inline size_t hql_apply_reg_smem(int D, int swp_cap) {
+  return (HQL_RTILE_OF(D) * HQL_RTILES + 2 * D) * sizeof(double2) + (size_t)swp_cap * sizeof(SweepIdx) + 16;
 }
 
 inline size_t hql_apply_smem(int d, int swp_cap) {

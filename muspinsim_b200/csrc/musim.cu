@@ -135,6 +135,8 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->opt_gemm = value;
   else if (!strcmp(key, "tridiag_reg"))  // 1: register-resident tridiagonalisation (d <= 96)
     g_tridiag_reg = value != 0;
+  else if (!strcmp(key, "tridiag_warp"))  // 0: CTA-per-matrix kernels also for d <= 32
+    g_tridiag_warp = value != 0;
   else if (!strcmp(key, "tridiag_rw"))  // 0: shared-memory tridiagonalisation kernel
     g_tridiag_rw = value != 0;
   else if (!strcmp(key, "reflect"))  // 0: form Q in the tridiagonalisation kernel + GEMM back-transformation
