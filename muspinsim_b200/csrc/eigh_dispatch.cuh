@@ -132,12 +132,13 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
       hql_tridiag_warp_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
           d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
     } else if (use_reflect(d) && g_tridiag_rw) {
-      if (d <= 32)
+      if (d <= 32) {
         hql_tridiag_rw_kernel<32><<<(unsigned)n, 128, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
-      else if (d <= 64)
+      } else if (d <= 64) {
         hql_tridiag_rw_kernel<64><<<(unsigned)n, 256, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
-      else
+      } else {
         hql_tridiag_rw_kernel<96><<<(unsigned)n, 384, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+      }
     } else if (d <= 96 && g_tridiag_reg) {
       // register-resident A (eigh_tridiag_reg.cuh): R = d rounded up to 32 / 64 / 96
       if (d <= 32) {

@@ -5,7 +5,7 @@
 // cycles: 50 % LSU, 22 % FP64, barrier + latency stalls (8 barriers per step).  The first
 // register-resident attempt (eigh_tridiag_reg.cuh: a thread owns one row across 4 column
 // groups) still needs 4 barriers per step and was slower.  Here:
-//   * warp w owns rows 8w .. 8w+7 completely: half-warp `hf` holds 4 of them, lane l16 the
+//   * a warp owns 8 rows completely: half-warp `hf` holds 4 of them, lane l16 the
 //     columns l16 + 16 jj.  The mat-vec y = A x' is then WARP-LOCAL (butterfly reduction over
 //     the 16 lanes that share a row), no barrier;
 //   * p = tau A v, v and the warp's share of p^H v are published, barrier #2, and every thread
@@ -14,7 +14,7 @@
 //     share of the norm): the column is spread over all warps, so there is no serial owner
 //     publishes column k+1 = conj(row k+1) (Hermitian symmetry keeps every register index
 //     static), barrier #1.
-// Work still shrinks with the trailing block: column blocks of 16 and whole warps drop out.
+// Work still shrinks with the trailing block: column blocks of 16 and row groups drop out.
 // Outputs d, e, tau and the reflectors packed for hql_reflect_kernel; Q is never formed.
 // Arithmetic identical to tools/hql_prototype.py::tridiag_lower (zhetd2, lower).
 #pragma once
@@ -26,22 +26,27 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int m) {
   return make_c(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
+// Row r lives in row group i = r / RG (RG = 2 NW rows), half-warp hf = (r % RG) / NW, warp
+// w = r % NW: the rows of a warp are spread CYCLICALLY over the matrix, so every warp keeps the
+// same number of live rows while the trailing block shrinks (whole row groups and column blocks
+// drop out with uniform branches) instead of whole warps going idle.
 template <int D>
-__global__ void __launch_bounds__(4 * D)
+__global__ void __launch_bounds__(4 * D, 1)
 hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict__ Z,
                       const double *__restrict__ Bf, const cplx *__restrict__ Ain,
                       double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Vp,
                       size_t vcap, cplx *__restrict__ tauout) {
   constexpr int CJ = D / 16;  // column blocks per thread
   constexpr int NW = D / 8;   // warps
-  __shared__ __align__(16) cplx sx[2][D];   // column k of the trailing matrix, by parity of k
-  __shared__ double sxn[2][NW];             // per-warp partial ||x[2:]||^2, by parity of k
-  __shared__ __align__(16) cplx sv[D];      // v of the current step
-  __shared__ __align__(16) cplx sp[D];      // p = tau A v
+  constexpr int RG = 2 * NW;  // rows per row group
+  __shared__ __align__(16) cplx sx[2][D];      // column k of the trailing matrix, by parity of k
+  __shared__ __align__(16) double sxn[2][NW];  // per-warp partial ||x[2:]||^2, by parity of k
+  __shared__ __align__(16) cplx sv[D];         // v of the current step
+  __shared__ __align__(16) cplx sp[D];         // p = tau A v
   __shared__ __align__(16) cplx sdot[NW];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int hf = lane >> 4, l16 = lane & 15;
-  const int r0 = 8 * w + 4 * hf;  // this thread's rows r0 .. r0+3
+  const int rb = w + NW * hf;  // this thread's rows rb + RG i, i = 0 .. 3
   const size_t cfg = blockIdx.x;
   const size_t dd = (size_t)d * d;
 
@@ -57,7 +62,7 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int jj = 0; jj < CJ; ++jj) {
-        const int r = r0 + i, c = l16 + 16 * jj;
+        const int r = rb + RG * i, c = l16 + 16 * jj;
         cplx v = make_c(0.0, 0.0);
         if (r < d && c < d) {
           const size_t idx = (size_t)r * d + c;
@@ -77,22 +82,28 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
 
   // Publish column kc of the (updated) matrix: every row's element A[r][kc] sits in the lane
   // with l16 == kc % 16 of the half-warp that owns row r, so the column and the partial norms
-  // come from ALL warps in parallel (no serial owner section).
+  // come from ALL warps in parallel (no serial owner section).  Only live rows (r > kc) are
+  // written; the owner of the diagonal zeroes the two entries that died since this parity was
+  // last published, so the mat-vec below needs no masks.
   auto publish_col = [&](int kc) {
     double xn = 0.0;
     const int j1 = kc >> 4;  // column block (uniform)
+    if (l16 == (kc & 15)) {
 #pragma unroll
-    for (int jj = 0; jj < CJ; ++jj) {
-      if (jj == j1 && l16 == (kc & 15)) {
+      for (int jj = 0; jj < CJ; ++jj) {
+        if (jj == j1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = r0 + i;
-          const cplx v = a[i][jj];
-          // rows <= kc are dead: publish zeros there so the mat-vec needs no masks
-          // (row kc+1 carries alpha, the only entry the mat-vec replaces)
-          sx[kc & 1][r] = (r > kc) ? v : make_c(0.0, 0.0);
-          if (r >= kc + 2 && r < d) xn += cnorm2(v);
-          if (r == kc) dout[cfg * d + kc] = v.x;
+          for (int i = 0; i < 4; ++i) {
+            const int r = rb + RG * i;
+            const cplx v = a[i][jj];
+            if (r > kc) sx[kc & 1][r] = v;
+            if (r > kc + 1) xn = fma(v.y, v.y, fma(v.x, v.x, xn));  // rows >= d hold zeros
+            if (r == kc) {
+              dout[cfg * d + kc] = v.x;
+              sx[kc & 1][kc] = make_c(0.0, 0.0);
+              if (kc > 0) sx[kc & 1][kc - 1] = make_c(0.0, 0.0);
+            }
+          }
         }
       }
     }
@@ -105,12 +116,21 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
     sp[i] = make_c(0.0, 0.0);
   }
   publish_col(0);
+  const int j_hi = (d + 15) >> 4;
   for (int k = 0; k < d - 1; ++k) {
     __syncthreads();  // #1: column k and its partial norms are visible
     const cplx *x = sx[k & 1];
-    double xn = sxn[k & 1][0];
+    double xn;
+    {
+      double t[NW];  // pairwise tree: depth log2(NW) instead of a chain of NW dependent adds
 #pragma unroll
-    for (int q = 1; q < NW; ++q) xn += sxn[k & 1][q];
+      for (int q = 0; q < NW; ++q) t[q] = sxn[k & 1][q];
+#pragma unroll
+      for (int s = 1; s < NW; s *= 2)
+#pragma unroll
+        for (int q = 0; q + s < NW; q += 2 * s) t[q] += t[q + s];
+      xn = t[0];
+    }
     const cplx alpha = x[k + 1];
     const int mk = d - k - 2;
     const size_t voff = (size_t)mk * (mk - 1) / 2;
@@ -119,8 +139,7 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
         eout[cfg * d + k] = alpha.x;
         tauout[cfg * d + k] = make_c(0.0, 0.0);
       }
-      if (w == (k % NW))
-        for (int i = lane; i < mk; i += 32) Vp[cfg * vcap + voff + i] = make_c(0.0, 0.0);
+      for (int i = tid; i < mk; i += 4 * D) Vp[cfg * vcap + voff + i] = make_c(0.0, 0.0);
       publish_col(k + 1);
       continue;
     }
@@ -140,38 +159,40 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
       eout[cfg * d + k] = beta;
       tauout[cfg * d + k] = tau;
     }
-    const bool warp_active = (8 * w + 7 > k);  // some row of this warp lies in the trailing block
-    if (warp_active) {
-      // ---- y = A22 x'  (warp-local) ----
-      cplx y[4];
+    const int i_lo = (k + 1) / RG;  // row groups below are dead (rows <= k)
+    const int j_lo = (k + 1) >> 4;  // column blocks below are dead (columns <= k)
+    // ---- y = A22 x'  (warp-local) ----
+    cplx y[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = make_c(0.0, 0.0);
+    for (int i = 0; i < 4; ++i) y[i] = make_c(0.0, 0.0);
 #pragma unroll
-      for (int jj = 0; jj < CJ; ++jj) {
-        if (16 * jj + 15 > k && 16 * jj < d) {  // block has columns > k (uniform)
-          const int c = l16 + 16 * jj;
-          cplx xv = x[c];  // zero for c <= k (publish_col)
-          if (jj == ((k + 1) >> 4) && c == k + 1) xv = xp0;  // the only term that needs the scalar chain
+    for (int jj = 0; jj < CJ; ++jj) {
+      if (jj >= j_lo && jj < j_hi) {  // block has columns > k (uniform)
+        const int c = l16 + 16 * jj;
+        cplx xv = x[c];            // zero for c <= k (publish_col)
+        if (c == k + 1) xv = xp0;  // the only term that needs the scalar chain
 #pragma unroll
-          for (int i = 0; i < 4; ++i) cfma(y[i], a[i][jj], xv);
-        }
+        for (int i = 0; i < 4; ++i)
+          if (i >= i_lo) cfma(y[i], a[i][jj], xv);
       }
-      // butterfly over the 16 lanes: 4 rows -> lane (b3, b2) ends up with row 2 b3 + b2
-      {
-        const bool up = (l16 & 8) != 0;
-        const cplx s0 = shfl_xor_c(up ? y[0] : y[2], 8);
-        const cplx s1 = shfl_xor_c(up ? y[1] : y[3], 8);
-        y[0] = cadd(up ? y[2] : y[0], s0);
-        y[1] = cadd(up ? y[3] : y[1], s1);
-      }
-      {
-        const bool up = (l16 & 4) != 0;
-        const cplx s0 = shfl_xor_c(up ? y[0] : y[1], 4);
-        y[0] = cadd(up ? y[1] : y[0], s0);
-      }
-      y[0] = cadd(y[0], shfl_xor_c(y[0], 2));
-      y[0] = cadd(y[0], shfl_xor_c(y[0], 1));
-      const int r = r0 + ((l16 >> 3) & 1) * 2 + ((l16 >> 2) & 1);
+    }
+    // butterfly over the 16 lanes: 4 rows -> lane (b3, b2) ends up with row group 2 b3 + b2
+    {
+      const bool up = (l16 & 8) != 0;
+      const cplx s0 = shfl_xor_c(up ? y[0] : y[2], 8);
+      const cplx s1 = shfl_xor_c(up ? y[1] : y[3], 8);
+      y[0] = cadd(up ? y[2] : y[0], s0);
+      y[1] = cadd(up ? y[3] : y[1], s1);
+    }
+    {
+      const bool up = (l16 & 4) != 0;
+      const cplx s0 = shfl_xor_c(up ? y[0] : y[1], 4);
+      y[0] = cadd(up ? y[1] : y[0], s0);
+    }
+    y[0] = cadd(y[0], shfl_xor_c(y[0], 2));
+    y[0] = cadd(y[0], shfl_xor_c(y[0], 1));
+    {
+      const int r = rb + RG * (((l16 >> 3) & 1) * 2 + ((l16 >> 2) & 1));
       cplx dt = make_c(0.0, 0.0);
       if ((l16 & 3) == 0 && r > k) {
         const cplx vr = (r == k + 1) ? make_c(1.0, 0.0) : cmul(scale, x[r]);
@@ -183,36 +204,51 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
 #pragma unroll
       for (int o = 16; o >= 4; o >>= 1) dt = cadd(dt, shfl_xor_c(dt, o));
       if (lane == 0) sdot[w] = dt;
-    } else if (lane == 0) {
-      sdot[w] = make_c(0.0, 0.0);
     }
     __syncthreads();  // #2: v, p and the partial dot products are visible
-    if (w == (k % NW))  // reflector k for hql_reflect_kernel (one warp per step, round-robin)
-      for (int i = lane; i < mk; i += 32) Vp[cfg * vcap + voff + i] = sv[k + 2 + i];
-    if (warp_active) {
-      cplx dot = sdot[0];
+    // reflector k for hql_reflect_kernel
+    for (int i = tid; i < mk; i += 4 * D) Vp[cfg * vcap + voff + i] = sv[k + 2 + i];
+    double a2;
+    {
+      cplx t[NW];
 #pragma unroll
-      for (int q = 1; q < NW; ++q) dot = cadd(dot, sdot[q]);
-      const cplx a2 = cscale(-0.5, cmul(tau, dot));
-      cplx vr[4], wr[4];
+      for (int q = 0; q < NW; ++q) t[q] = sdot[q];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // rows / columns <= k are dead (never read again): they may take the stale, bounded
-        // v / p values without masking
-        vr[i] = sv[r0 + i];
-        wr[i] = cadd(sp[r0 + i], cmul(a2, vr[i]));
-      }
+      for (int s = 1; s < NW; s *= 2)
 #pragma unroll
-      for (int jj = 0; jj < CJ; ++jj) {
-        if (16 * jj + 15 > k && 16 * jj < d) {
-          const int c = l16 + 16 * jj;
-          const cplx vc = sv[c];
-          const cplx wc = cadd(sp[c], cmul(a2, vc));
+        for (int q = 0; q + s < NW; q += 2 * s) t[q] = cadd(t[q], t[q + s]);
+      // a2 = -1/2 tau p^H v = -1/2 |tau|^2 v^H A v is real for Hermitian A (its imaginary part
+      // is rounding noise), so w = p + a2 v costs two FMAs per entry
+      a2 = -0.5 * (tau.x * t[0].x - tau.y * t[0].y);
+    }
+    cplx vr[4], wr[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4; ++i) {
+      // rows / columns <= k are dead (never read again): they may take the stale, bounded
+      // v / p values without masking
+      vr[i] = sv[rb + RG * i];
+      const cplx pi = sp[rb + RG * i];
+      wr[i] = make_c(fma(a2, vr[i].x, pi.x), fma(a2, vr[i].y, pi.y));
+    }
+#pragma unroll
+    for (int jj = 0; jj < CJ; ++jj) {
+      if (jj >= j_lo && jj < j_hi) {
+        const int c = l16 + 16 * jj;
+        const cplx vc = sv[c];
+        const cplx pc = sp[c];
+        const cplx wc = make_c(fma(a2, vc.x, pc.x), fma(a2, vc.y, pc.y));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i >= i_lo) {  // A -= v w^H + w v^H, eight FMAs per element
             cplx &e = a[i][jj];
-            e.x -= vr[i].x * wc.x + vr[i].y * wc.y + wr[i].x * vc.x + wr[i].y * vc.y;
-            e.y -= vr[i].y * wc.x - vr[i].x * wc.y + wr[i].y * vc.x - wr[i].x * vc.y;
+            e.x = fma(-vr[i].x, wc.x, e.x);
+            e.x = fma(-vr[i].y, wc.y, e.x);
+            e.x = fma(-wr[i].x, vc.x, e.x);
+            e.x = fma(-wr[i].y, vc.y, e.x);
+            e.y = fma(-vr[i].y, wc.x, e.y);
+            e.y = fma(vr[i].x, wc.y, e.y);
+            e.y = fma(-wr[i].y, vc.x, e.y);
+            e.y = fma(wr[i].x, vc.y, e.y);
           }
         }
       }
