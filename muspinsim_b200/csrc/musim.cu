@@ -529,13 +529,14 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
     }
     const bool mma = (h->opt_gemm != 1) && d <= 96;  // FP64 tensor-pipe GEMMs (option "gemm" = 1: vector-FMA kernels)
+    const bool upper = !integral;  // the polarisation kernels read W[i][j] for i <= j only
     {
       ProfScope pt(&h->prof, st, PH_ROTATE);
       const double sc = 1.0 / d_other;
       if (mma && h->mu.enabled) {
         // O' = U^H (O U) with O U formed on the fly from the muon operator's two non-zeros per row
         if (!general)  // fast path: W = |O'|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
-          launch_zgemm_dmma<true, 1, true>(d, n, h->U, dd, h->U, dd, h->W, sc, nullptr, h->mu, p + 3 * c0, st);
+          launch_zgemm_dmma<true, 1, true>(d, n, h->U, dd, h->U, dd, h->W, sc, nullptr, h->mu, p + 3 * c0, st, upper);
         else
           launch_zgemm_dmma<true, 0, true>(d, n, h->U, dd, h->U, dd, h->Y, 1.0, nullptr, h->mu, p + 3 * c0, st);
         ++h->launches;
@@ -546,7 +547,7 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
         if (mma) {
           launch_zgemm_dmma<false, 0, false>(d, n, h->Oc, dd, h->U, dd, h->T1, 1.0, nullptr, h->mu, nullptr, st);
           if (!general)
-            launch_zgemm_dmma<true, 1, false>(d, n, h->U, dd, h->T1, dd, h->W, sc, nullptr, h->mu, nullptr, st);
+            launch_zgemm_dmma<true, 1, false>(d, n, h->U, dd, h->T1, dd, h->W, sc, nullptr, h->mu, nullptr, st, upper);
           else
             launch_zgemm_dmma<true, 0, false>(d, n, h->U, dd, h->T1, dd, h->Y, 1.0, nullptr, h->mu, nullptr, st);
           h->launches += 2;
@@ -573,7 +574,7 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       if (mma) {
         // rho' = U^H (rho0 U);  W = rho' .* conj(O')  in the epilogue
         launch_zgemm_dmma<false, 0, false>(d, n, R, rs, h->U, dd, h->T1, 1.0, nullptr, h->mu, nullptr, st);
-        launch_zgemm_dmma<true, 3, false>(d, n, h->U, dd, h->T1, dd, h->W, 1.0, h->Y, h->mu, nullptr, st);
+        launch_zgemm_dmma<true, 3, false>(d, n, h->U, dd, h->T1, dd, h->W, 1.0, h->Y, h->mu, nullptr, st, upper);
         h->launches += 2;
       } else {
         launch_gemm<false, 0>(d, n, R, rs, h->U, dd, h->T1, 1.0, st, &h->launches);

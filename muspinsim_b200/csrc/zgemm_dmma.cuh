@@ -14,6 +14,8 @@
 // O = sum_a p_a S_mu^a (x) 1 (two non-zeros per row: spinsys.py:707-732), which removes the
 // T = O U product and its HBM round trip from the fast path.
 // EPI: 0 store C; 1 store (|C|^2 scale, 0); 2 store C + D; 3 store C .* conj(D).
+// upper: only the tiles that touch i <= j are computed and stored (the polarisation kernels read
+// the upper triangle of the Hermitian weight matrix only).
 #pragma once
 #include "common.cuh"
 #include "polar.cuh"  // dmma884
@@ -31,7 +33,7 @@ template <int T, bool CONJ_A, int EPI, bool B_MUON>
 __global__ void __launch_bounds__(64 * T * T, (T == 3 ? 1 : (T == 2 ? 2 : 8)))
 zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx *__restrict__ B,
                   size_t b_stride, cplx *C, double scale, const cplx *D, MuonObs mu,
-                  const double *__restrict__ pvec) {
+                  const double *__restrict__ pvec, int upper) {
   constexpr int DP = 32 * T;     // padded dimension
   constexpr int LD = DP + 4;     // = 4 (mod 16)
   constexpr int LDK = ZG_KS + 4; // for the non-transposed A slab [m][k]
@@ -44,6 +46,9 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / (2 * T), wn = warp % (2 * T);  // this warp's 32 (rows) x 16 (columns) tile
   const int fr = lane >> 2, fk = lane & 3;
+  // upper: the consumer reads C[i][j] for i <= j only (Hermitian result): warps whose tile lies
+  // strictly below the diagonal only help staging
+  const bool tile_live = !upper || (wn * 16 + 15 >= wm * 32);
   const size_t cfg = blockIdx.x;
   const size_t dd = (size_t)d * d;
   const cplx *Ab = A + cfg * a_stride;
@@ -101,6 +106,7 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
       sBi[k * LD + n] = v.y;
     }
     __syncthreads();
+    if (tile_live) {
 #pragma unroll
     for (int ks = 0; ks < ZG_KS; ks += 4) {
       double ar[4], ai[4], br[2], bi[2], nb[2];
@@ -132,8 +138,10 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
           dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);  // + Ai Br
         }
     }
+    }
     __syncthreads();
   }
+  if (!tile_live) return;
   // ---- epilogue ----
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -166,19 +174,20 @@ inline size_t zgemm_dmma_smem() {
 // host launcher; returns false if d is outside the tensor-pipe kernel's range (d <= 96)
 template <bool CONJ_A, int EPI, bool B_MUON>
 inline bool launch_zgemm_dmma(int d, int64_t n, const cplx *A, size_t as, const cplx *B, size_t bs, cplx *C,
-                              double scale, const cplx *D, MuonObs mu, const double *pvec, cudaStream_t st) {
+                              double scale, const cplx *D, MuonObs mu, const double *pvec, cudaStream_t st,
+                              bool upper = false) {
   if (d > 96) return false;
   if (d <= 32) {
     const size_t sm = zgemm_dmma_smem<1, CONJ_A>();
-    zgemm_dmma_kernel<1, CONJ_A, EPI, B_MUON><<<(unsigned)n, 64, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec);
+    zgemm_dmma_kernel<1, CONJ_A, EPI, B_MUON><<<(unsigned)n, 64, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
   } else if (d <= 64) {
     const size_t sm = zgemm_dmma_smem<2, CONJ_A>();
     cudaFuncSetAttribute(zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON><<<(unsigned)n, 256, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec);
+    zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON><<<(unsigned)n, 256, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
   } else {
     const size_t sm = zgemm_dmma_smem<3, CONJ_A>();
     cudaFuncSetAttribute(zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON><<<(unsigned)n, 576, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec);
+    zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON><<<(unsigned)n, 576, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
   }
   return true;
 }

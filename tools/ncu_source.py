@@ -1,5 +1,5 @@
 """Aggregate an `ncu --page source --csv --print-source cuda,sass` dump: per-opcode instruction mix and
-per-source-line stall samples.  usage: ncu_source.py dump.csv [n_lines]"""
+per-source-line stall samples (per-line figures are inclusive of inlined callees).  usage: ncu_source.py dump.csv [n_lines]"""
 import collections
 import csv
 import sys
@@ -15,6 +15,7 @@ opc = collections.Counter()
 opsamp = collections.Counter()
 tot = collections.Counter()
 cur = None
+seen = set()
 for r in rows:
     if r and r[0] == "File Path":
         fpath = r[1].split("/")[-1]
@@ -35,20 +36,24 @@ for r in rows:
         samp = int(r[si] or 0)
     except ValueError:
         continue
+    first = r[2] not in seen  # inlined code is listed once per file of its inline stack
+    seen.add(r[2])
     toks = r[3].split()
     op = toks[1] if toks and toks[0].startswith("@") else (toks[0] if toks else "")
     op = op.split(".")[0]
-    opc[op] += inst
-    opsamp[op] += samp
+    if first:
+        opc[op] += inst
+        opsamp[op] += samp
+        tot["inst"] += inst
+        tot["samp"] += samp
     a = bysrc.setdefault(cur, [0, 0, collections.Counter()])
     a[0] += inst
     a[1] += samp
     for s, j in sidx.items():
         v = int(r[j] or 0)
         a[2][s] += v
-        tot[s] += v
-    tot["inst"] += inst
-    tot["samp"] += samp
+        if first:
+            tot[s] += v
 print("warp instructions %d, samples %d" % (tot["inst"], tot["samp"]))
 print("stalls: " + "  ".join("%s %.1f%%" % (s[6:], 100 * tot[s] / tot["samp"]) for s in stalls))
 print("--- by opcode")
