@@ -15,6 +15,8 @@ namespace musim {
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
 static bool g_tridiag_warp = true; // option "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
+static int g_reflect_cpt = 2;      // option "reflect_cpt": columns per thread of the d > 64 reflector kernel (1 or 2)
+static int g_tql_threads = 16;    // option "tql_threads": matrices per block of the QL kernel (8, 16 or 32)
 static bool g_tridiag_rw = true;   // option "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96)
 static bool g_tridiag_reg = false;  // option "tridiag_reg": register-resident tridiagonalisation (slower)
 
@@ -198,14 +200,22 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
                               cudaStream_t st, int64_t *launches, Profiler *prof, bool sorted) {
   if (method != EIGH_HQL) return 0;
   cudaError_t e;
-  const unsigned tb = (unsigned)((n + HQL_TQL_THREADS - 1) / HQL_TQL_THREADS);
-  e = cudaFuncSetAttribute(hql_tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hql_tql_smem(d));
-  if (e != cudaSuccess) return (int)e;
   {
     ProfScope ps(prof, st, PH_EIGH_TQL);
-    hql_tql_kernel<<<tb, HQL_TQL_THREADS, hql_tql_smem(d), st>>>(d, n, ws.dbuf[buf], ws.ebuf[buf], lam, ws.perm, ws.rot,
-                                                                ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, status,
-                                                                sorted ? 1 : 0);
+    const int nt = g_tql_threads;
+    const unsigned tb = (unsigned)((n + nt - 1) / nt);
+    const size_t sm = hql_tql_smem(d, nt);
+#define TQL_LAUNCH(NT)                                                                                       \
+  {                                                                                                          \
+    e = cudaFuncSetAttribute(hql_tql_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
+    if (e != cudaSuccess) return (int)e;                                                                     \
+    cudaFuncSetAttribute(hql_tql_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,                 \
+                         cudaSharedmemCarveoutMaxShared);                                                    \
+    hql_tql_kernel<NT><<<tb, NT, sm, st>>>(d, n, ws.dbuf[buf], ws.ebuf[buf], lam, ws.perm, ws.rot, ws.rot_cap, \
+                                           ws.swp, ws.swp_cap, ws.nswp, status, sorted ? 1 : 0);             \
+  }
+    if (nt == 8) TQL_LAUNCH(8) else if (nt == 16) TQL_LAUNCH(16) else TQL_LAUNCH(32)
+#undef TQL_LAUNCH
   }
   ++*launches;
   const size_t zsmem = hql_apply_smem(d, ws.swp_cap);
@@ -249,8 +259,13 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
         hql_reflect_kernel<64, 4><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
       } else {
         const size_t sm = hql_reflect_smem(96);
-        cudaFuncSetAttribute(hql_reflect_kernel<96, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_reflect_kernel<96, 8><<<(unsigned)n, 768, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        if (g_reflect_cpt == 2) {
+          cudaFuncSetAttribute(hql_reflect_kernel<96, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          hql_reflect_kernel<96, 8, 2><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        } else {
+          cudaFuncSetAttribute(hql_reflect_kernel<96, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          hql_reflect_kernel<96, 8><<<(unsigned)n, 768, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        }
       }
     } else {
       dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);

@@ -346,15 +346,16 @@ __device__ __forceinline__ void dlaev2_dev(double a, double b, double c, double 
 // (d, e) live in shared memory, laid out [i][thread] so that the threads of a warp (different
 // matrices, nearly the same i) hit different banks; the next (d, e) pair is prefetched one step
 // ahead so that shared-memory latency is off the serial chain.
-#define HQL_TQL_THREADS 32
-
-__global__ void __launch_bounds__(HQL_TQL_THREADS)
+// NT = matrices per block (one warp, NT active lanes).  The kernel is bound by the latency of
+// one thread's serial chain (ncu: one warp per SM sub-partition issues every ~4.3 cycles, FP64
+// pipe 4 % busy), not by lanes: NT = 8 puts four times as many warps on each sub-partition.
+template <int NT>
+__global__ void __launch_bounds__(NT)
 hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *__restrict__ ein,
                double *__restrict__ lam, unsigned short *__restrict__ perm, double2 *__restrict__ rot,
                size_t rot_cap, SweepIdx *__restrict__ swp, int swp_cap, int *__restrict__ nswp,
                int *__restrict__ status, int sorted) {
   extern __shared__ double tql_smem[];
-  constexpr int NT = HQL_TQL_THREADS;
   double *dl = tql_smem + threadIdx.x;  // dl[i*NT]
   double *el = tql_smem + (size_t)d * NT + threadIdx.x;
 #define DL(i) dl[(i) * NT]
@@ -474,7 +475,7 @@ hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *_
 #undef EL
 }
 
-inline size_t hql_tql_smem(int d) { return 2 * (size_t)d * HQL_TQL_THREADS * sizeof(double); }
+inline size_t hql_tql_smem(int d, int nt) { return 2 * (size_t)d * nt * sizeof(double); }
 
 // ---------------------------------------------------------------------------------------
 // K3: replay the rotations on Zt (real, starts as identity), one thread per row.  The
@@ -725,21 +726,26 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
 // Thread (c, h) = (tid / TPC, tid % TPC) holds rows i = TPC jj + h of column c (D/TPC complex
 // numbers); the TPC partial dot products of a column are combined with log2(TPC) shuffles.
 // TPC = 8 at D = 96: 768 threads = 24 warps per SM instead of 12 -- the kernel is latency bound.
-template <int D, int TPC>
-__global__ void __launch_bounds__(TPC *D)
+template <int D, int TPC, int CPT = 1>
+__global__ void __launch_bounds__(TPC *D / CPT)
 hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__ Vp, size_t vcap,
                    const cplx *__restrict__ tau, cplx *__restrict__ U) {
+  // CPT columns per thread: every reflector entry read from shared memory is used for CPT
+  // columns and is kept in registers between the dot-product pass and the update pass (ncu on
+  // the CPT = 1 version at d = 96: LSU 65 %, FP64 38 %)
   constexpr int RPT = D / TPC;  // rows per thread
   static_assert(RPT % 4 == 0, "rows per thread in blocks of 4");
-  constexpr int NT = TPC * D;
+  constexpr int NT = TPC * D / CPT;
   constexpr int BR = 4 * TPC;  // rows covered by a block of 4 jj
+  constexpr int REGS = (65536 / NT > 255) ? 255 : 65536 / NT;
+  constexpr bool KEEPV = (CPT >= 2) || (4 * RPT * (CPT + 1) + 40 <= REGS);  // else v is re-read in the update pass
   extern __shared__ __align__(16) unsigned char refl_smem[];
   constexpr int HQL_RTILE = HQL_RTILE_OF(D), HQL_RPAD = D;
   constexpr int RING = HQL_RTILE * HQL_RTILES;
   cplx *ring = reinterpret_cast<cplx *>(refl_smem) + HQL_RPAD;
   cplx *stau = ring + RING + HQL_RPAD;  // [D]
   const int tid = threadIdx.x;
-  const int c = tid / TPC, hh = tid % TPC;
+  const int c0 = (tid / TPC) * CPT, hh = tid % TPC;
   const size_t mat = blockIdx.x;
   const size_t dd = (size_t)d * d;
   const cplx *myv = Vp + mat * vcap;
@@ -760,12 +766,14 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
   while (t_issued < ntiles && t_issued < HQL_RTILES) issue();
   for (int k = tid; k < d; k += NT) stau[k] = tau[mat * d + k];
 
-  cplx x[RPT];
+  cplx x[CPT][RPT];
 #pragma unroll
-  for (int jj = 0; jj < RPT; ++jj) {
-    const int i = TPC * jj + hh;
-    x[jj] = make_c((i < d && c < d) ? Zt[mat * dd + (size_t)i * d + c] : 0.0, 0.0);
-  }
+  for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+    for (int jj = 0; jj < RPT; ++jj) {
+      const int i = TPC * jj + hh, c = c0 + cc;
+      x[cc][jj] = make_c((i < d && c < d) ? Zt[mat * dd + (size_t)i * d + c] : 0.0, 0.0);
+    }
   __syncthreads();
 
   size_t g = 0;  // stream position of v_k[2:]
@@ -783,37 +791,12 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
     // v for row i (i >= k+2) sits at vb0[i]; this thread's rows are i = TPC jj + hh
     const cplx *vb = ring + (int)(g % RING) - (k + 2) + hh;
     // rows in blocks of 4 jj: one uniform branch per block; blocks that lie entirely inside
-    // (k+1, d) run without per-row predicates
-    cplx u0 = make_c(0.0, 0.0), u1 = u0;
+    // (k+1, d) run without per-row predicates.  vv[] holds v (1 at row k+1, 0 outside the
+    // reflector) for the update pass.
+    cplx vv[KEEPV ? RPT : 1];
+    cplx u[CPT];
 #pragma unroll
-    for (int b = 0; b < RPT / 4; ++b) {
-      if (BR * b + BR - 1 >= k + 1 && BR * b < d) {
-        if (BR * b > k + 1 && BR * b + BR - 1 < d) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int J = 4 * b + q;
-            ccfma((q & 1) ? u1 : u0, vb[TPC * J], x[J]);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int J = 4 * b + q;
-            const int i = TPC * J + hh;
-            if (i > k + 1 && i < d)
-              ccfma((q & 1) ? u1 : u0, vb[TPC * J], x[J]);
-            else if (i == k + 1)
-              u0 = cadd(u0, x[J]);
-          }
-        }
-      }
-    }
-    cplx u = cadd(u0, u1);
-#pragma unroll
-    for (int o = 1; o < TPC; o <<= 1) {
-      u.x += __shfl_xor_sync(0xffffffffu, u.x, o);
-      u.y += __shfl_xor_sync(0xffffffffu, u.y, o);
-    }
-    const cplx tu = cmul(t, u);
+    for (int cc = 0; cc < CPT; ++cc) u[cc] = make_c(0.0, 0.0);
 #pragma unroll
     for (int b = 0; b < RPT / 4; ++b) {
       if (BR * b + BR - 1 >= k + 1 && BR * b < d) {
@@ -822,32 +805,72 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
           for (int q = 0; q < 4; ++q) {
             const int J = 4 * b + q;
             const cplx v = vb[TPC * J];
-            x[J].x -= v.x * tu.x - v.y * tu.y;
-            x[J].y -= v.x * tu.y + v.y * tu.x;
+            if (KEEPV) vv[J] = v;
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) ccfma(u[cc], v, x[cc][J]);
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int J = 4 * b + q;
             const int i = TPC * J + hh;
-            if (i > k + 1 && i < d) {
-              const cplx v = vb[TPC * J];
-              x[J].x -= v.x * tu.x - v.y * tu.y;
-              x[J].y -= v.x * tu.y + v.y * tu.x;
-            } else if (i == k + 1) {
-              x[J] = csub(x[J], tu);
-            }
+            cplx v = make_c(0.0, 0.0);
+            if (i > k + 1 && i < d)
+              v = vb[TPC * J];
+            else if (i == k + 1)
+              v = make_c(1.0, 0.0);
+            if (KEEPV) vv[J] = v;
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) ccfma(u[cc], v, x[cc][J]);
+          }
+        }
+      }
+    }
+    cplx tu[CPT];
+#pragma unroll
+    for (int cc = 0; cc < CPT; ++cc) {
+#pragma unroll
+      for (int o = 1; o < TPC; o <<= 1) {
+        u[cc].x += __shfl_xor_sync(0xffffffffu, u[cc].x, o);
+        u[cc].y += __shfl_xor_sync(0xffffffffu, u[cc].y, o);
+      }
+      tu[cc] = cmul(t, u[cc]);
+    }
+#pragma unroll
+    for (int b = 0; b < RPT / 4; ++b) {
+      if (BR * b + BR - 1 >= k + 1 && BR * b < d) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int J = 4 * b + q;
+          cplx v;
+          if (KEEPV) {
+            v = vv[J];
+          } else {
+            const int i = TPC * J + hh;
+            v = make_c(i == k + 1 ? 1.0 : 0.0, 0.0);
+            if (i > k + 1 && i < d) v = vb[TPC * J];
+          }
+#pragma unroll
+          for (int cc = 0; cc < CPT; ++cc) {  // x -= v (tau u)
+            x[cc][J].x = fma(-v.x, tu[cc].x, x[cc][J].x);
+            x[cc][J].x = fma(v.y, tu[cc].y, x[cc][J].x);
+            x[cc][J].y = fma(-v.x, tu[cc].y, x[cc][J].y);
+            x[cc][J].y = fma(-v.y, tu[cc].x, x[cc][J].y);
           }
         }
       }
     }
     g = need;
   }
-  if (c < d) {
 #pragma unroll
-    for (int jj = 0; jj < RPT; ++jj) {
-      const int i = TPC * jj + hh;
-      if (i < d) U[mat * dd + (size_t)i * d + c] = x[jj];
+  for (int cc = 0; cc < CPT; ++cc) {
+    const int c = c0 + cc;
+    if (c < d) {
+#pragma unroll
+      for (int jj = 0; jj < RPT; ++jj) {
+        const int i = TPC * jj + hh;
+        if (i < d) U[mat * dd + (size_t)i * d + c] = x[cc][jj];
+      }
     }
   }
 }

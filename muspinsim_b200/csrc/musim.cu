@@ -47,10 +47,19 @@ struct musim_handle {
   double *times_dev = nullptr;
   int times_cap = 0;
   // workspaces (sized for `ws_cfg` configurations)
+  // Two LANES: launch groups alternate between two streams, each with its own workspace set,
+  // so that the latency-bound kernels of one group (the thread-per-matrix QL kernel runs one
+  // warp per SM sub-partition for ~2.5 ms at d = 96; the barrier-bound tridiagonalisation)
+  // overlap with the throughput-bound kernels of the other.
+  struct LaneWs {
+    double *lam = nullptr;
+    cplx *U = nullptr, *T1 = nullptr, *Y = nullptr, *X = nullptr, *W = nullptr, *Oc = nullptr;
+    EighWs ews;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+  } lane[2];
   int64_t ws_cfg = 0;
-  double *lam = nullptr;
-  cplx *U = nullptr, *T1 = nullptr, *Y = nullptr, *X = nullptr, *W = nullptr, *Oc = nullptr;
-  EighWs ews;
+  int ws_lanes = 0;
   LindWs lws;
   cplx *exA = nullptr;
   double *exg = nullptr;
@@ -60,9 +69,8 @@ struct musim_handle {
   void *stage = nullptr;
   size_t stage_bytes = 0;
   // options
-  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_overlap = 0;
-  cudaStream_t st2 = nullptr;
-  cudaEvent_t evA[2] = {nullptr, nullptr}, evB[2] = {nullptr, nullptr}, evIn = nullptr;
+  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_lanes = 2;
+  cudaEvent_t evIn = nullptr;
   // bookkeeping
   int64_t launches = 0;
   Profiler prof;
@@ -91,17 +99,20 @@ static cudaError_t dev_alloc(T **p, size_t n) {
 }
 
 static void free_ws(musim_handle *h) {
-  cudaFree(h->lam);
-  cudaFree(h->U);
-  cudaFree(h->T1);
-  cudaFree(h->Y);
-  cudaFree(h->X);
-  cudaFree(h->W);
-  cudaFree(h->Oc);
-  h->ews.release();
-  h->lam = nullptr;
-  h->U = h->T1 = h->Y = h->X = h->W = h->Oc = nullptr;
+  for (auto &L : h->lane) {
+    cudaFree(L.lam);
+    cudaFree(L.U);
+    cudaFree(L.T1);
+    cudaFree(L.Y);
+    cudaFree(L.X);
+    cudaFree(L.W);
+    cudaFree(L.Oc);
+    L.ews.release();
+    L.lam = nullptr;
+    L.U = L.T1 = L.Y = L.X = L.W = L.Oc = nullptr;
+  }
   h->ws_cfg = 0;
+  h->ws_lanes = 0;
 }
 
 extern "C" int musim_version(void) { return MUSIM_VERSION; }
@@ -135,14 +146,18 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->opt_gemm = value;
   else if (!strcmp(key, "tridiag_reg"))  // 1: register-resident tridiagonalisation (d <= 96)
     g_tridiag_reg = value != 0;
+  else if (!strcmp(key, "reflect_cpt"))
+    g_reflect_cpt = value == 1 ? 1 : 2;
+  else if (!strcmp(key, "tql_threads"))
+    g_tql_threads = (value == 8 || value == 16) ? (int)value : 32;
   else if (!strcmp(key, "tridiag_warp"))  // 0: CTA-per-matrix kernels also for d <= 32
     g_tridiag_warp = value != 0;
   else if (!strcmp(key, "tridiag_rw"))  // 0: shared-memory tridiagonalisation kernel
     g_tridiag_rw = value != 0;
   else if (!strcmp(key, "reflect"))  // 0: form Q in the tridiagonalisation kernel + GEMM back-transformation
     g_reflect = value != 0;
-  else if (!strcmp(key, "overlap"))  // 0: single stream, no stage overlap
-    h->opt_overlap = value;
+  else if (!strcmp(key, "lanes"))  // 1: one stream, launch groups run back to back; 2: two concurrent lanes
+    h->opt_lanes = value < 1 ? 1 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "polar_mma"))  // 1 (default): DMMA polarisation kernel, 0: vector-FMA version
     h->opt_polar_mma = value;
   else if (!strcmp(key, "sorted"))  // 1: keep eigenpairs sorted inside the pipeline (slower replay kernel)
@@ -296,10 +311,9 @@ extern "C" int musim_destroy(musim_handle *h) {
   cudaFree(h->exA);
   cudaFree(h->exg);
   h->prof.destroy();
-  if (h->st2) cudaStreamDestroy(h->st2);
-  for (int i = 0; i < 2; ++i) {
-    if (h->evA[i]) cudaEventDestroy(h->evA[i]);
-    if (h->evB[i]) cudaEventDestroy(h->evB[i]);
+  for (auto &L : h->lane) {
+    if (L.st) cudaStreamDestroy(L.st);
+    if (L.done) cudaEventDestroy(L.done);
   }
   if (h->evIn) cudaEventDestroy(h->evIn);
   delete h;
@@ -342,20 +356,24 @@ extern "C" int musim_eigh(int device, int d, int64_t batch, const double *A, dou
 // ---------------------------------------------------------------------------------------
 // the batched run
 // ---------------------------------------------------------------------------------------
-static int ensure_ws(musim_handle *h, int64_t n, bool general) {
+static int ensure_ws(musim_handle *h, int lanes, int64_t n, bool general) {
   const size_t dd = (size_t)h->d * h->d;
-  if (h->ws_cfg >= n && (!general || h->X)) return MUSIM_OK;
+  if (h->ws_cfg >= n && h->ws_lanes >= lanes && (!general || h->lane[0].X)) return MUSIM_OK;
   free_ws(h);
-  CK(dev_alloc(&h->lam, (size_t)n * h->d));
-  CK(dev_alloc(&h->U, n * dd));
-  CK(dev_alloc(&h->T1, n * dd));
-  CK(dev_alloc(&h->W, n * dd));
-  CK(dev_alloc(&h->Oc, n * dd));
-  if (general) {
-    CK(dev_alloc(&h->Y, n * dd));
-    CK(dev_alloc(&h->X, n * dd));
+  for (int l = 0; l < lanes; ++l) {
+    auto &L = h->lane[l];
+    CK(dev_alloc(&L.lam, (size_t)n * h->d));
+    CK(dev_alloc(&L.U, n * dd));
+    CK(dev_alloc(&L.T1, n * dd));
+    CK(dev_alloc(&L.W, n * dd));
+    CK(dev_alloc(&L.Oc, n * dd));
+    if (general) {
+      CK(dev_alloc(&L.Y, n * dd));
+      CK(dev_alloc(&L.X, n * dd));
+    }
   }
   h->ws_cfg = n;
+  h->ws_lanes = lanes;
   return MUSIM_OK;
 }
 
@@ -455,76 +473,50 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   }
 
   const int method = pick_eigh(h->opt_eigh, d);
-  // chunk: bound the workspace to ~24 GB of the 180 GB (big launch groups keep the
+  // chunk: bound the workspace to ~48 GB of the 180 GB (big launch groups keep the
   // latency-bound QL stage at full occupancy)
   const int nbuf = general ? 6 : 4;
   const size_t per_cfg = nbuf * dd * sizeof(cplx) + EighWs::bytes_per_matrix(method, d) + d * sizeof(double);
-  int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>(148, (int64_t)(24.0e9 / per_cfg));
+  int64_t chunk = h->opt_chunk > 0 ? h->opt_chunk : std::max<int64_t>(148, (int64_t)(48.0e9 / per_cfg));
   chunk = std::min<int64_t>(chunk, n_cfg);
   chunk = std::min<int64_t>(chunk, 65535);  // grid.y / grid.z limit of the batched kernels
-  // Two-stage software pipeline over launch groups: the tridiagonalisation (stage A) is a
-  // long chain of barrier-separated steps that leaves most of the SM idle (ncu: 22 % FP64,
-  // 64 registers/thread), so stage A of group i+1 runs on a second stream while the
-  // throughput-bound kernels of group i (QL replay, GEMMs, polarisation) fill the same SMs.
-  const bool overlap = h->opt_overlap != 0 && method == EIGH_HQL && n_cfg >= 4 * 148;
-  if (overlap && h->opt_chunk <= 0) chunk = std::min<int64_t>(chunk, (n_cfg + 3) / 4);
-  int rc = ensure_ws(h, chunk, general);
+  // lanes: see musim_handle::LaneWs.  Small batches stay on the caller's stream.
+  const int lanes = (h->opt_lanes >= 2 && n_cfg >= 4 * 148) ? 2 : 1;
+  if (lanes == 2 && h->opt_chunk <= 0) {  // an even number of equal launch groups
+    const int64_t cap = std::max<int64_t>(148, chunk / 2);
+    const int64_t ngroups = 2 * ((n_cfg + 2 * cap - 1) / (2 * cap));
+    chunk = (n_cfg + ngroups - 1) / ngroups;
+  }
+  int rc = ensure_ws(h, lanes, chunk, general);
   if (rc) return rc;
-  {
-    cudaError_t e = h->ews.ensure(method, d, chunk, overlap);
+  for (int l = 0; l < lanes; ++l) {
+    cudaError_t e = h->lane[l].ews.ensure(method, d, chunk, false);
     if (e != cudaSuccess) return set_err(h, MUSIM_ECUDA, std::string("eigh workspace: ") + cudaGetErrorString(e));
   }
   CK(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
-  if (overlap && !h->st2) {
-    CK(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CK(cudaEventCreateWithFlags(&h->evA[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->evB[i], cudaEventDisableTiming));
+  if (lanes == 2) {
+    if (!h->evIn) CK(cudaEventCreateWithFlags(&h->evIn, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->evIn, st));  // inputs (and the status reset) are ordered before both lanes
+    for (auto &L : h->lane) {
+      if (!L.st) {
+        CK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+      }
+      CK(cudaStreamWaitEvent(L.st, h->evIn, 0));
     }
-    CK(cudaEventCreateWithFlags(&h->evIn, cudaEventDisableTiming));
   }
-  cudaStream_t stA = overlap ? h->st2 : st;
-  if (overlap) {
-    CK(cudaEventRecord(h->evIn, st));  // inputs (and the status reset) are ordered before stage A
-    CK(cudaStreamWaitEvent(stA, h->evIn, 0));
-  }
+  cudaStream_t const st_caller = st;
 
   const double d_other = (double)d / h->tab.dims[h->tab.muon_index];
   const int64_t nchunks = (n_cfg + chunk - 1) / chunk;
-  auto stageA = [&](int64_t ci) -> int {
-    const int64_t c0 = ci * chunk;
-    const int64_t n = std::min(chunk, n_cfg - c0);
-    const int buf = overlap ? (int)(ci & 1) : 0;
-    if (overlap && ci >= 2) cudaStreamWaitEvent(stA, h->evB[buf], 0);  // buffer set free again
-    int r = launch_eigh_stageA(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, h->lam, h->U, h->ews, buf, h->status,
-                               stA, &h->launches, &h->prof);
-    if (overlap) cudaEventRecord(h->evA[buf], stA);
-    return r;
-  };
-  if (overlap) {
-    rc = stageA(0);
-    if (rc == 0 && nchunks > 1) rc = stageA(1);
-    if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
-    if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
-  }
-
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int64_t c0 = ci * chunk;
     const int64_t n = std::min(chunk, n_cfg - c0);
-    const int buf = overlap ? (int)(ci & 1) : 0;
+    auto &L = h->lane[lanes == 2 ? (ci & 1) : 0];
+    st = (lanes == 2) ? L.st : st_caller;
     {
-      if (!overlap)
-        rc = stageA(ci);
-      else
-        rc = (int)cudaStreamWaitEvent(st, h->evA[buf], 0);
-      if (rc == 0)
-        rc = launch_eigh_stageB(method, d, n, h->lam, h->U, h->ews, buf, h->status, st, &h->launches, &h->prof,
-                                h->opt_sorted != 0);
-      if (overlap) {
-        // U is complete: the (d, e, Q) buffer set may be overwritten by stage A of group ci + 2
-        cudaEventRecord(h->evB[buf], st);
-        if (rc == 0 && ci + 2 < nchunks) rc = stageA(ci + 2);
-      }
+      rc = launch_eigh(method, d, n, h->H0, h->Z, B + 3 * c0, nullptr, L.lam, L.U, L.ews, h->status, st, &h->launches,
+                       &h->prof, h->opt_sorted != 0);
       if (rc == MUSIM_EUNSUP) return set_err(h, MUSIM_EUNSUP, "dimension not supported by the eigensolver");
       if (rc != 0) return set_err(h, MUSIM_ECUDA, std::string("eigh launch: ") + cudaGetErrorString((cudaError_t)rc));
     }
@@ -536,27 +528,27 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       if (mma && h->mu.enabled) {
         // O' = U^H (O U) with O U formed on the fly from the muon operator's two non-zeros per row
         if (!general)  // fast path: W = |O'|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
-          launch_zgemm_dmma<true, 1, true>(d, n, h->U, dd, h->U, dd, h->W, sc, nullptr, h->mu, p + 3 * c0, st, upper);
+          launch_zgemm_dmma<true, 1, true>(d, n, L.U, dd, L.U, dd, L.W, sc, nullptr, h->mu, p + 3 * c0, st, upper);
         else
-          launch_zgemm_dmma<true, 0, true>(d, n, h->U, dd, h->U, dd, h->Y, 1.0, nullptr, h->mu, p + 3 * c0, st);
+          launch_zgemm_dmma<true, 0, true>(d, n, L.U, dd, L.U, dd, L.Y, 1.0, nullptr, h->mu, p + 3 * c0, st);
         ++h->launches;
       } else {
         dim3 g1((unsigned)((dd + 255) / 256), (unsigned)n);
-        form_obs_kernel<<<g1, 256, 0, st>>>(d, h->M, p + 3 * c0, h->Oc);
+        form_obs_kernel<<<g1, 256, 0, st>>>(d, h->M, p + 3 * c0, L.Oc);
         ++h->launches;
         if (mma) {
-          launch_zgemm_dmma<false, 0, false>(d, n, h->Oc, dd, h->U, dd, h->T1, 1.0, nullptr, h->mu, nullptr, st);
+          launch_zgemm_dmma<false, 0, false>(d, n, L.Oc, dd, L.U, dd, L.T1, 1.0, nullptr, h->mu, nullptr, st);
           if (!general)
-            launch_zgemm_dmma<true, 1, false>(d, n, h->U, dd, h->T1, dd, h->W, sc, nullptr, h->mu, nullptr, st, upper);
+            launch_zgemm_dmma<true, 1, false>(d, n, L.U, dd, L.T1, dd, L.W, sc, nullptr, h->mu, nullptr, st, upper);
           else
-            launch_zgemm_dmma<true, 0, false>(d, n, h->U, dd, h->T1, dd, h->Y, 1.0, nullptr, h->mu, nullptr, st);
+            launch_zgemm_dmma<true, 0, false>(d, n, L.U, dd, L.T1, dd, L.Y, 1.0, nullptr, h->mu, nullptr, st);
           h->launches += 2;
         } else {
-          launch_gemm<false, 0>(d, n, h->Oc, dd, h->U, dd, h->T1, 1.0, st, &h->launches);
+          launch_gemm<false, 0>(d, n, L.Oc, dd, L.U, dd, L.T1, 1.0, st, &h->launches);
           if (!general)
-            launch_gemm<true, 1>(d, n, h->U, dd, h->T1, dd, h->W, sc, st, &h->launches);
+            launch_gemm<true, 1>(d, n, L.U, dd, L.T1, dd, L.W, sc, st, &h->launches);
           else
-            launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->Y, 1.0, st, &h->launches);
+            launch_gemm<true, 0>(d, n, L.U, dd, L.T1, dd, L.Y, 1.0, st, &h->launches);
         }
       }
     }
@@ -565,28 +557,28 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       size_t rs = 0;
       if (!R) {
         ProfScope pt(&h->prof, st, PH_RHO0);
-        rho0_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->tab, B + 3 * c0, p + 3 * c0, T + c0, h->Oc);
+        rho0_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->tab, B + 3 * c0, p + 3 * c0, T + c0, L.Oc);
         ++h->launches;
-        R = h->Oc;
+        R = L.Oc;
         rs = dd;
       }
       ProfScope pt(&h->prof, st, PH_ROTATE);
       if (mma) {
         // rho' = U^H (rho0 U);  W = rho' .* conj(O')  in the epilogue
-        launch_zgemm_dmma<false, 0, false>(d, n, R, rs, h->U, dd, h->T1, 1.0, nullptr, h->mu, nullptr, st);
-        launch_zgemm_dmma<true, 3, false>(d, n, h->U, dd, h->T1, dd, h->W, 1.0, h->Y, h->mu, nullptr, st, upper);
+        launch_zgemm_dmma<false, 0, false>(d, n, R, rs, L.U, dd, L.T1, 1.0, nullptr, h->mu, nullptr, st);
+        launch_zgemm_dmma<true, 3, false>(d, n, L.U, dd, L.T1, dd, L.W, 1.0, L.Y, h->mu, nullptr, st, upper);
         h->launches += 2;
       } else {
-        launch_gemm<false, 0>(d, n, R, rs, h->U, dd, h->T1, 1.0, st, &h->launches);
-        launch_gemm<true, 0>(d, n, h->U, dd, h->T1, dd, h->X, 1.0, st, &h->launches);
+        launch_gemm<false, 0>(d, n, R, rs, L.U, dd, L.T1, 1.0, st, &h->launches);
+        launch_gemm<true, 0>(d, n, L.U, dd, L.T1, dd, L.X, 1.0, st, &h->launches);
         const size_t tot = (size_t)n * dd;
-        weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, h->X, h->Y, h->W);
+        weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, L.X, L.Y, L.W);
         ++h->launches;
       }
     }
     if (integral) {
       ProfScope pt(&h->prof, st, PH_INTEGRAL);
-      integral_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->W, h->lam, w + c0, slot + c0, tau, out);
+      integral_kernel<<<(unsigned)n, 128, 0, st>>>(d, L.W, L.lam, w + c0, slot + c0, tau, out);
       ++h->launches;
     } else {
       ProfScope pt(&h->prof, st, PH_POLAR);
@@ -608,24 +600,29 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
           const size_t smem = polar_dmma_smem(d);
           CK(cudaFuncSetAttribute(polar_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           dim3 grid(g2, (NA_total + 31) / 32);
-          polar_dmma_kernel<<<grid, 128, smem, st>>>(d, h->npairs, h->pairs, (int)n, per2, h->W, h->lam, w + c0,
+          polar_dmma_kernel<<<grid, 128, smem, st>>>(d, h->npairs, h->pairs, (int)n, per2, L.W, L.lam, w + c0,
                                                      slot + c0, nt, tg.t0, tg.dt, NA_total, NB, out);
         } else {
           const size_t smem = polar_fact_smem(d);
           CK(cudaFuncSetAttribute(polar_fact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           dim3 grid(groups, (NA_total + 31) / 32);
-          polar_fact_kernel<<<grid, 256, smem, st>>>(d, h->npairs, h->pairs, (int)n, per, h->W, h->lam, w + c0,
+          polar_fact_kernel<<<grid, 256, smem, st>>>(d, h->npairs, h->pairs, (int)n, per, L.W, L.lam, w + c0,
                                                      slot + c0, nt, tg.t0, tg.dt, NA_total, NB, out);
         }
       } else {
         dim3 grid(groups, (nt + 255) / 256);
-        polar_direct_kernel<<<grid, 256, d * sizeof(double), st>>>(d, h->npairs, h->pairs, (int)n, per, h->W,
-                                                                  h->lam, w + c0, slot + c0, nt, h->times_dev, out);
+        polar_direct_kernel<<<grid, 256, d * sizeof(double), st>>>(d, h->npairs, h->pairs, (int)n, per, L.W,
+                                                                  L.lam, w + c0, slot + c0, nt, h->times_dev, out);
       }
       ++h->launches;
     }
     CK(cudaGetLastError());
   }
+  if (lanes == 2)
+    for (auto &L : h->lane) {
+      CK(cudaEventRecord(L.done, L.st));
+      CK(cudaStreamWaitEvent(st_caller, L.done, 0));
+    }
   return MUSIM_OK;
 }
 

@@ -28,7 +28,7 @@ def test_golden(name):
 
 
 @pytest.mark.parametrize("opts", [{"polar": 1}, {"eigh": 1}, {"eigh": 2, "polar": 2}, {"chunk": 3},
-                                  {"polar_mma": 0}, {"sorted": 1}, {"tridiag_reg": 1}, {"overlap": 1}, {"reflect": 0}, {"tridiag_rw": 0}, {"gemm": 1}, {"tridiag_warp": 0}])
+                                  {"polar_mma": 0}, {"sorted": 1}, {"tridiag_reg": 1}, {"lanes": 1}, {"reflect": 0}, {"tridiag_rw": 0}, {"gemm": 1}, {"tridiag_warp": 0}, {"reflect_cpt": 1}, {"tql_threads": 32}, {"tql_threads": 8}])
 @pytest.mark.parametrize("name", ["c2_fast_d16", "c2_general_d8_T0p3", "c3_alc_d12", "c5_fast_d96",
                                   "polarization_filerange", "ground_state_T0"])
 def test_golden_all_kernel_variants(name, opts):
@@ -101,17 +101,17 @@ def test_device_pointer_entry_matches_host_entry():
     assert r.handle.launches > 0
 
 
-def test_stage_overlap_matches_single_stream():
-    """>= 4*148 configurations take the two-stream pipeline (stage A of group i+1 overlapping
-    stage B of group i); it must give the same answer as the single-stream order."""
+def test_two_lanes_match_single_stream():
+    """>= 4*148 configurations run as launch groups alternating between two concurrent lanes
+    (streams with their own workspaces); same answer as the single-stream order."""
     from muspinsim_b200 import workloads
 
     spec = workloads.c2_hfine_powder(n_orient=1500, nt=200, n_h=2)
-    a, _ = _run(spec, overlap=1, chunk=200)  # 8 launch groups through 2 buffer sets
-    b, _ = _run(spec, overlap=0)
+    a, _ = _run(spec, lanes=2, chunk=200)  # 8 launch groups through 2 lanes
+    b, _ = _run(spec, lanes=1)
     assert np.max(np.abs(a - b)) < 1e-12
-    c, _ = _run(dict(spec, temperature=[0.7]), overlap=1, chunk=300)
-    d, _ = _run(dict(spec, temperature=[0.7]), overlap=0)
+    c, _ = _run(dict(spec, temperature=[0.7]), lanes=2, chunk=300)
+    d, _ = _run(dict(spec, temperature=[0.7]), lanes=1)
     assert np.max(np.abs(c - d)) < 1e-12
 
 
