@@ -15,6 +15,7 @@ namespace musim {
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
 static bool g_tridiag_warp = true; // option "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
+static bool g_apply_warp = true;   // option "apply_warp": rotation replay with one warp per CTA (d > 32)
 static int g_reflect_cpt = 2;      // option "reflect_cpt": columns per thread of the d > 64 reflector kernel (1 or 2)
 static int g_tql_threads = 16;    // option "tql_threads": matrices per block of the QL kernel (8, 16 or 32)
 static bool g_tridiag_rw = true;   // option "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96)
@@ -224,18 +225,22 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   const int ath = std::min(128, (d + 31) & ~31);
   if (!sorted && d <= 96) {
     // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
-    const size_t rsmem = hql_apply_reg_smem(d <= 32 ? 32 : (d <= 64 ? 64 : 96), ws.swp_cap);
+    const int D = d <= 32 ? 32 : (d <= 64 ? 64 : 96);
+    const int nth = g_apply_warp ? 32 : D;  // option "apply_warp": one warp (32 rows of Z) per CTA
+    const size_t rsmem = hql_apply_reg_smem(D, nth, ws.swp_cap);
+    const dim3 grid((unsigned)n, D / nth);
     ProfScope ps(prof, st, PH_EIGH_APPLY);
-    if (d <= 32) {
-      cudaFuncSetAttribute(hql_apply_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-      hql_apply_reg_kernel<32><<<(unsigned)n, 32, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
-    } else if (d <= 64) {
-      cudaFuncSetAttribute(hql_apply_reg_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-      hql_apply_reg_kernel<64><<<(unsigned)n, 64, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
-    } else {
-      cudaFuncSetAttribute(hql_apply_reg_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-      hql_apply_reg_kernel<96><<<(unsigned)n, 96, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt);
-    }
+#define APPLY_LAUNCH(DD, NTH)                                                                                   \
+  {                                                                                                             \
+    cudaFuncSetAttribute(hql_apply_reg_kernel<DD, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem); \
+    hql_apply_reg_kernel<DD, NTH><<<grid, NTH, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt); \
+  }
+    if (D == 32) APPLY_LAUNCH(32, 32)
+    else if (D == 64 && nth == 32) APPLY_LAUNCH(64, 32)
+    else if (D == 64) APPLY_LAUNCH(64, 64)
+    else if (nth == 32) APPLY_LAUNCH(96, 32)
+    else APPLY_LAUNCH(96, 96)
+#undef APPLY_LAUNCH
   } else {
     ProfScope ps(prof, st, PH_EIGH_APPLY);
     hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);

@@ -598,24 +598,31 @@ hql_apply_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
 // the ring and D mirrored entries behind it (a sweep / reflector has < D entries)
 #define HQL_RTILE_OF(D) ((D) <= 32 ? 128 : 512)
 #define HQL_RTILES 4
+#define HQL_ARTILE_OF(D, NTH) ((NTH) < (D) ? 256 : HQL_RTILE_OF(D))  // rotation tile of the replay kernel
 
-template <int D>
+// NTH = rows (threads) per CTA.  The register file is split per SM sub-partition (16 K registers
+// each): at 224 registers a sub-partition holds two warps, so 3-warp CTAs (NTH = D = 96) leave a
+// quarter of the slots empty (ncu: 2 CTAs = 6 warps per SM).  NTH = 32 makes every warp its own
+// CTA -- the rows of Z are independent, the warps of a matrix only share the rotation stream,
+// which the second and third warp then find in L2 -- and fills all 8 slots.
+template <int D, int NTH = D>
 __global__ void __maxnreg__(224)
 hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
                      const SweepIdx *__restrict__ swp, int swp_cap, const int *__restrict__ nswp,
                      double *__restrict__ Zt) {
   extern __shared__ __align__(16) unsigned char apply_smem[];
-  constexpr int HQL_RTILE = HQL_RTILE_OF(D), HQL_RPAD = D;
+  constexpr int HQL_RTILE = HQL_ARTILE_OF(D, NTH), HQL_RPAD = D;
   constexpr int RING = HQL_RTILE * HQL_RTILES;
   // [RPAD guard][RING][RPAD mirror of the first entries]: a sweep's <= 95 rotations starting
   // anywhere in the ring are contiguous, so every (c, s) load is base + immediate offset
   double2 *ring = reinterpret_cast<double2 *>(apply_smem) + HQL_RPAD;
   SweepIdx *sswp = reinterpret_cast<SweepIdx *>(ring + RING + HQL_RPAD);
   const int tid = threadIdx.x;
+  const int row0 = blockIdx.y * NTH;  // first row of Z held by this CTA
   const size_t mat = blockIdx.x;
   const double2 *myrot = rot + mat * rot_cap;
   const int ns = nswp[mat];
-  for (int i = tid; i < ns; i += D) sswp[i] = swp[mat * swp_cap + i];
+  for (int i = tid; i < ns; i += NTH) sswp[i] = swp[mat * swp_cap + i];
   __syncthreads();
   size_t total = 0;
   for (int i = 0; i < ns; ++i) total += (size_t)(sswp[i].m - sswp[i].l);
@@ -624,7 +631,7 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
   auto issue = [&]() {  // issue tile t_issued into its ring slot (+ mirror if it is slot 0)
     const size_t base = (size_t)t_issued * HQL_RTILE;
     const int slot0 = (t_issued % HQL_RTILES) * HQL_RTILE;
-    for (int e = tid; e < HQL_RTILE; e += D)
+    for (int e = tid; e < HQL_RTILE; e += NTH)
       if (base + e < total) {
         cp_async16(&ring[slot0 + e], &myrot[base + e]);
         if (slot0 == 0 && e < HQL_RPAD) cp_async16(&ring[RING + e], &myrot[base + e]);
@@ -636,7 +643,7 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
 
   double z[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) z[j] = (j == tid) ? 1.0 : 0.0;
+  for (int j = 0; j < D; ++j) z[j] = (j == row0 + tid) ? 1.0 : 0.0;
 
   size_t g = 0;
   for (int sidx = 0; sidx < ns; ++sidx) {
@@ -701,9 +708,9 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
       if (j >= c0 && j < c0 + 32) sbuf[tid * 33 + (j - c0)] = z[j];
     __syncthreads();
     const int w = min(32, d - c0);
-    for (int idx = tid; idx < d * 32; idx += D) {
+    for (int idx = tid; idx < NTH * 32; idx += NTH) {
       const int rr = idx >> 5, jj = idx & 31;
-      if (jj < w) Zt[mat * dd + (size_t)rr * d + c0 + jj] = sbuf[rr * 33 + jj];
+      if (jj < w && row0 + rr < d) Zt[mat * dd + (size_t)(row0 + rr) * d + c0 + jj] = sbuf[rr * 33 + jj];
     }
     __syncthreads();
   }
@@ -879,8 +886,8 @@ inline size_t hql_reflect_smem(int D) {
   return (HQL_RTILE_OF(D) * HQL_RTILES + 2 * D + D) * sizeof(cplx) + 16;
 }
 
-inline size_t hql_apply_reg_smem(int D, int swp_cap) {
-  return (HQL_RTILE_OF(D) * HQL_RTILES + 2 * D) * sizeof(double2) + (size_t)swp_cap * sizeof(SweepIdx) + 16;
+inline size_t hql_apply_reg_smem(int D, int NTH, int swp_cap) {
+  return (HQL_ARTILE_OF(D, NTH) * HQL_RTILES + 2 * D) * sizeof(double2) + (size_t)swp_cap * sizeof(SweepIdx) + 16;
 }
 
 inline size_t hql_apply_smem(int d, int swp_cap) {
