@@ -15,6 +15,7 @@ namespace musim {
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
 static bool g_tridiag_warp = true; // option "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
+static bool g_tridiag_phases = true;  // option "tridiag_phases": K1 in up to three launches of decreasing size
 static bool g_apply_warp = true;   // option "apply_warp": rotation replay with one warp per CTA (d > 32)
 static int g_reflect_cpt = 2;      // option "reflect_cpt": columns per thread of the d > 64 reflector kernel (1 or 2)
 static int g_tql_threads = 16;    // option "tql_threads": matrices per block of the QL kernel (8, 16 or 32)
@@ -99,7 +100,7 @@ struct EighWs {
       for (int i = 0; i < (dbl ? 2 : 1); ++i) {
         EW_ALLOC(dbuf[i], (size_t)n * d);
         EW_ALLOC(ebuf[i], (size_t)n * d);
-        EW_ALLOC(Q[i], (size_t)n * dd);
+        EW_ALLOC(Q[i], (size_t)n * std::max<size_t>(dd, 64 * 64 + 32 * 32));
         EW_ALLOC(Vp[i], (size_t)n * vcap);
         EW_ALLOC(tauv[i], (size_t)n * d);
       }
@@ -135,12 +136,29 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
       hql_tridiag_warp_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
           d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
     } else if (use_reflect(d) && g_tridiag_rw) {
+      double *dd_ = ws.dbuf[buf], *ee_ = ws.ebuf[buf];
+      cplx *vp_ = ws.Vp[buf], *tt_ = ws.tauv[buf];
+      // phase buffers for the trailing blocks (Q is not used on the reflector path)
+      cplx *A64 = ws.Q[buf], *A32 = ws.Q[buf] + (size_t)n * 64 * 64;
+      const unsigned g = (unsigned)n;
       if (d <= 32) {
-        hql_tridiag_rw_kernel<32><<<(unsigned)n, 128, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+        hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+      } else if (!g_tridiag_phases) {
+        if (d <= 64)
+          hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        else
+          hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
       } else if (d <= 64) {
-        hql_tridiag_rw_kernel<64><<<(unsigned)n, 256, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+        const int k1 = d - 32;
+        hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A32);
+        hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(32, d, k1, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        ++*launches;
       } else {
-        hql_tridiag_rw_kernel<96><<<(unsigned)n, 384, 0, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+        const int k1 = d - 64;
+        hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A64);
+        hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(64, d, k1, 32, nullptr, nullptr, nullptr, A64, dd_, ee_, vp_, ws.vcap, tt_, A32);
+        hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(32, d, k1 + 32, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        *launches += 2;
       }
     } else if (d <= 96 && g_tridiag_reg) {
       // register-resident A (eigh_tridiag_reg.cuh): R = d rounded up to 32 / 64 / 96

@@ -30,12 +30,20 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int m) {
 // w = r % NW: the rows of a warp are spread CYCLICALLY over the matrix, so every warp keeps the
 // same number of live rows while the trailing block shrinks (whole row groups and column blocks
 // drop out with uniform branches) instead of whole warps going idle.
+//
+// PHASES.  Late steps are dominated by the fixed per-step latency (two barriers, the scalar
+// chain, the butterflies) while the live block needs only a fraction of the registers, so the
+// host runs the reduction as up to three launches: the kernel stops after `nsteps` steps and
+// writes the trailing (d - nsteps)^2 block to Aout; the next launch (a smaller D: more CTAs per
+// SM) continues on that block -- the trailing problem is self-similar, the packed reflectors
+// keep their offsets, and d / e / tau are written at offset `koff` of rows of length `dstride`.
 template <int D>
-__global__ void __launch_bounds__(4 * D, 1)
-hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict__ Z,
-                      const double *__restrict__ Bf, const cplx *__restrict__ Ain,
-                      double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Vp,
-                      size_t vcap, cplx *__restrict__ tauout) {
+__global__ void __launch_bounds__(4 * D, (D <= 32 ? 4 : (D <= 64 ? 2 : 1)))
+hql_tridiag_rw_kernel(int d, int dstride, int koff, int nsteps, const cplx *__restrict__ H0,
+                      const cplx *__restrict__ Z, const double *__restrict__ Bf,
+                      const cplx *__restrict__ Ain, double *__restrict__ dout,
+                      double *__restrict__ eout, cplx *__restrict__ Vp, size_t vcap,
+                      cplx *__restrict__ tauout, cplx *__restrict__ Aout) {
   constexpr int CJ = D / 16;  // column blocks per thread
   constexpr int NW = D / 8;   // warps
   constexpr int RG = 2 * NW;  // rows per row group
@@ -99,7 +107,7 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
             if (r > kc) sx[kc & 1][r] = v;
             if (r > kc + 1) xn = fma(v.y, v.y, fma(v.x, v.x, xn));  // rows >= d hold zeros
             if (r == kc) {
-              dout[cfg * d + kc] = v.x;
+              dout[cfg * dstride + koff + kc] = v.x;
               sx[kc & 1][kc] = make_c(0.0, 0.0);
               if (kc > 0) sx[kc & 1][kc - 1] = make_c(0.0, 0.0);
             }
@@ -117,7 +125,8 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
   }
   publish_col(0);
   const int j_hi = (d + 15) >> 4;
-  for (int k = 0; k < d - 1; ++k) {
+  const int kend = (nsteps < d - 1) ? nsteps : d - 1;
+  for (int k = 0; k < kend; ++k) {
     __syncthreads();  // #1: column k and its partial norms are visible
     const cplx *x = sx[k & 1];
     double xn;
@@ -136,8 +145,8 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
     const size_t voff = (size_t)mk * (mk - 1) / 2;
     if (xn == 0.0 && alpha.y == 0.0) {  // identity reflector (uniform: every thread sees the same values)
       if (tid == 0) {
-        eout[cfg * d + k] = alpha.x;
-        tauout[cfg * d + k] = make_c(0.0, 0.0);
+        eout[cfg * dstride + koff + k] = alpha.x;
+        tauout[cfg * dstride + koff + k] = make_c(0.0, 0.0);
       }
       for (int i = tid; i < mk; i += 4 * D) Vp[cfg * vcap + voff + i] = make_c(0.0, 0.0);
       publish_col(k + 1);
@@ -156,8 +165,8 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
     const cplx scale = make_c(xp0.x * den, -xp0.y * den);
     const cplx ts = cmul(tau, scale);
     if (tid == 0) {
-      eout[cfg * d + k] = beta;
-      tauout[cfg * d + k] = tau;
+      eout[cfg * dstride + koff + k] = beta;
+      tauout[cfg * dstride + koff + k] = tau;
     }
     const int i_lo = (k + 1) / RG;  // row groups below are dead (rows <= k)
     const int j_lo = (k + 1) >> 4;  // column blocks below are dead (columns <= k)
@@ -255,7 +264,19 @@ hql_tridiag_rw_kernel(int d, const cplx *__restrict__ H0, const cplx *__restrict
     }
     publish_col(k + 1);
   }
-  if (tid == 0) eout[cfg * d + d - 1] = 0.0;
+  if (kend == d - 1) {
+    if (tid == 0) eout[cfg * dstride + koff + d - 1] = 0.0;
+  } else {  // hand the trailing block to the next phase
+    const int ds = d - kend;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < CJ; ++jj) {
+        const int r = rb + RG * i, c = l16 + 16 * jj;
+        if (r >= kend && c >= kend && r < d && c < d)
+          Aout[cfg * (size_t)ds * ds + (size_t)(r - kend) * ds + (c - kend)] = a[i][jj];
+      }
+  }
 }
 
 }  // namespace musim

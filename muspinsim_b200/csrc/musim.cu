@@ -146,6 +146,8 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->opt_gemm = value;
   else if (!strcmp(key, "tridiag_reg"))  // 1: register-resident tridiagonalisation (d <= 96)
     g_tridiag_reg = value != 0;
+  else if (!strcmp(key, "tridiag_phases"))
+    g_tridiag_phases = value != 0;
   else if (!strcmp(key, "apply_warp"))
     g_apply_warp = value != 0;
   else if (!strcmp(key, "reflect_cpt"))
