@@ -600,6 +600,19 @@ hql_apply_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
 #define HQL_RTILES 4
 #define HQL_ARTILE_OF(D, NTH) ((NTH) < (D) ? 256 : HQL_RTILE_OF(D))  // rotation tile of the replay kernel
 
+// One rotation of the replay, (z_j, z_j1) <- (cy z_j1 + cx z_j, cx z_j1 - cy z_j), with both results
+// written IN PLACE ("+d"): every z[j] then stays in one physical register for the whole kernel.
+// Left to itself the compiler rotates register names along the dependent chain, and the merge
+// points of the unrolled block structure pay for it in moves (ncu: 21 % of all instructions
+// were IMAD.MOV).  The dependent chain is still one FMA per rotation.
+__device__ __forceinline__ void rot_inplace(double &zj, double &zj1, const double2 cs) {
+  double nu;
+  asm("{\n\t.reg .f64 ncy;\n\tneg.f64 ncy, %1;\n\tmul.rn.f64 %0, ncy, %2;\n\t}" : "=d"(nu) : "d"(cs.y), "d"(zj));
+  asm("mul.rn.f64 %0, %0, %1;" : "+d"(zj) : "d"(cs.x));
+  asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(zj) : "d"(cs.y), "d"(zj1));
+  asm("fma.rn.f64 %0, %1, %0, %2;" : "+d"(zj1) : "d"(cs.x), "d"(nu));
+}
+
 // NTH = rows (threads) per CTA.  The register file is split per SM sub-partition (16 K registers
 // each): at 224 registers a sub-partition holds two warps, so 3-warp CTAs (NTH = D = 96) leave a
 // quarter of the slots empty (ncu: 2 CTAs = 6 warps per SM).  NTH = 32 makes every warp its own
@@ -664,34 +677,32 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
     for (int b = (D - 2) / 8; b >= 0; --b) {
       const int jlo = 8 * b;
       const int jhi = (8 * b + 7 < D - 2) ? 8 * b + 7 : D - 2;
-      if (jlo >= l && jhi < m) {
-        // interior block: all steps active, loads first, then the dependent chain
+      // QL windows sit at the high end (l grows as eigenvalues converge, m stays near d - 1):
+      // once a block lies below l, so do all the remaining ones.  Each skipped block costs a
+      // dependent uniform compare + branch (~15 cycles), as much as a rotation.
+      if (jhi < l) break;
+      if (jlo < m) {
+        // loads first, then the dependent chain; in a block cut by l or m the rotations
+        // outside [l, m) become the identity (c, s) = (1, 0), which is exact
         double2 cs[8];
+        if (jlo >= l && jhi < m) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (jhi - u >= jlo) cs[u] = base[-(jhi - u)];
+          for (int u = 0; u < 8; ++u)
+            if (jhi - u >= jlo) cs[u] = base[-(jhi - u)];
+        } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = jhi - u;
-          if (j >= jlo) {
-            const double t = z[j + 1];
-            z[j + 1] = cs[u].x * t - cs[u].y * z[j];
-            z[j] = fma(cs[u].y, t, cs[u].x * z[j]);
-          }
-        }
-      } else if (jlo < m && jhi >= l) {
-        // edge block
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = jhi - u;
-          if (j >= jlo) {
-            if (j < m && j >= l) {
-              const double2 c1 = base[-j];
-              const double t = z[j + 1];
-              z[j + 1] = c1.x * t - c1.y * z[j];
-              z[j] = fma(c1.y, t, c1.x * z[j]);
+          for (int u = 0; u < 8; ++u) {
+            const int j = jhi - u;
+            if (j >= jlo) {
+              const double2 c1 = base[-j];  // in bounds for every j (guard + mirror)
+              cs[u] = (j < m && j >= l) ? c1 : make_double2(1.0, 0.0);
             }
           }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = jhi - u;
+          if (j >= jlo) rot_inplace(z[j], z[j + 1], cs[u]);
         }
       }
     }
