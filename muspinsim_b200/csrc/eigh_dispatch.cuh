@@ -222,6 +222,7 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   {
     ProfScope ps(prof, st, PH_EIGH_TQL);
     const int nt = g_tql_threads;
+    const int dpad = (!sorted && d <= 96) ? (d <= 32 ? 32 : (d <= 64 ? 64 : 96)) : 0;  // register replay kernel follows
     const unsigned tb = (unsigned)((n + nt - 1) / nt);
     const size_t sm = hql_tql_smem(d, nt);
 #define TQL_LAUNCH(NT)                                                                                       \
@@ -231,7 +232,7 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     cudaFuncSetAttribute(hql_tql_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,                 \
                          cudaSharedmemCarveoutMaxShared);                                                    \
     hql_tql_kernel<NT><<<tb, NT, sm, st>>>(d, n, ws.dbuf[buf], ws.ebuf[buf], lam, ws.perm, ws.rot, ws.rot_cap, \
-                                           ws.swp, ws.swp_cap, ws.nswp, status, sorted ? 1 : 0);             \
+                                           ws.swp, ws.swp_cap, ws.nswp, status, sorted ? 1 : 0, dpad);       \
   }
     if (nt == 8) TQL_LAUNCH(8) else if (nt == 16) TQL_LAUNCH(16) else TQL_LAUNCH(32)
 #undef TQL_LAUNCH

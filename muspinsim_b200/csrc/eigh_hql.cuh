@@ -354,7 +354,10 @@ __global__ void __launch_bounds__(NT)
 hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *__restrict__ ein,
                double *__restrict__ lam, unsigned short *__restrict__ perm, double2 *__restrict__ rot,
                size_t rot_cap, SweepIdx *__restrict__ swp, int swp_cap, int *__restrict__ nswp,
-               int *__restrict__ status, int sorted) {
+               int *__restrict__ status, int sorted, int dpad) {
+  // dpad > 0 (register replay kernel with dpad columns): every sweep (l, m) is recorded for the
+  // whole 8-column blocks it touches, columns jhi(b(m-1)) .. 8 b(l), with identity rotations
+  // outside [l, m) -- the replay kernel then has no partially active blocks
   extern __shared__ double tql_smem[];
   double *dl = tql_smem + threadIdx.x;  // dl[i*NT]
   double *el = tql_smem + (size_t)d * NT + threadIdx.x;
@@ -388,14 +391,22 @@ hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *_
       ++l;
       continue;
     }
-    if (ns >= swp_cap || nrot + (size_t)(m - l) > rot_cap || nit >= maxit) {
+    int pad_top = 0, pad_bot = 0;
+    if (dpad > 0) {
+      const int jtop = min(8 * ((m - 1) >> 3) + 7, dpad - 2);
+      pad_top = jtop - (m - 1);
+      pad_bot = l - 8 * (l >> 3);
+    }
+    if (ns >= swp_cap || nrot + (size_t)(m - l + pad_top + pad_bot) > rot_cap || nit >= maxit) {
       fail = true;
       break;
     }
+    for (int q = 0; q < pad_top; ++q) myrot[nrot++] = make_double2(1.0, 0.0);
     if (m == l + 1) {
       double rt1, rt2, c, s;
       dlaev2_dev(DL(l), EL(l), DL(l + 1), rt1, rt2, c, s);
       myrot[nrot++] = make_double2(c, s);
+      for (int q = 0; q < pad_bot; ++q) myrot[nrot++] = make_double2(1.0, 0.0);
       myswp[ns++] = SweepIdx{(unsigned short)l, (unsigned short)(l + 1)};
       DL(l) = rt1;
       DL(l + 1) = rt2;
@@ -446,6 +457,7 @@ hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *_
       d_i = d_nx;
     }
     nrot += (size_t)(m - l);
+    for (int q = 0; q < pad_bot; ++q) myrot[nrot++] = make_double2(1.0, 0.0);
     DL(l) = DL(l) - p;
     EL(l) = g;
     myswp[ns++] = SweepIdx{(unsigned short)l, (unsigned short)m};
@@ -619,7 +631,7 @@ __device__ __forceinline__ void rot_inplace(double &zj, double &zj1, const doubl
 // CTA -- the rows of Z are independent, the warps of a matrix only share the rotation stream,
 // which the second and third warp then find in L2 -- and fills all 8 slots.
 template <int D, int NTH = D>
-__global__ void __maxnreg__(224)
+__global__ void __maxnreg__(255)
 hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
                      const SweepIdx *__restrict__ swp, int swp_cap, const int *__restrict__ nswp,
                      double *__restrict__ Zt) {
@@ -638,7 +650,10 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
   for (int i = tid; i < ns; i += NTH) sswp[i] = swp[mat * swp_cap + i];
   __syncthreads();
   size_t total = 0;
-  for (int i = 0; i < ns; ++i) total += (size_t)(sswp[i].m - sswp[i].l);
+  for (int i = 0; i < ns; ++i) {  // padded to whole 8-column blocks by the QL kernel
+    const int bh = (sswp[i].m - 1) >> 3, bl = sswp[i].l >> 3;
+    total += (size_t)(((8 * bh + 7 < D - 2) ? 8 * bh + 7 : D - 2) - 8 * bl + 1);
+  }
   const int ntiles = (int)((total + HQL_RTILE - 1) / HQL_RTILE);
   int t_issued = 0, t_landed = 0;
   auto issue = [&]() {  // issue tile t_issued into its ring slot (+ mirror if it is slot 0)
@@ -658,10 +673,36 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
 #pragma unroll
   for (int j = 0; j < D; ++j) z[j] = (j == row0 + tid) ? 1.0 : 0.0;
 
+  // Sweeps are replayed in PAIRS (A = sweep s, B = sweep s + 1), B one 8-column block behind A:
+  // a rotation of B at column j only needs A's rotations at columns j - 1, j, j + 1, so with A
+  // eight columns ahead the two dependent chains are independent and interleave (two FMAs in
+  // flight instead of one, one set of block branches for both).  The QL kernel pads every sweep
+  // to whole blocks with identity rotations, so a block is either active or not: no masks.
+  constexpr int BMAX = (D - 2) / 8;
+  auto blk_hi = [](int b) { return (8 * b + 7 < D - 2) ? 8 * b + 7 : D - 2; };
+  auto single = [&](int b, const double2 *base) {  // loads first, then the dependent chain
+    const int jlo = 8 * b, jhi = blk_hi(b);
+    double2 cs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (jhi - u >= jlo) cs[u] = base[-(jhi - u)];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (jhi - u >= jlo) rot_inplace(z[jhi - u], z[jhi - u + 1], cs[u]);
+  };
+
   size_t g = 0;
-  for (int sidx = 0; sidx < ns; ++sidx) {
-    const int l = sswp[sidx].l, m = sswp[sidx].m;
-    const size_t need = g + (size_t)(m - l);
+  for (int sidx = 0; sidx < ns; sidx += 2) {
+    const int blA = sswp[sidx].l >> 3, bhA = (sswp[sidx].m - 1) >> 3;
+    int blB = 1 << 20, bhB = -1;  // no partner: never active
+    size_t lenB = 0;
+    if (sidx + 1 < ns) {
+      blB = sswp[sidx + 1].l >> 3;
+      bhB = (sswp[sidx + 1].m - 1) >> 3;
+      lenB = (size_t)(blk_hi(bhB) - 8 * blB + 1);
+    }
+    const size_t gB = g + (size_t)(blk_hi(bhA) - 8 * blA + 1);
+    const size_t need = gB + lenB;
     while ((size_t)t_landed * HQL_RTILE < need && t_landed < ntiles) {
       cp_async_wait<0>();
       __syncthreads();
@@ -672,39 +713,39 @@ hql_apply_reg_kernel(int d, const double2 *__restrict__ rot, size_t rot_cap,
       while (t_issued < ntiles && t_issued - consumed < HQL_RTILES - 1) issue();
     }
     // rotation for column j sits at base[-j]
-    const double2 *base = ring + (int)(g % RING) + (m - 1);
+    const double2 *baseA = ring + (int)(g % RING) + blk_hi(bhA);
+    const double2 *baseB = ring + (int)(gB % RING) + blk_hi(bhB < 0 ? 0 : bhB);
 #pragma unroll
-    for (int b = (D - 2) / 8; b >= 0; --b) {
-      const int jlo = 8 * b;
-      const int jhi = (8 * b + 7 < D - 2) ? 8 * b + 7 : D - 2;
-      // QL windows sit at the high end (l grows as eigenvalues converge, m stays near d - 1):
-      // once a block lies below l, so do all the remaining ones.  Each skipped block costs a
-      // dependent uniform compare + branch (~15 cycles), as much as a rotation.
-      if (jhi < l) break;
-      if (jlo < m) {
-        // loads first, then the dependent chain; in a block cut by l or m the rotations
-        // outside [l, m) become the identity (c, s) = (1, 0), which is exact
-        double2 cs[8];
-        if (jlo >= l && jhi < m) {
+    for (int b = BMAX; b >= -1; --b) {
+      // A works on block b, B on block b + 1
+      const bool actA = (b >= 0) && b >= blA && b <= bhA;
+      const bool actB = (b + 1 <= BMAX) && b + 1 >= blB && b + 1 <= bhB;
+      if (actA && actB) {
+        const int jloA = 8 * b, jhiA = blk_hi(b);
+        const int jloB = 8 * (b + 1), jhiB = blk_hi(b + 1);
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (jhi - u >= jlo) cs[u] = base[-(jhi - u)];
-        } else {
+        for (int hf = 0; hf < 2; ++hf) {
+          double2 ca[4], cb[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = jhi - u;
-            if (j >= jlo) {
-              const double2 c1 = base[-j];  // in bounds for every j (guard + mirror)
-              cs[u] = (j < m && j >= l) ? c1 : make_double2(1.0, 0.0);
-            }
+          for (int u = 0; u < 4; ++u) {
+            if (jhiA - 4 * hf - u >= jloA) ca[u] = baseA[-(jhiA - 4 * hf - u)];
+            if (jhiB - 4 * hf - u >= jloB) cb[u] = baseB[-(jhiB - 4 * hf - u)];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ja = jhiA - 4 * hf - u, jb = jhiB - 4 * hf - u;
+            if (ja >= jloA) rot_inplace(z[ja], z[ja + 1], ca[u]);
+            if (jb >= jloB) rot_inplace(z[jb], z[jb + 1], cb[u]);
           }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = jhi - u;
-          if (j >= jlo) rot_inplace(z[j], z[j + 1], cs[u]);
-        }
+      } else if (actA) {
+        single(b, baseA);
+      } else if (actB) {
+        single(b + 1, baseB);
       }
+      // QL windows sit at the high end (l grows as eigenvalues converge, m stays near d - 1):
+      // stop once the remaining blocks lie below both windows
+      if (b - 1 < blA && b < blB) break;
     }
     g = need;
   }

@@ -47,10 +47,11 @@ struct musim_handle {
   double *times_dev = nullptr;
   int times_cap = 0;
   // workspaces (sized for `ws_cfg` configurations)
-  // Two LANES: launch groups alternate between two streams, each with its own workspace set,
-  // so that the latency-bound kernels of one group (the thread-per-matrix QL kernel runs one
-  // warp per SM sub-partition for ~2.5 ms at d = 96; the barrier-bound tridiagonalisation)
-  // overlap with the throughput-bound kernels of the other.
+  // LANES (option "lanes" = 2): launch groups alternate between two streams, each with its own
+  // workspace set, so that the latency-bound kernels of one group could overlap with the
+  // throughput-bound kernels of the other.  Measured on C5: 67.4 vs 67.5 ms -- every kernel of the
+  // pipeline already fills the SMs' register files, so co-resident kernels only take turns.
+  // Default is one lane (kernel times then add up to the step time).
   struct LaneWs {
     double *lam = nullptr;
     cplx *U = nullptr, *T1 = nullptr, *Y = nullptr, *X = nullptr, *W = nullptr, *Oc = nullptr;
@@ -69,7 +70,7 @@ struct musim_handle {
   void *stage = nullptr;
   size_t stage_bytes = 0;
   // options
-  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_lanes = 2;
+  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_lanes = 1;
   cudaEvent_t evIn = nullptr;
   // bookkeeping
   int64_t launches = 0;
@@ -160,7 +161,7 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     g_tridiag_rw = value != 0;
   else if (!strcmp(key, "reflect"))  // 0: form Q in the tridiagonalisation kernel + GEMM back-transformation
     g_reflect = value != 0;
-  else if (!strcmp(key, "lanes"))  // 1: one stream, launch groups run back to back; 2: two concurrent lanes
+  else if (!strcmp(key, "lanes"))  // 1 (default): one stream, launch groups back to back; 2: two concurrent lanes (measured: no gain)
     h->opt_lanes = value < 1 ? 1 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "polar_mma"))  // 1 (default): DMMA polarisation kernel, 0: vector-FMA version
     h->opt_polar_mma = value;
