@@ -52,7 +52,7 @@ struct EighWs {
     const size_t dd = (size_t)d * d;
     if (method == EIGH_HQL)
       return 2 * (2 * d * sizeof(double) + dd * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
-             (2 * dd + 64) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
+             (2 * dd + 64 + 14 * (6 * d + 16)) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
              d * sizeof(unsigned short);
     return jacobi_vglobal(d) ? (size_t)d * (d | 1) * sizeof(cplx) : 0;
   }
@@ -94,7 +94,7 @@ struct EighWs {
 #define EW_ALLOC(ptr, count)                                              \
   if (e == cudaSuccess) e = cudaMalloc((void **)&ptr, (count) * sizeof(*ptr));
     if (method == EIGH_HQL) {
-      rot_cap = 2 * dd + 64;  // ~1.2 d^2 rotations observed; overflow is reported as ENOTCONV
+      rot_cap = 2 * dd + 64 + 14 * (size_t)(6 * d + 16);  // ~1.2 d^2 rotations observed + <= 14 padding entries per sweep; overflow is reported as ENOTCONV
       swp_cap = 6 * d + 16;
       vcap = (size_t)(d - 1) * (d - 2) / 2 + 8;
       for (int i = 0; i < (dbl ? 2 : 1); ++i) {
