@@ -83,7 +83,10 @@ def kernel_flops(name, d, nt):
         "eigh_back": (16.0 / 3) * d**3,  # zunmtr: reflectors applied to the real eigenvector matrix
         "eigh_jacobi": 16.0 * d**3,
         "rotate": 8.0 * d**3,  # one complex GEMM (fast path; O U is formed on the fly)
-        "polar": 10.0 * nt * npairs,
+        # EXECUTED flops of the time-factorised kernel: 2 FMA per (pair incl. diagonal, time).  SURVEY 8(d)
+        # counts 10 flops per (pair, time) for the direct cos/sin evaluation; that figure stays in the
+        # whole-path number (algorithmic_flops) -- here it would put the kernel above the DFMA peak.
+        "polar": 4.0 * nt * (npairs + d),
     }.get(name, 0.0)
 
 
@@ -387,9 +390,15 @@ def main():
     kf = kernel_flops(top, d, nt) * n_local
     achieved = kf / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
     path_flops = algorithmic_flops(d, nt, mode_name) * n_local
+    # DRAM bytes per configuration of each phase at d = 96, from the ncu --set full capture in
+    # profiles/r1_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum over 2960 configurations)
+    ncu_dram_per_cfg_d96 = {"eigh_tridiag": 589.2e6 / 2960, "eigh_tql": 410.9e6 / 2960, "eigh_apply": 1570.4e6 / 2960,
+                            "eigh_back": 821.9e6 / 2960, "rotate": 689.5e6 / 2960, "polar": 246.8e6 / 2960}
+    traffic = ncu_dram_per_cfg_d96[top] * n_local if (d == 96 and top in ncu_dram_per_cfg_d96 and mode_name == "fast") else None
     roofline = {
         "bound": "fp64", "kernel": top, "achieved": achieved, "peak": peak_dfma, "unit": "TFLOP/s",
-        "frac": achieved / peak_dfma if peak_dfma else None, "traffic": None,
+        "frac": achieved / peak_dfma if peak_dfma else None, "traffic": traffic,
+        "traffic_note": "bytes per step of the dominant phase (all its launches), ncu dram read+write per configuration x configurations",
         "peak_source": "measured live: DFMA micro-benchmark musim_fp64_peak (MEASURED_PEAKS.json has no FP64 entry); "
                        "DMMA m8n8k4 measured %.1f TFLOP/s" % peak_dmma,
         "kernel_ms_per_step": top_ms,
