@@ -23,6 +23,7 @@
 #include "lindblad.cuh"
 #include "peak.cuh"
 #include "polar.cuh"
+#include "polar_nufft.cuh"
 #include "rotate.cuh"
 #include "zgemm_dmma.cuh"
 
@@ -62,6 +63,7 @@ struct musim_handle {
   int64_t ws_cfg = 0;
   int ws_lanes = 0;
   LindWs lws;
+  NufftWs nws;
   cplx *exA = nullptr;
   double *exg = nullptr;
   int n_explicit = 0;
@@ -313,6 +315,7 @@ extern "C" int musim_destroy(musim_handle *h) {
   cudaFree(h->status);
   cudaFree(h->stage);
   h->lws.release();
+  h->nws.release();
   cudaFree(h->exA);
   cudaFree(h->exg);
   h->prof.destroy();
@@ -587,13 +590,21 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       ++h->launches;
     } else {
       ProfScope pt(&h->prof, st, PH_POLAR);
-      const bool fact = (h->opt_polar == 2) || (h->opt_polar == 0 && tg.uniform);
-      if (h->opt_polar == 2 && !tg.uniform)
-        return set_err(h, MUSIM_EINVAL, "time-factorised polarisation needs a uniform time grid");
+      if ((h->opt_polar == 2 || h->opt_polar == 3) && !tg.uniform)
+        return set_err(h, MUSIM_EINVAL, "time-factorised / NUFFT polarisation needs a uniform time grid");
+      // uniform grids: type-1 NUFFT (cost per pair independent of nt) once nt is large enough to
+      // pay for the 12-cell spreading; otherwise the time-factorised DMMA kernel
+      const bool nufft = (h->opt_polar == 3 || (h->opt_polar == 0 && tg.uniform && nt >= 96)) &&
+                         nu_supported(nt, n_slots) && lanes == 1;
+      const bool fact = !nufft && (h->opt_polar >= 2 || (h->opt_polar == 0 && tg.uniform));
       int groups = (int)std::min<int64_t>(n, 148);
       int per = (int)((n + groups - 1) / groups);
       groups = (int)((n + per - 1) / per);
-      if (fact) {
+      if (nufft) {
+        CK(launch_polar_nufft(h->nws, d, h->npairs, h->pairs, n, L.W, L.lam, w + c0, slot + c0, nt, tg.t0, tg.dt,
+                              n_slots, out, st, &h->launches));
+        --h->launches;  // counted once more below
+      } else if (fact) {
         int NB = 1;
         while (NB * NB < nt && NB < 32) ++NB;
         const int NA_total = (nt + NB - 1) / NB;

@@ -1,0 +1,532 @@
+// polar_nufft.cuh -- polarisation on a UNIFORM time grid as a type-1 non-uniform FFT.
+//
+//   out[slot_c, k] += weight_c * ( sum_i Re w_ii + 2 sum_{i<j} Re( w_ij exp(-2 pi i f_ij t_k) ) ),
+//   t_k = t0 + k dt,  k = 0 .. N-1,   f_ij = l_i - l_j
+//
+// Replaces the time loop of Hamiltonian.evolve (/root/reference/muspinsim/hamiltonian.py:87-107)
+// and the Cython kernel parallel_fast_time_evolve (cython/parallel.pyx:56-67) -- same sum, other
+// order.  The time-factorised DMMA kernel (polar.cuh) spends 2 FMAs per (pair, time point); on a
+// uniform grid the sum is the discrete Fourier transform of point masses at the non-uniform
+// positions u = -f dt (cycles per step, taken mod 1 -- exact for a uniform grid), so it costs
+// O(w) per PAIR plus one length-M FFT per output row instead:
+//   1. spread kernel: every (configuration, pair) adds  c * phi(m - u M)  to w = 12 neighbouring
+//      cells of a fine grid of M >= 2 N cells (phi = "exponential of semicircle" kernel
+//      exp(beta (sqrt(1 - z^2) - 1)), beta = 2.30 w, evaluated as a degree-10 polynomial per tap);
+//      c carries the weights, exp(-2 pi i f t0) and the half-band shift exp(2 pi i (N/2) u), so
+//      that the wanted modes are k' = k - N/2 in [-N/2, N/2).  All configurations accumulated into
+//      one output row share one grid: the powder average happens BEFORE the transform.
+//   2. FFT kernel (one CTA per output row): s_k' = sum_m grid[m] exp(2 pi i k' m / M), divided
+//      by the kernel's Fourier transform phi^(k').
+// Aliasing error for w = 12, M/N >= 2: 7e-13 * sum|c| (tools/nufft_prototype.py), far inside the
+// 1e-9 parity bar; non-uniform time arrays keep the direct kernel.
+//
+// Spread kernel mapping: one private grid per WARP in shared memory (M complex = 32 KB at
+// N <= 1024: 7 warps per SM), so there are no atomics: a half-warp handles one point, lane = tap,
+// plain read-modify-write of 12 consecutive cells.  The two half-warps' windows may overlap
+// (then the two updates are issued one after the other).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "polar.cuh"
+
+namespace musim {
+
+#define NU_W 12
+#define MUSIM_NU_SMEM (227 * 1024)
+#define NU_DEG 10
+#define NU_BETA (2.30 * NU_W)
+
+// coef[l][m]: phi_l(y) = sum_m coef[l][m] y^m, y = 2 x in [-1, 1], x = fractional offset of the
+// point from the centre of its cell; tap l sits (l - (w-1)/2 - x) cells from the point.
+__constant__ double nu_coef[NU_W][NU_DEG + 1];
+
+struct __align__(16) NuPoint {
+  double cre, cim, y;
+  int base, flag;
+};
+
+__device__ __forceinline__ void lds_f64x2(unsigned addr, double &x, double &y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(x), "=d"(y) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(unsigned addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+
+__device__ __forceinline__ double nu_horner(const double (&cf)[NU_DEG + 1], double y) {
+  double r = cf[NU_DEG];
+#pragma unroll
+  for (int m = NU_DEG - 1; m >= 0; --m) r = fma(r, y, cf[m]);
+  return r;
+}
+
+// units: unit u = (configuration u / S, part u % S of its pair list, `plen` pairs each)
+__global__ void __launch_bounds__(256)
+polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, int n_cfg, int S, int plen,
+                          int units_per_warp, const cplx *__restrict__ W, const double *__restrict__ lam,
+                          const double *__restrict__ wgt, const int *__restrict__ slot, int N, double t0,
+                          double dt, int M, cplx *__restrict__ G, int *__restrict__ touched) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  cplx *grid_all = reinterpret_cast<cplx *>(smem_raw);
+  cplx *grid = grid_all + (size_t)warp * M;
+  NuPoint *stage = reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * M) + warp * 32;
+  int *wslot = reinterpret_cast<int *>(reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * M) + nwarps * 32);
+  const int tap = lane & 15, half = lane >> 4;
+  const bool tap_on = tap < NU_W;
+  const int Mm = M - 1;
+  const unsigned grid_s = (unsigned)__cvta_generic_to_shared(grid);
+  double cf[NU_DEG + 1];
+#pragma unroll
+  for (int m = 0; m <= NU_DEG; ++m) cf[m] = tap_on ? nu_coef[tap_on ? tap : 0][m] : 0.0;
+
+  for (int m = lane; m < M; m += 32) grid[m] = make_c(0.0, 0.0);
+  __syncwarp();
+
+  const size_t dd = (size_t)d * d;
+  const long gw = (long)blockIdx.x * nwarps + warp;
+  const long total_units = (long)n_cfg * S;
+  const long u0 = gw * units_per_warp;
+  const long u1 = min(total_units, u0 + units_per_warp);
+  const double halfN = (double)(N / 2);
+  int cur_slot = -1;
+
+  auto flush_warp = [&](int s) {
+    cplx *Gs = G + (size_t)s * M;
+    for (int m = lane; m < M; m += 32) {
+      const cplx v = grid[m];
+      if (v.x != 0.0) atomicAdd(&Gs[m].x, v.x);
+      if (v.y != 0.0) atomicAdd(&Gs[m].y, v.y);
+      grid[m] = make_c(0.0, 0.0);
+    }
+    if (lane == 0) touched[s] = 1;
+    __syncwarp();
+  };
+
+  // Flat iteration over batches of 32 pairs, software-pipelined: the pair indices are loaded two
+  // batches ahead and W / lambda one batch ahead, so their latency hides behind the spreading.
+  struct It {
+    long u;
+    int c, pb, p_end;
+  };
+  auto it_init = [&](It &it, long u) {
+    it.u = u;
+    it.c = 0;
+    it.pb = 0;
+    it.p_end = 0;
+    if (u < u1) {
+      it.c = (int)(u / S);
+      const int part = (int)(u - (long)it.c * S);
+      it.pb = part * plen;
+      it.p_end = min(npairs, it.pb + plen);
+    }
+  };
+  auto it_next = [&](It &it) {
+    it.pb += 32;
+    if (it.pb >= it.p_end) it_init(it, it.u + 1);
+  };
+  auto load_pair = [&](const It &it) {
+    PairIdx ij;
+    ij.i = 0xffff;  // marks "no point"
+    ij.j = 0;
+    const int p = it.pb + lane;
+    if (it.u < u1 && p < it.p_end) ij = pairs[p];
+    return ij;
+  };
+  struct Dat {
+    cplx w;
+    double li, lj, wc;
+  };
+  auto load_dat = [&](const It &it, PairIdx ij) {
+    Dat q;
+    q.w = make_c(0.0, 0.0);
+    q.li = q.lj = q.wc = 0.0;
+    if (ij.i != 0xffff) {
+      q.w = W[(size_t)it.c * dd + (size_t)ij.i * d + ij.j];
+      q.li = lam[(size_t)it.c * d + ij.i];
+      q.lj = lam[(size_t)it.c * d + ij.j];
+      q.wc = wgt[it.c];
+    }
+    return q;
+  };
+  It i0, i1, i2;
+  it_init(i0, u0);
+  i1 = i0;
+  it_next(i1);
+  i2 = i1;
+  if (i1.u < u1) it_next(i2);
+  PairIdx ij0 = load_pair(i0), ij1 = load_pair(i1);
+  Dat d0 = load_dat(i0, ij0);
+  while (i0.u < u1) {
+    const PairIdx ij2 = load_pair(i2);
+    const Dat d1 = load_dat(i1, ij1);
+    {
+      const int s = slot[i0.c];
+      if (s != cur_slot) {
+        if (cur_slot >= 0) flush_warp(cur_slot);
+        cur_slot = s;
+      }
+    }
+    {
+      // ---- every lane prepares one point ----
+      {
+        NuPoint pt;
+        pt.y = 0.0;
+        pt.cre = 0.0;
+        pt.cim = 0.0;
+        pt.base = 0;
+        pt.flag = 0;
+        if (ij0.i != 0xffff) {
+          const cplx w = d0.w;
+          const double f = d0.li - d0.lj;
+          const double x = f * dt;
+          const double uu = rint(x) - x;  // -frac(f dt) in [-1/2, 1/2]: cycles per time step
+          double pos = uu * (double)M;
+          if (pos < 0.0) pos += (double)M;
+          double fl = floor(pos);
+          if (fl >= (double)M) fl = (double)M - 1.0;  // pos rounded up to M
+          pt.y = 2.0 * (pos - fl) - 1.0;
+          pt.base = ((int)fl - (NU_W / 2 - 1)) & Mm;
+          // strength: weights * exp(-2 pi i f t0) * exp(2 pi i (N/2) u)
+          double ph = fma(halfN, uu, -f * t0);
+          ph -= rint(ph);
+          double sn, cs;
+          sincospi(2.0 * ph, &sn, &cs);
+          const double sc = (ij0.i == ij0.j) ? d0.wc : 2.0 * d0.wc;
+          pt.cre = sc * fma(w.x, cs, -w.y * sn);
+          pt.cim = sc * fma(w.x, sn, w.y * cs);
+        }
+        // points q and q + 16 are updated in the same step by the two half-warps: do their
+        // windows overlap?  (symmetric, so both halves see the same flag)
+        const int ob = __shfl_xor_sync(0xffffffffu, pt.base, 16);
+        const int diff = (pt.base - ob) & Mm;
+        pt.flag = (diff < 16 || diff > M - 16) ? 1 : 0;
+        stage[lane] = pt;
+      }
+      __syncwarp();
+      const NuPoint *mine = stage + half * 16;
+      // everything the 16 steps need goes to registers first, so that no staging load sits
+      // between two dependent grid updates
+      double yy[16], phi[16], cre[16], cim[16];
+      unsigned off[16];
+      unsigned ovl = 0;
+#pragma unroll
+      for (int st = 0; st < 16; ++st) {
+        const double2 a = *reinterpret_cast<const double2 *>(&mine[st].cre);
+        const double2 b = *reinterpret_cast<const double2 *>(&mine[st].y);
+        cre[st] = a.x;
+        cim[st] = a.y;
+        yy[st] = b.x;
+        const int2 bf = *reinterpret_cast<const int2 *>(&b.y);
+        off[st] = grid_s + ((((unsigned)bf.x + tap) & Mm) << 4);
+        ovl |= (unsigned)bf.y << st;
+      }
+      // phase A: the 16 kernel values of this lane's tap, Horner steps interleaved across points
+#pragma unroll
+      for (int st = 0; st < 16; ++st) phi[st] = cf[NU_DEG];
+#pragma unroll
+      for (int m = NU_DEG - 1; m >= 0; --m)
+#pragma unroll
+        for (int st = 0; st < 16; ++st) phi[st] = fma(phi[st], yy[st], cf[m]);
+      // phase B: read-modify-write, one point per half-warp per step (lanes 12..15 of each half
+      // carry zero coefficients and add 0: no predicates; windows count as 16 wide).  Straight-line
+      // code: shared-memory accesses of one converged warp are performed in program order, so the
+      // update of step s is visible to the load of step s+1.  Where the two half-warps' windows
+      // overlap, the upper half skips its store and repeats the step afterwards.
+      const unsigned skip = half ? ovl : 0u;
+#pragma unroll
+      for (int st = 0; st < 16; ++st) {
+        double vx, vy;
+        lds_f64x2(off[st], vx, vy);
+        vx = fma(cre[st], phi[st], vx);
+        vy = fma(cim[st], phi[st], vy);
+        if (!((skip >> st) & 1u)) sts_f64x2(off[st], vx, vy);
+      }
+      if (ovl) {  // warp-uniform, rare
+        __syncwarp();
+#pragma unroll
+        for (int st = 0; st < 16; ++st) {
+          if ((skip >> st) & 1u) {
+            double vx, vy;
+            lds_f64x2(off[st], vx, vy);
+            vx = fma(cre[st], phi[st], vx);
+            vy = fma(cim[st], phi[st], vy);
+            sts_f64x2(off[st], vx, vy);
+          }
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+    }
+    i0 = i1;
+    i1 = i2;
+    if (i2.u < u1) it_next(i2);
+    ij0 = ij1;
+    ij1 = ij2;
+    d0 = d1;
+  }
+  // ---- end: if every warp of the CTA ended on the same output row, reduce the private grids
+  // inside the CTA first (one atomic per cell per CTA instead of per warp) ----
+  if (lane == 0) wslot[warp] = cur_slot;
+  __syncthreads();
+  bool same = true;
+  const int s0 = wslot[0];
+  for (int q = 1; q < nwarps; ++q) same = same && (wslot[q] == s0);
+  if (same) {
+    if (s0 >= 0) {
+      cplx *Gs = G + (size_t)s0 * M;
+      for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        cplx v = grid_all[m];
+        for (int q = 1; q < nwarps; ++q) {
+          const cplx t = grid_all[(size_t)q * M + m];
+          v.x += t.x;
+          v.y += t.y;
+        }
+        if (v.x != 0.0) atomicAdd(&Gs[m].x, v.x);
+        if (v.y != 0.0) atomicAdd(&Gs[m].y, v.y);
+      }
+      if (threadIdx.x == 0) touched[s0] = 1;
+    }
+  } else if (cur_slot >= 0) {
+    flush_warp(cur_slot);
+  }
+}
+
+// One CTA per output row: in-place radix-2 FFT (positive exponent) of the row's fine grid in
+// shared memory, deconvolution, accumulation into out.  Leaves G[row] zeroed and the flag reset,
+// so the workspace keeps its all-zero invariant between launches.
+__global__ void __launch_bounds__(256)
+polar_nufft_fft_kernel(int M, int logM, int N, cplx *__restrict__ G, int *__restrict__ touched,
+                       const double *__restrict__ deconv, double *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx *a = reinterpret_cast<cplx *>(smem_raw);
+  const int row = blockIdx.x;
+  if (!touched[row]) return;
+  cplx *Gs = G + (size_t)row * M;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const int r = (int)(__brev((unsigned)m) >> (32 - logM));
+    a[r] = Gs[m];
+    Gs[m] = make_c(0.0, 0.0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) touched[row] = 0;
+  for (int s = 0; s < logM; ++s) {
+    const int hs = 1 << s;
+    for (int t = threadIdx.x; t < M / 2; t += blockDim.x) {
+      const int k = t & (hs - 1);
+      const int i0 = ((t >> s) << (s + 1)) + k, i1 = i0 + hs;
+      double sn, cs;
+      sincospi((double)k / (double)hs, &sn, &cs);  // exp(+2 pi i k / (2 hs))
+      const cplx x0 = a[i0], x1 = a[i1];
+      const cplx tw = make_c(fma(x1.x, cs, -x1.y * sn), fma(x1.x, sn, x1.y * cs));
+      a[i0] = make_c(x0.x + tw.x, x0.y + tw.y);
+      a[i1] = make_c(x0.x - tw.x, x0.y - tw.y);
+    }
+    __syncthreads();
+  }
+  const int hN = N / 2;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const int idx = (k - hN) & (M - 1);
+    atomicAdd(&out[(size_t)row * N + k], a[idx].x * deconv[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: kernel tables, workspace, launcher
+// ---------------------------------------------------------------------------------------
+inline double nu_es(double z) {
+  if (!(fabs(z) < 1.0)) return 0.0;
+  return exp(NU_BETA * (sqrt(1.0 - z * z) - 1.0));
+}
+
+// per-tap interpolation polynomials at Chebyshev nodes (monomials in y = 2x), long double solve
+inline void nu_build_coef(double coef[NU_W][NU_DEG + 1]) {
+  const int n = NU_DEG + 1;
+  const long double PI = 3.14159265358979323846264338327950288L;
+  for (int l = 0; l < NU_W; ++l) {
+    long double A[NU_DEG + 1][NU_DEG + 2];
+    for (int r = 0; r < n; ++r) {
+      const long double y = cosl(PI * (r + 0.5L) / n);
+      const double dist = (double)l - (NU_W - 1) / 2.0 - (double)(y / 2);
+      long double pw = 1.0L;
+      for (int m = 0; m < n; ++m) {
+        A[r][m] = pw;
+        pw *= y;
+      }
+      A[r][n] = (long double)nu_es(2.0 * dist / NU_W);
+    }
+    for (int c = 0; c < n; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < n; ++r)
+        if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+      for (int m = 0; m <= n; ++m) std::swap(A[c][m], A[piv][m]);
+      for (int r = 0; r < n; ++r) {
+        if (r == c) continue;
+        const long double f = A[r][c] / A[c][c];
+        for (int m = c; m <= n; ++m) A[r][m] -= f * A[c][m];
+      }
+    }
+    for (int m = 0; m < n; ++m) coef[l][m] = (double)(A[m][n] / A[m][m]);
+  }
+}
+
+// deconv[k] = 1 / phi^(k - N/2),  phi^(k') = (w/2) int_{-1}^{1} phi(z) cos(pi w k' z / M) dz
+// (Gauss-Legendre, 128 nodes)
+inline void nu_build_deconv(int N, int M, std::vector<double> &dec) {
+  const int nq = 128;
+  std::vector<double> xq(nq), wq(nq);
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < (nq + 1) / 2; ++i) {
+    double x = cos(PI * (i + 0.75) / (nq + 0.5));
+    double dp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p0 = 1.0, p1 = x;
+      for (int k = 2; k <= nq; ++k) {
+        const double p2 = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+        p0 = p1;
+        p1 = p2;
+      }
+      dp = nq * (x * p1 - p0) / (x * x - 1.0);
+      const double dx = p1 / dp;
+      x -= dx;
+      if (fabs(dx) < 1e-16) break;
+    }
+    {  // derivative at the converged node
+      double p0 = 1.0, p1 = x;
+      for (int k = 2; k <= nq; ++k) {
+        const double p2 = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+        p0 = p1;
+        p1 = p2;
+      }
+      dp = nq * (x * p1 - p0) / (x * x - 1.0);
+    }
+    xq[i] = -x;
+    xq[nq - 1 - i] = x;
+    wq[i] = wq[nq - 1 - i] = 2.0 / ((1.0 - x * x) * dp * dp);
+  }
+  std::vector<double> ph(nq);
+  for (int i = 0; i < nq; ++i) ph[i] = wq[i] * nu_es(xq[i]);
+  dec.resize(N);
+  for (int k = 0; k < N; ++k) {
+    const double kk = (double)(k - N / 2);
+    double s = 0.0;
+    for (int i = 0; i < nq; ++i) s += ph[i] * cos(PI * NU_W * kk * xq[i] / M);
+    dec[k] = 1.0 / (0.5 * NU_W * s);
+  }
+}
+
+struct NufftWs {
+  cplx *G = nullptr;
+  int *touched = nullptr;
+  double *deconv = nullptr;
+  int64_t rows = 0;
+  int M = 0, N = 0, dN = 0, dM = 0;
+  bool coef_ready = false;
+
+  void release() {
+    cudaFree(G);
+    cudaFree(touched);
+    cudaFree(deconv);
+    G = nullptr;
+    touched = nullptr;
+    deconv = nullptr;
+    rows = 0;
+    M = N = dN = dM = 0;
+  }
+};
+
+inline int nu_grid_size(int N) {
+  int M = 64;
+  while (M < 2 * N) M <<= 1;
+  return M;
+}
+
+// Whether the NUFFT path applies: uniform grid handled by the caller; here only sizes.
+inline bool nu_supported(int N, int64_t n_slots) {
+  if (N < 2) return false;
+  const int M = nu_grid_size(N);
+  if (M > 8192) return false;                                    // one private grid per warp must fit an SM
+  if ((double)n_slots * M * sizeof(cplx) > 1.0e9) return false;  // fine-grid workspace
+  return true;
+}
+
+// Returns cudaSuccess or the failing error; *launches += 2.
+inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const PairIdx *pairs, int64_t n,
+                                      const cplx *W, const double *lam, const double *wgt, const int *slot,
+                                      int N, double t0, double dt, int n_slots, double *out, cudaStream_t st,
+                                      int64_t *launches) {
+  cudaError_t e;
+  const int M = nu_grid_size(N);
+  int logM = 0;
+  while ((1 << logM) < M) ++logM;
+  if (!ws.coef_ready) {
+    double coef[NU_W][NU_DEG + 1];
+    nu_build_coef(coef);
+    e = cudaMemcpyToSymbol(nu_coef, coef, sizeof coef);
+    if (e != cudaSuccess) return e;
+    ws.coef_ready = true;
+  }
+  if (ws.M != M || ws.rows < n_slots) {
+    cudaFree(ws.G);
+    cudaFree(ws.touched);
+    ws.G = nullptr;
+    ws.touched = nullptr;
+    ws.rows = 0;
+    e = cudaMalloc((void **)&ws.G, (size_t)n_slots * M * sizeof(cplx));
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc((void **)&ws.touched, (size_t)n_slots * sizeof(int));
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ws.G, 0, (size_t)n_slots * M * sizeof(cplx), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ws.touched, 0, (size_t)n_slots * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    ws.M = M;
+    ws.rows = n_slots;
+  }
+  if (ws.dN != N || ws.dM != M) {
+    std::vector<double> dec;
+    nu_build_deconv(N, M, dec);
+    cudaFree(ws.deconv);
+    ws.deconv = nullptr;
+    e = cudaMalloc((void **)&ws.deconv, (size_t)N * sizeof(double));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(ws.deconv, dec.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);  // `dec` is pageable host memory going out of scope
+    if (e != cudaSuccess) return e;
+    ws.dN = N;
+    ws.dM = M;
+  }
+  // geometry: as many warps (private grids) per CTA as shared memory allows, one CTA per SM
+  const size_t per_warp = (size_t)M * sizeof(cplx) + 32 * sizeof(NuPoint);
+  int nwarps = (int)std::min<size_t>(8, (size_t)(MUSIM_NU_SMEM - 256) / per_warp);
+  if (nwarps < 1) return cudaErrorInvalidConfiguration;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const long total_warps = (long)n_sm * nwarps;
+  int S = 1;
+  if (n < 8 * total_warps) {
+    S = (int)std::min<long>((8 * total_warps + n - 1) / n, std::max(1, npairs / 64));
+    if (S < 1) S = 1;
+  }
+  int plen = (npairs + S - 1) / S;
+  plen = (plen + 31) & ~31;
+  S = (npairs + plen - 1) / plen;
+  const long units = (long)n * S;
+  const int upw = (int)((units + total_warps - 1) / total_warps);
+  const int ctas = (int)((units + (long)upw * nwarps - 1) / ((long)upw * nwarps));
+  const size_t smem = nwarps * per_warp + nwarps * sizeof(int) + 16;
+  e = cudaFuncSetAttribute(polar_nufft_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  polar_nufft_spread_kernel<<<ctas, 32 * nwarps, smem, st>>>(d, npairs, pairs, (int)n, S, plen, upw, W, lam, wgt,
+                                                            slot, N, t0, dt, M, ws.G, ws.touched);
+  const size_t fsmem = (size_t)M * sizeof(cplx);
+  e = cudaFuncSetAttribute(polar_nufft_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+  if (e != cudaSuccess) return e;
+  polar_nufft_fft_kernel<<<n_slots, 256, fsmem, st>>>(M, logM, N, ws.G, ws.touched, ws.deconv, out);
+  *launches += 2;
+  return cudaGetLastError();
+}
+
+}  // namespace musim

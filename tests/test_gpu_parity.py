@@ -27,7 +27,7 @@ def test_golden(name):
     assert np.max(np.abs(got - want)) < TOL
 
 
-@pytest.mark.parametrize("opts", [{"polar": 1}, {"eigh": 1}, {"eigh": 2, "polar": 2}, {"chunk": 3},
+@pytest.mark.parametrize("opts", [{"polar": 1}, {"polar": 3}, {"eigh": 1}, {"eigh": 2, "polar": 2}, {"chunk": 3},
                                   {"polar_mma": 0}, {"sorted": 1}, {"tridiag_reg": 1}, {"lanes": 2}, {"reflect": 0}, {"tridiag_rw": 0}, {"gemm": 1}, {"tridiag_warp": 0}, {"reflect_cpt": 1}, {"tridiag_phases": 0}, {"apply_warp": 0}, {"tql_threads": 32}, {"tql_threads": 8}])
 @pytest.mark.parametrize("name", ["c2_fast_d16", "c2_general_d8_T0p3", "c3_alc_d12", "c5_fast_d96",
                                   "polarization_filerange", "ground_state_T0"])
@@ -43,6 +43,42 @@ def test_nonuniform_times_take_direct_path_and_match():
     assert np.max(np.abs(got - want)) < TOL
     with pytest.raises(ValueError):
         _run(spec, polar=2)  # the factorised kernel refuses non-uniform grids
+    with pytest.raises(ValueError):
+        _run(spec, polar=3)  # and so does the NUFFT kernel
+
+
+@pytest.mark.parametrize("nt,t0", [(2, 0.0), (50, 0.0), (100, 0.3), (1000, 0.0), (1024, 1.7), (1025, 0.0), (4096, 0.0),
+                                   (5000, 0.0)])
+@pytest.mark.parametrize("temperature", [np.inf, 0.4])
+def test_nufft_polarisation_matches_direct_kernel(nt, t0, temperature):
+    """Type-1 NUFFT polarisation (polar=3; the default for uniform grids of >= 96 points) against
+    the direct sincos kernel: fast and general paths, t0 != 0, grid sizes 64 .. 8192 (nt = 5000
+    falls back to the time-factorised kernel)."""
+    from muspinsim_b200 import workloads
+
+    spec = workloads.c2_hfine_powder(n_orient=37, nt=nt, n_h=2, temperature=temperature)
+    spec["time"] = t0 + np.linspace(0.0, 10.0, nt)
+    want, _ = _run(spec, polar=1)
+    got, _ = _run(spec, polar=3)
+    assert np.max(np.abs(got - want)) < 1e-11
+    auto, _ = _run(spec)
+    assert np.max(np.abs(auto - want)) < 1e-11
+
+
+def test_nufft_many_slots_degenerate_spectrum_and_oracle():
+    """Field scan with time as a file range (one fine grid per output row), zero-field row
+    (degenerate eigenvalues: every pair of a multiplet lands on the same cells), few
+    configurations (pair lists split over warps); checked against the CPU oracle."""
+    from muspinsim_b200 import workloads
+    from oracle import muspin_oracle as mo
+
+    spec = workloads.c2_hfine_powder(n_orient=5, nt=128, n_h=1)
+    spec["field"] = [[0.0], [0.005], [0.02]]
+    spec["x_axis"] = "field"
+    want = mo.run_spec(spec, evolve_fn=mo.evolve_vectorised)
+    got, _ = _run(spec, polar=3)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) < TOL
 
 
 @pytest.mark.parametrize("seed", range(4))

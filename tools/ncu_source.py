@@ -46,7 +46,7 @@ for r in rows:
         opsamp[op] += samp
         tot["inst"] += inst
         tot["samp"] += samp
-    a = bysrc.setdefault(cur, [0, 0, collections.Counter()])
+    a = bysrc.setdefault(cur or ("?", "?", "?"), [0, 0, collections.Counter()])
     a[0] += inst
     a[1] += samp
     for s, j in sidx.items():
