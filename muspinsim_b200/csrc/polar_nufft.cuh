@@ -25,6 +25,7 @@
 // plain read-modify-write of 12 consecutive cells.  The two half-warps' windows may overlap
 // (then the two updates are issued one after the other).
 #pragma once
+#include <cstddef>
 #include <vector>
 
 #include "common.cuh"
@@ -53,6 +54,19 @@ __device__ __forceinline__ void sts_f64x2(unsigned addr, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
 
+// volatile: keeps its place between the volatile shared-memory accesses around it (the compiler
+// otherwise sinks the whole polynomial evaluation below the update loop it is meant to overlap)
+__device__ __forceinline__ double fma_pinned(double a, double b, double c) {
+  double r;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;\n" : "=d"(r) : "d"(a), "d"(b), "d"(c));
+  return r;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double r;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(r) : "r"(addr) : "memory");
+  return r;
+}
+
 __device__ __forceinline__ double nu_horner(const double (&cf)[NU_DEG + 1], double y) {
   double r = cf[NU_DEG];
 #pragma unroll
@@ -60,10 +74,19 @@ __device__ __forceinline__ double nu_horner(const double (&cf)[NU_DEG + 1], doub
   return r;
 }
 
-// units: unit u = (configuration u / S, part u % S of its pair list, `plen` pairs each)
+// units: unit u = (configuration u / S, part u % S of its pair list, `plen` pairs each).  CTA b owns
+// the contiguous units [b * units_per_cta, ...); its warps draw them one at a time from a shared
+// counter (the 6 warps of a CTA do not share the 4 schedulers evenly).
+//
+// Per warp and batch of 32 pairs:
+//   prep     every lane turns one pair into a point (cell offset, strength) -> staging buffer
+//   phase A  Horner evaluation of the kernel at this lane's tap for the 16 points of its half-warp
+//   phase B  16 read-modify-write steps on the private grid
+// Software pipeline: pair indices are loaded three batches ahead, W / lambda two batches ahead, and
+// phase A of batch b+1 is interleaved with phase B of batch b (FP64 work under the LDS latency).
 __global__ void __launch_bounds__(256)
 polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, int n_cfg, int S, int plen,
-                          int units_per_warp, const cplx *__restrict__ W, const double *__restrict__ lam,
+                          int units_per_cta, const cplx *__restrict__ W, const double *__restrict__ lam,
                           const double *__restrict__ wgt, const int *__restrict__ slot, int N, double t0,
                           double dt, int M, cplx *__restrict__ G, int *__restrict__ touched) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -72,22 +95,24 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
   cplx *grid = grid_all + (size_t)warp * M;
   NuPoint *stage = reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * M) + warp * 32;
   int *wslot = reinterpret_cast<int *>(reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * M) + nwarps * 32);
+  int *ctr = wslot + nwarps;
   const int tap = lane & 15, half = lane >> 4;
   const bool tap_on = tap < NU_W;
   const int Mm = M - 1;
   const unsigned grid_s = (unsigned)__cvta_generic_to_shared(grid);
+  const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
   double cf[NU_DEG + 1];
 #pragma unroll
   for (int m = 0; m <= NU_DEG; ++m) cf[m] = tap_on ? nu_coef[tap_on ? tap : 0][m] : 0.0;
 
   for (int m = lane; m < M; m += 32) grid[m] = make_c(0.0, 0.0);
-  __syncwarp();
+  if (threadIdx.x == 0) *ctr = 0;
+  __syncthreads();
 
   const size_t dd = (size_t)d * d;
-  const long gw = (long)blockIdx.x * nwarps + warp;
   const long total_units = (long)n_cfg * S;
-  const long u0 = gw * units_per_warp;
-  const long u1 = min(total_units, u0 + units_per_warp);
+  const long U0 = (long)blockIdx.x * units_per_cta;
+  const long U1 = min(total_units, U0 + units_per_cta);
   const double halfN = (double)(N / 2);
   int cur_slot = -1;
 
@@ -103,34 +128,36 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
     __syncwarp();
   };
 
-  // Flat iteration over batches of 32 pairs, software-pipelined: the pair indices are loaded two
-  // batches ahead and W / lambda one batch ahead, so their latency hides behind the spreading.
   struct It {
     long u;
     int c, pb, p_end;
   };
-  auto it_init = [&](It &it, long u) {
-    it.u = u;
+  auto it_draw = [&](It &it) {  // next unit of this CTA (warp-uniform)
+    int k = 0;
+    if (lane == 0) k = atomicAdd(ctr, 1);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    it.u = min(U1, U0 + (long)k);
     it.c = 0;
     it.pb = 0;
     it.p_end = 0;
-    if (u < u1) {
-      it.c = (int)(u / S);
-      const int part = (int)(u - (long)it.c * S);
+    if (it.u < U1) {
+      it.c = (int)(it.u / S);
+      const int part = (int)(it.u - (long)it.c * S);
       it.pb = part * plen;
       it.p_end = min(npairs, it.pb + plen);
     }
   };
   auto it_next = [&](It &it) {
+    if (it.u >= U1) return;
     it.pb += 32;
-    if (it.pb >= it.p_end) it_init(it, it.u + 1);
+    if (it.pb >= it.p_end) it_draw(it);
   };
   auto load_pair = [&](const It &it) {
     PairIdx ij;
     ij.i = 0xffff;  // marks "no point"
     ij.j = 0;
     const int p = it.pb + lane;
-    if (it.u < u1 && p < it.p_end) ij = pairs[p];
+    if (it.u < U1 && p < it.p_end) ij = pairs[p];
     return ij;
   };
   struct Dat {
@@ -149,15 +176,73 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
     }
     return q;
   };
+  // one pair -> one point in the staging buffer; point q of the batch goes to entry 2 (q % 16) +
+  // q / 16, so the two points of a step share a 64-byte line
+  auto prep = [&](PairIdx ij, const Dat &q) {
+    NuPoint pt;
+    pt.y = 0.0;
+    pt.cre = 0.0;
+    pt.cim = 0.0;
+    pt.base = 0;
+    pt.flag = 0;
+    if (ij.i != 0xffff) {
+      const double f = q.li - q.lj;
+      const double x = f * dt;
+      const double uu = rint(x) - x;  // -frac(f dt) in [-1/2, 1/2]: cycles per time step
+      double pos = uu * (double)M;
+      if (pos < 0.0) pos += (double)M;
+      double fl = floor(pos);
+      if (fl >= (double)M) fl = (double)M - 1.0;  // pos rounded up to M
+      pt.y = 2.0 * (pos - fl) - 1.0;
+      pt.base = ((int)fl - (NU_W / 2 - 1)) & Mm;
+      // strength: weights * exp(-2 pi i f t0) * exp(2 pi i (N/2) u)
+      double ph = fma(halfN, uu, -f * t0);
+      ph -= rint(ph);
+      double sn, cs;
+      sincospi(2.0 * ph, &sn, &cs);
+      const double sc = (ij.i == ij.j) ? q.wc : 2.0 * q.wc;
+      pt.cre = sc * fma(q.w.x, cs, -q.w.y * sn);
+      pt.cim = sc * fma(q.w.x, sn, q.w.y * cs);
+    }
+    // points q and q + 16 are updated in the same step by the two half-warps: do their windows
+    // (16 cells: lanes 12..15 add zeros) overlap?  Symmetric, so both halves see the same flag.
+    const int ob = __shfl_xor_sync(0xffffffffu, pt.base, 16);
+    const int diff = (pt.base - ob) & Mm;
+    pt.flag = (diff < 16 || diff > M - 16) ? 1 : 0;
+    stage[2 * tap + half] = pt;
+  };
+
+  double yy[16], phi[16], cre[16], cim[16];
+  unsigned off[16];
+  unsigned ovl = 0;
+  auto load_y = [&]() {
+#pragma unroll
+    for (int st = 0; st < 16; ++st) yy[st] = lds_f64(stage_s + (unsigned)((2 * st + half) * sizeof(NuPoint) + offsetof(NuPoint, y)));
+  };
+  auto load_points = [&]() {
+    ovl = 0;
+#pragma unroll
+    for (int st = 0; st < 16; ++st) {
+      const NuPoint *q = stage + 2 * st + half;
+      const double2 a = *reinterpret_cast<const double2 *>(&q->cre);
+      const int2 bf = *reinterpret_cast<const int2 *>(&q->base);
+      cre[st] = a.x;
+      cim[st] = a.y;
+      off[st] = grid_s + ((((unsigned)bf.x + tap) & Mm) << 4);
+      ovl |= (unsigned)bf.y << st;
+    }
+  };
+
   It i0, i1, i2;
-  it_init(i0, u0);
+  it_draw(i0);
   i1 = i0;
   it_next(i1);
-  i2 = i1;
-  if (i1.u < u1) it_next(i2);
   PairIdx ij0 = load_pair(i0), ij1 = load_pair(i1);
   Dat d0 = load_dat(i0, ij0);
-  while (i0.u < u1) {
+  while (i0.u < U1) {
+    // global loads for the next batches
+    i2 = i1;
+    it_next(i2);
     const PairIdx ij2 = load_pair(i2);
     const Dat d1 = load_dat(i1, ij1);
     {
@@ -167,100 +252,52 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
         cur_slot = s;
       }
     }
-    {
-      // ---- every lane prepares one point ----
-      {
-        NuPoint pt;
-        pt.y = 0.0;
-        pt.cre = 0.0;
-        pt.cim = 0.0;
-        pt.base = 0;
-        pt.flag = 0;
-        if (ij0.i != 0xffff) {
-          const cplx w = d0.w;
-          const double f = d0.li - d0.lj;
-          const double x = f * dt;
-          const double uu = rint(x) - x;  // -frac(f dt) in [-1/2, 1/2]: cycles per time step
-          double pos = uu * (double)M;
-          if (pos < 0.0) pos += (double)M;
-          double fl = floor(pos);
-          if (fl >= (double)M) fl = (double)M - 1.0;  // pos rounded up to M
-          pt.y = 2.0 * (pos - fl) - 1.0;
-          pt.base = ((int)fl - (NU_W / 2 - 1)) & Mm;
-          // strength: weights * exp(-2 pi i f t0) * exp(2 pi i (N/2) u)
-          double ph = fma(halfN, uu, -f * t0);
-          ph -= rint(ph);
-          double sn, cs;
-          sincospi(2.0 * ph, &sn, &cs);
-          const double sc = (ij0.i == ij0.j) ? d0.wc : 2.0 * d0.wc;
-          pt.cre = sc * fma(w.x, cs, -w.y * sn);
-          pt.cim = sc * fma(w.x, sn, w.y * cs);
-        }
-        // points q and q + 16 are updated in the same step by the two half-warps: do their
-        // windows overlap?  (symmetric, so both halves see the same flag)
-        const int ob = __shfl_xor_sync(0xffffffffu, pt.base, 16);
-        const int diff = (pt.base - ob) & Mm;
-        pt.flag = (diff < 16 || diff > M - 16) ? 1 : 0;
-        stage[lane] = pt;
-      }
-      __syncwarp();
-      const NuPoint *mine = stage + half * 16;
-      // everything the 16 steps need goes to registers first, so that no staging load sits
-      // between two dependent grid updates
-      double yy[16], phi[16], cre[16], cim[16];
-      unsigned off[16];
-      unsigned ovl = 0;
+    prep(ij0, d0);
+    __syncwarp();
+    load_y();
+    load_points();
+    // Phases A and B as one systolic schedule: the Horner chain of point q advances by one
+    // iteration in each of the ten steps before step q (true dependencies, so neither compiler
+    // stage can move the polynomial work away from the loads it is meant to overlap); each step
+    // therefore has up to 10 INDEPENDENT DFMAs between the grid load and its use.
+    // Shared-memory accesses of one converged warp are performed in program order, so the
+    // update of step s is visible to the load of step s+1.  Where the two half-warps' windows
+    // overlap, the upper half skips its store and repeats the step afterwards.
 #pragma unroll
-      for (int st = 0; st < 16; ++st) {
-        const double2 a = *reinterpret_cast<const double2 *>(&mine[st].cre);
-        const double2 b = *reinterpret_cast<const double2 *>(&mine[st].y);
-        cre[st] = a.x;
-        cim[st] = a.y;
-        yy[st] = b.x;
-        const int2 bf = *reinterpret_cast<const int2 *>(&b.y);
-        off[st] = grid_s + ((((unsigned)bf.x + tap) & Mm) << 4);
-        ovl |= (unsigned)bf.y << st;
-      }
-      // phase A: the 16 kernel values of this lane's tap, Horner steps interleaved across points
+    for (int q = 0; q < 16; ++q) phi[q] = cf[NU_DEG];
 #pragma unroll
-      for (int st = 0; st < 16; ++st) phi[st] = cf[NU_DEG];
+    for (int it = 0; it < NU_DEG; ++it)  // iterations that fall before step 0
 #pragma unroll
-      for (int m = NU_DEG - 1; m >= 0; --m)
+      for (int q = 0; q < NU_DEG - it; ++q) phi[q] = fma_pinned(phi[q], yy[q], cf[NU_DEG - 1 - it]);
+    const unsigned skip = half ? ovl : 0u;
 #pragma unroll
-        for (int st = 0; st < 16; ++st) phi[st] = fma(phi[st], yy[st], cf[m]);
-      // phase B: read-modify-write, one point per half-warp per step (lanes 12..15 of each half
-      // carry zero coefficients and add 0: no predicates; windows count as 16 wide).  Straight-line
-      // code: shared-memory accesses of one converged warp are performed in program order, so the
-      // update of step s is visible to the load of step s+1.  Where the two half-warps' windows
-      // overlap, the upper half skips its store and repeats the step afterwards.
-      const unsigned skip = half ? ovl : 0u;
+    for (int st = 0; st < 16; ++st) {
+      double vx, vy;
+      lds_f64x2(off[st], vx, vy);
 #pragma unroll
-      for (int st = 0; st < 16; ++st) {
-        double vx, vy;
-        lds_f64x2(off[st], vx, vy);
-        vx = fma(cre[st], phi[st], vx);
-        vy = fma(cim[st], phi[st], vy);
-        if (!((skip >> st) & 1u)) sts_f64x2(off[st], vx, vy);
-      }
-      if (ovl) {  // warp-uniform, rare
-        __syncwarp();
-#pragma unroll
-        for (int st = 0; st < 16; ++st) {
-          if ((skip >> st) & 1u) {
-            double vx, vy;
-            lds_f64x2(off[st], vx, vy);
-            vx = fma(cre[st], phi[st], vx);
-            vy = fma(cim[st], phi[st], vy);
-            sts_f64x2(off[st], vx, vy);
-          }
-          __syncwarp();
-        }
-      }
-      __syncwarp();
+      for (int q = st + 1; q < 16 && q <= st + NU_DEG; ++q)
+        phi[q] = fma_pinned(phi[q], yy[q], cf[NU_DEG - 1 - (st - q + NU_DEG)]);
+      vx = fma(cre[st], phi[st], vx);
+      vy = fma(cim[st], phi[st], vy);
+      if (!((skip >> st) & 1u)) sts_f64x2(off[st], vx, vy);
     }
+    if (ovl) {  // warp-uniform, rare
+      __syncwarp();
+#pragma unroll
+      for (int st = 0; st < 16; ++st) {
+        if ((skip >> st) & 1u) {
+          double vx, vy;
+          lds_f64x2(off[st], vx, vy);
+          vx = fma(cre[st], phi[st], vx);
+          vy = fma(cim[st], phi[st], vy);
+          sts_f64x2(off[st], vx, vy);
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
     i0 = i1;
     i1 = i2;
-    if (i2.u < u1) it_next(i2);
     ij0 = ij1;
     ij1 = ij2;
     d0 = d1;
@@ -514,12 +551,12 @@ inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const Pair
   plen = (plen + 31) & ~31;
   S = (npairs + plen - 1) / plen;
   const long units = (long)n * S;
-  const int upw = (int)((units + total_warps - 1) / total_warps);
-  const int ctas = (int)((units + (long)upw * nwarps - 1) / ((long)upw * nwarps));
-  const size_t smem = nwarps * per_warp + nwarps * sizeof(int) + 16;
+  const long upc = (units + n_sm - 1) / n_sm;  // contiguous units per CTA, drawn dynamically by its warps
+  const int ctas = (int)((units + upc - 1) / upc);
+  const size_t smem = nwarps * per_warp + (nwarps + 1) * sizeof(int) + 16;
   e = cudaFuncSetAttribute(polar_nufft_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  polar_nufft_spread_kernel<<<ctas, 32 * nwarps, smem, st>>>(d, npairs, pairs, (int)n, S, plen, upw, W, lam, wgt,
+  polar_nufft_spread_kernel<<<ctas, 32 * nwarps, smem, st>>>(d, npairs, pairs, (int)n, S, plen, (int)upc, W, lam, wgt,
                                                             slot, N, t0, dt, M, ws.G, ws.touched);
   const size_t fsmem = (size_t)M * sizeof(cplx);
   e = cudaFuncSetAttribute(polar_nufft_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
