@@ -2,6 +2,7 @@
 #pragma once
 #include "eigh_hql.cuh"
 #include "eigh_jacobi.cuh"
+#include "eigh_large.cuh"
 #include "eigh_tridiag_reg.cuh"
 #include "eigh_tridiag_rw.cuh"
 #include "eigh_tridiag_warp.cuh"
@@ -35,6 +36,7 @@ struct EighWs {
   int d = 0, method = 0;
   cplx *Vg = nullptr;
   double *dbuf[2] = {nullptr, nullptr}, *ebuf[2] = {nullptr, nullptr}, *Zt = nullptr;
+  cplx *Awork = nullptr;  // column-major working matrices of the d > HQL_MAX_D path
   cplx *Q[2] = {nullptr, nullptr};  // [2]: stage A (tridiagonalisation) of the next launch group overlaps stage B
   bool dbl = false;
   cplx *Vp[2] = {nullptr, nullptr}, *tauv[2] = {nullptr, nullptr};  // packed reflectors + tau (d <= 96 path)
@@ -51,7 +53,8 @@ struct EighWs {
   static size_t bytes_per_matrix(int method, int d) {
     const size_t dd = (size_t)d * d;
     if (method == EIGH_HQL)
-      return 2 * (2 * d * sizeof(double) + dd * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
+      return (d > HQL_MAX_D ? (size_t)d * (d | 1) * sizeof(cplx) : 0) +
+             2 * (2 * d * sizeof(double) + dd * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
              (2 * dd + 64 + 14 * (6 * d + 16)) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
              d * sizeof(unsigned short);
     return jacobi_vglobal(d) ? (size_t)d * (d | 1) * sizeof(cplx) : 0;
@@ -70,6 +73,8 @@ struct EighWs {
       Vp[i] = tauv[i] = nullptr;
     }
     cudaFree(Zt);
+    cudaFree(Awork);
+    Awork = nullptr;
     cudaFree(rot);
     cudaFree(swp);
     cudaFree(nswp);
@@ -105,6 +110,7 @@ struct EighWs {
         EW_ALLOC(tauv[i], (size_t)n * d);
       }
       EW_ALLOC(Zt, (size_t)n * dd);
+      if (d > HQL_MAX_D) EW_ALLOC(Awork, (size_t)n * d * (d | 1));
       EW_ALLOC(rot, (size_t)n * rot_cap);
       EW_ALLOC(swp, (size_t)n * swp_cap);
       EW_ALLOC(nswp, (size_t)n);
@@ -126,6 +132,24 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
   cudaError_t e;
   if (method == EIGH_HQL) {
     if (!hql_supported(d)) return -5;
+    if (d > HQL_MAX_D) {  // working matrix in global memory (eigh_large.cuh)
+      const HqlLargeGeom lg = hql_large_geom(d);
+      const size_t sm = hql_tridiag_gmem_smem(d, lg);
+      ProfScope ps(prof, st, PH_EIGH_TRIDIAG);
+      if (Ain) {
+        e = cudaFuncSetAttribute(hql_tridiag_gmem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+        hql_tridiag_gmem_kernel<false><<<(unsigned)n, lg.nth, sm, st>>>(d, lg.R, lg.G, H0, Z, B, Ain, ws.Awork, ws.dbuf[buf],
+                                                                        ws.ebuf[buf], ws.Q[buf]);
+      } else {
+        e = cudaFuncSetAttribute(hql_tridiag_gmem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+        hql_tridiag_gmem_kernel<true><<<(unsigned)n, lg.nth, sm, st>>>(d, lg.R, lg.G, H0, Z, B, Ain, ws.Awork, ws.dbuf[buf],
+                                                                       ws.ebuf[buf], ws.Q[buf]);
+      }
+      ++*launches;
+      return (int)cudaGetLastError();
+    }
     const HqlGeom g = hql_geom(d);
     const size_t smem = hql_tridiag_smem(d, g);
     if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
@@ -221,7 +245,8 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   cudaError_t e;
   {
     ProfScope ps(prof, st, PH_EIGH_TQL);
-    const int nt = g_tql_threads;
+    int nt = g_tql_threads;
+    while (nt > 8 && hql_tql_smem(d, nt) > 200 * 1024) nt >>= 1;  // (d, e) of nt matrices per CTA in shared memory
     const int dpad = (!sorted && d <= 96) ? (d <= 32 ? 32 : (d <= 64 ? 64 : 96)) : 0;  // register replay kernel follows
     const unsigned tb = (unsigned)((n + nt - 1) / nt);
     const size_t sm = hql_tql_smem(d, nt);
@@ -239,8 +264,10 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   }
   ++*launches;
   const size_t zsmem = hql_apply_smem(d, ws.swp_cap);
-  e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
-  if (e != cudaSuccess) return (int)e;
+  if (d <= HQL_MAX_D) {
+    e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
+    if (e != cudaSuccess) return (int)e;
+  }
   const int ath = std::min(128, (d + 31) & ~31);
   if (!sorted && d <= 96) {
     // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
@@ -260,6 +287,14 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     else if (nth == 32) APPLY_LAUNCH(96, 32)
     else APPLY_LAUNCH(96, 96)
 #undef APPLY_LAUNCH
+  } else if (d > HQL_MAX_D) {
+    ProfScope ps(prof, st, PH_EIGH_APPLY);
+    const int rb = hql_apply_rows_rb(d);
+    const size_t rsm = hql_apply_rows_smem(d, rb);
+    e = cudaFuncSetAttribute(hql_apply_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+    if (e != cudaSuccess) return (int)e;
+    const dim3 grid((unsigned)n, (unsigned)((d + rb - 1) / rb));
+    hql_apply_rows_kernel<<<grid, rb, rsm, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
   } else {
     ProfScope ps(prof, st, PH_EIGH_APPLY);
     hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);

@@ -24,9 +24,10 @@
 
 namespace musim {
 
-#define HQL_MAX_D 118  // A (d x (d|1) complex) must fit the 227 KB of opt-in shared memory
+#define HQL_MAX_D 112  // A (d x (d|1) complex) + vectors must fit the 227 KB of opt-in shared memory
 
-inline bool hql_supported(int d) { return d >= 1 && d <= HQL_MAX_D; }
+#define HQL_LARGE_MAX_D_ 1024  // global-memory kernels of eigh_large.cuh take over above HQL_MAX_D
+inline bool hql_supported(int d) { return d >= 1 && d <= HQL_LARGE_MAX_D_; }
 
 struct HqlGeom {
   int R, G, nth;

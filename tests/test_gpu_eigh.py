@@ -85,3 +85,28 @@ def test_large_batch_all_matrices_processed():
     rng = np.random.default_rng(9)
     A = _rand_herm(rng, 3000, 12)
     _check(A, 2)
+
+
+@pytest.mark.parametrize("d", [97, 112, 113, 128, 160, 200, 256, 384, 512, 1024])
+def test_large_dimensions_global_memory_path(d):
+    """d > 112 does not fit one SM's shared memory: working matrix in global memory
+    (eigh_large.cuh); d <= 112 stays on the shared-memory kernels."""
+    rng = np.random.default_rng(d)
+    _check(_rand_herm(rng, 3 if d <= 256 else 2, d), 2, tol=5e-13 * max(1.0, d / 96.0))
+
+
+def test_large_dimension_degenerate_and_physical():
+    from muspinsim_b200.spinsys import system_from_spec
+
+    d = 128
+    rng = np.random.default_rng(7)
+    q, _ = np.linalg.qr(_rand_herm(rng, 1, d)[0])
+    lam = (np.arange(d) // 8).astype(float)
+    mats = [(q * lam) @ q.conj().T, np.zeros((d, d), dtype=complex), np.eye(d, dtype=complex) * 2.0]
+    s, _ = system_from_spec({"spins": ["mu", "e"] + ["H"] * 5,
+                             "couplings": [{"type": "hyperfine", "i": 1, "value": np.diag([100.0, 100.0, 120.0])}]
+                             + [{"type": "hyperfine", "i": 3 + k, "j": 2, "value": np.diag([3.0 + k, 4.0, 5.0])} for k in range(5)]})
+    mats.append(s.hamiltonian)  # zero field: massively degenerate
+    mats.append(s.hamiltonian + 0.3 * s.zeeman_operators()[2])
+    A = np.array([0.5 * (m + m.conj().T) for m in mats])
+    _check(A, 2, tol=2e-12)

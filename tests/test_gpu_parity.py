@@ -160,3 +160,20 @@ def test_accumulate_semantics_and_rank_shards():
     a = r.run_partial(0, 2)
     b = r.run_partial(1, 2)
     assert np.max(np.abs(r.config.finish(a + b) - want)) < TOL
+
+
+@pytest.mark.parametrize("temperature", [np.inf, 0.5])
+def test_d128_system_matches_oracle(temperature):
+    """mu + e + 5 x 1H (d = 128): beyond the single-SM eigensolver kernels; whole path against
+    the oracle (fast and general evolve, and the integral)."""
+    from muspinsim_b200 import workloads
+    from oracle import muspin_oracle as mo
+
+    spec = workloads.c2_hfine_powder(n_orient=3, nt=120, n_h=5, temperature=temperature)
+    want = mo.run_spec(spec, evolve_fn=mo.evolve_vectorised)
+    got, _ = _run(spec)
+    assert np.max(np.abs(got - want)) < TOL
+    spec_i = dict(spec, y_axis="integral", x_axis="field", field=[[0.0, 0.0, 0.01], [0.0, 0.0, 0.3]])
+    want = mo.run_spec(spec_i)
+    got, _ = _run(spec_i)
+    assert np.max(np.abs(got - want)) < TOL
