@@ -13,7 +13,8 @@
 //   * E1 = exp(2 pi L dt) by scaling-and-squaring of a degree-12 Taylor polynomial
 //     (Paterson-Stockmeyer), entirely as batched complex GEMMs (rotate.cuh);
 //   * for a uniform grid t_k = t0 + (a NB + b) dt:  P[a,b] = (o^T E1^b) (EB^a v0), EB = E1^NB
-//     (lind_series_kernel: 2*NB-1 mat-vecs per 32x32 block of time points);
+//     (lind_series_kernel: 2*NB-1 mat-vecs per 32x32 block of time points; for d*d > 76 the
+//     matrices are read in place from global memory and only the vectors are kept on chip);
 //   * the integral is one LU solve with partial pivoting (lind_solve_kernel).
 #pragma once
 #include <string>
@@ -266,24 +267,32 @@ __global__ void lind_scale_kernel(size_t total, double s, const cplx *__restrict
 
 // Uniform-grid time series, one CTA (256 threads) per configuration.
 //   v_a = EB^a v0 (v0 = E0 r0 or r0), o_b^T = o^T E1^b, P[a,b] = Re(o_b . v_a)
+template <bool GMEM>
 __global__ void __launch_bounds__(256)
 lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ EB,
                    const cplx *__restrict__ E0, const cplx *__restrict__ r0, const cplx *__restrict__ ov,
-                   const double *__restrict__ wgt, const int *__restrict__ slot, int nt, int NB,
+                   const double *__restrict__ wgt, const int *__restrict__ slot, int nt, int NB, int AB,
                    double *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx *s1 = reinterpret_cast<cplx *>(smem_raw);  // E1 [n][n]
-  cplx *sB = s1 + (size_t)n * n;                   // EB [n][n+1] (padded: read by rows)
-  cplx *sO = sB + (size_t)n * (n + 1);             // OB [32][n]
-  cplx *sV = sO + 32 * (size_t)n;                  // VA [32][n]  (column a stored as a row)
-  cplx *sv = sV + 32 * (size_t)n;                  // [n] scratch
+  // gmem = 0: E1 and EB are copied to shared memory (n <= 76); gmem = 1: read in place from
+  // global memory (L2-resident), only the AB + AB + 1 vectors live in shared memory
   const int tid = threadIdx.x;
   const size_t cfg = blockIdx.x;
   const size_t nn = (size_t)n * n;
-  for (int idx = tid; idx < nn; idx += 256) {
-    s1[idx] = E1[cfg * nn + idx];
-    const int r = idx / n, c = idx - r * n;
-    sB[r * (n + 1) + c] = EB[cfg * nn + idx];
+  if (!GMEM) AB = 32;  // compile-time constant on the shared-memory path
+  cplx *sm0 = reinterpret_cast<cplx *>(smem_raw);
+  const cplx *s1 = GMEM ? E1 + cfg * nn : sm0;                     // E1 [n][n]
+  const int ldB = GMEM ? n : n + 1;
+  const cplx *sB = GMEM ? EB + cfg * nn : sm0 + nn;                // EB [n][ldB] (padded in smem: read by rows)
+  cplx *sO = GMEM ? sm0 : sm0 + nn + (size_t)n * (n + 1);          // OB [AB][n]
+  cplx *sV = sO + (size_t)AB * n;                                  // VA [AB][n]  (column a stored as a row)
+  cplx *sv = sV + (size_t)AB * n;                                  // [n] scratch
+  if (!GMEM) {
+    for (int idx = tid; idx < nn; idx += 256) {
+      sm0[idx] = E1[cfg * nn + idx];
+      const int r = idx / n, c = idx - r * n;
+      sm0[nn + r * (n + 1) + c] = EB[cfg * nn + idx];
+    }
   }
   for (int i = tid; i < n; i += 256) {
     sO[i] = ov[cfg * n + i];
@@ -313,14 +322,14 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
   const int NA_total = (nt + NB - 1) / NB;
   const double wc = wgt[cfg];
   const int sl = slot[cfg];
-  for (int a0 = 0; a0 < NA_total; a0 += 32) {
-    const int na = min(32, NA_total - a0);
+  for (int a0 = 0; a0 < NA_total; a0 += AB) {
+    const int na = min(AB, NA_total - a0);
     // v_a = EB v_{a-1}: thread per row i
     for (int a = (a0 == 0 ? 1 : 0); a < na; ++a) {
       const cplx *vp = (a == 0) ? sv : sV + (size_t)(a - 1) * n;
       for (int i = tid; i < n; i += 256) {
         cplx acc = make_c(0, 0);
-        const cplx *row = sB + (size_t)i * (n + 1);
+        const cplx *row = sB + (size_t)i * ldB;
         for (int k = 0; k < n; ++k) cfma(acc, row[k], vp[k]);
         sV[(size_t)a * n + i] = acc;
       }
@@ -338,29 +347,32 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
       }
     }
     __syncthreads();
-    // carry the last vector into the next block of 32
+    // carry the last vector into the next block
     for (int i = tid; i < n; i += 256) sv[i] = sV[(size_t)(na - 1) * n + i];
     __syncthreads();
   }
 }
 
-inline size_t lind_series_smem(int n) {
-  return ((size_t)n * n + (size_t)n * (n + 1) + 64 * (size_t)n + n) * sizeof(cplx);
+inline size_t lind_series_smem(int n, int AB = 32, bool gmem = false) {
+  return ((gmem ? 0 : (size_t)n * n + (size_t)n * (n + 1)) + 2 * (size_t)AB * n + n) * sizeof(cplx);
 }
 
 // Integral: solve (I/tau - 2 pi L) x = r0 by LU with partial pivoting; val = Re(o . x)/tau.
+template <bool GMEM>
 __global__ void __launch_bounds__(256)
 lind_solve_kernel(int n, const cplx *__restrict__ L, const cplx *__restrict__ r0,
                   const cplx *__restrict__ ov, const double *__restrict__ wgt,
                   const int *__restrict__ slot, double tau, double *__restrict__ out,
-                  int *__restrict__ status) {
+                  int *__restrict__ status, cplx *gwork) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[64];
+  __shared__ int ipiv[4];
   const int ld = n + 2;  // augmented with the rhs column, padded
-  cplx *sM = reinterpret_cast<cplx *>(smem_raw);  // [n][ld]
-  double *red = reinterpret_cast<double *>(sM + (size_t)n * ld);  // [64]
-  int *ipiv = reinterpret_cast<int *>(red + 64);
   const int tid = threadIdx.x;
   const size_t cfg = blockIdx.x;
+  // [n][ld] in shared memory, or (n > 76) in a global workspace: block-scope barriers order
+  // the accesses of one CTA in either memory
+  cplx *sM = GMEM ? gwork + cfg * (size_t)n * ld : reinterpret_cast<cplx *>(smem_raw);
   const size_t nn = (size_t)n * n;
   const double twopi = 6.283185307179586476925286766559, it = 1.0 / tau;
   for (int idx = tid; idx < nn; idx += 256) {
@@ -458,9 +470,7 @@ lind_solve_kernel(int n, const cplx *__restrict__ L, const cplx *__restrict__ r0
   }
 }
 
-inline size_t lind_solve_smem(int n) {
-  return (size_t)n * (n + 2) * sizeof(cplx) + 64 * sizeof(double) + 4 * sizeof(int);
-}
+inline size_t lind_solve_smem(int n) { return (size_t)n * (n + 2) * sizeof(cplx) + 16; }
 
 inline size_t lind_build_smem(int d, int nops) {
   return ((size_t)d * d * (1 + 2 * nops)) * sizeof(cplx) + (LIND_MAX_OPS + 34) * sizeof(double);
@@ -473,10 +483,10 @@ struct LindWs {
   int64_t cap = 0;
   int n = 0;
   cplx *L = nullptr, *X = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *Ra = nullptr, *Rb = nullptr,
-       *E1 = nullptr, *E0 = nullptr, *EBs = nullptr, *r0 = nullptr, *ov = nullptr;
+       *E1 = nullptr, *E0 = nullptr, *EBs = nullptr, *r0 = nullptr, *ov = nullptr, *gwork = nullptr;
   unsigned long long *norm = nullptr;
   void release() {
-    cplx **ps[] = {&L, &X, &X2, &X3, &X4, &Ra, &Rb, &E1, &E0, &EBs, &r0, &ov};
+    cplx **ps[] = {&L, &X, &X2, &X3, &X4, &Ra, &Rb, &E1, &E0, &EBs, &r0, &ov, &gwork};
     for (auto p : ps) {
       cudaFree(*p);
       *p = nullptr;
@@ -486,7 +496,8 @@ struct LindWs {
     cap = 0;
   }
   cudaError_t ensure(int n_, int64_t cnt, bool series) {
-    if (cap >= cnt && n == n_ && (!series || X)) return cudaSuccess;
+    const bool need_g = !series && lind_solve_smem(n_) > 200 * 1024;
+    if (cap >= cnt && n == n_ && (!series || X) && (!need_g || gwork)) return cudaSuccess;
     release();
     n = n_;
     const size_t nn = (size_t)n * n;
@@ -497,6 +508,7 @@ struct LindWs {
     al(&L, cnt * nn);
     al(&r0, (size_t)cnt * n);
     al(&ov, (size_t)cnt * n);
+    if (!series && lind_solve_smem(n) > 200 * 1024) al(&gwork, (size_t)cnt * n * (n + 2));
     if (series) {
       al(&X, cnt * nn);
       al(&X2, cnt * nn);
@@ -581,16 +593,21 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
     return -5;
   }
   const size_t bsmem = lind_build_smem(d, nops);
-  if (bsmem > 227 * 1024 || lind_series_smem(n) > 227 * 1024 || lind_solve_smem(n) > 227 * 1024) {
-    err = "Lindbladian path supports d*d <= 76 (shared-memory resident super-operator)";
+  if (bsmem > 200 * 1024 || n > 1024) {
+    err = "Lindbladian path supports d <= 32 (and fewer dissipators at d = 32: operators are built in shared memory)";
     return -5;
   }
   if (!integral && !uniform) {
     err = "Lindbladian evolution needs a uniform time grid (non-uniform grids: planned)";
     return -5;
   }
+  // n <= 76: super-operator resident in shared memory; above that the series / solve kernels read
+  // the matrices in place from global memory and keep only AB + AB + 1 vectors on chip
+  const bool gmem = lind_series_smem(n) > 227 * 1024 || lind_solve_smem(n) > 227 * 1024;
+  int AB = 32;
+  while (gmem && AB > 2 && lind_series_smem(n, AB, true) > 200 * 1024) AB >>= 1;
   const size_t nn = (size_t)n * n;
-  const int nbuf = integral ? 1 : 11;
+  const int nbuf = integral ? 2 : 11;
   int64_t chunk = chunk_opt > 0 ? chunk_opt : std::max<int64_t>(1, (int64_t)(2.0e9 / (nbuf * nn * sizeof(cplx))));
   chunk = std::min(chunk, n_cfg);
   cudaError_t e = ws.ensure(n, chunk, !integral);
@@ -599,10 +616,13 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
     return -2;
   }
   cudaFuncSetAttribute(lind_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
-  cudaFuncSetAttribute(lind_series_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lind_series_smem(n));
-  cudaFuncSetAttribute(lind_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lind_solve_smem(n));
+  const size_t ssmem = lind_series_smem(n, AB, gmem);
+  const size_t vsmem = gmem ? 16 : lind_solve_smem(n);
+  cudaFuncSetAttribute(lind_series_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+  cudaFuncSetAttribute(lind_series_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+  cudaFuncSetAttribute(lind_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem);
   int NB = 1;
-  while (NB * NB < nt && NB < 32) NB <<= 1;
+  while (NB * NB < nt && NB < AB) NB <<= 1;
   const double twopi = 6.283185307179586476925286766559;
   for (int64_t c0 = 0; c0 < n_cfg; c0 += chunk) {
     const int64_t cnt = std::min(chunk, n_cfg - c0);
@@ -613,8 +633,12 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
                                                         ws.r0, ws.ov, ws.norm);
     ++*launches;
     if (integral) {
-      lind_solve_kernel<<<(unsigned)cnt, 256, lind_solve_smem(n), st>>>(n, ws.L, ws.r0, ws.ov, w + c0, slot + c0, tau,
-                                                                       out, status);
+      if (gmem)
+        lind_solve_kernel<true><<<(unsigned)cnt, 256, vsmem, st>>>(n, ws.L, ws.r0, ws.ov, w + c0, slot + c0, tau, out, status,
+                                                                   ws.gwork);
+      else
+        lind_solve_kernel<false><<<(unsigned)cnt, 256, vsmem, st>>>(n, ws.L, ws.r0, ws.ov, w + c0, slot + c0, tau, out, status,
+                                                                    nullptr);
       ++*launches;
     } else {
       unsigned long long bits = 0;
@@ -646,8 +670,12 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
         }
         E0 = lind_expm(ws, n, cnt, twopi * t0, norm * twopi * fabs(t0), ws.E0, st, launches);
       }
-      lind_series_kernel<<<(unsigned)cnt, 256, lind_series_smem(n), st>>>(n, ws.E1, EB, E0, ws.r0, ws.ov, w + c0,
-                                                                          slot + c0, nt, NB, out);
+      if (gmem)
+        lind_series_kernel<true><<<(unsigned)cnt, 256, ssmem, st>>>(n, ws.E1, EB, E0, ws.r0, ws.ov, w + c0, slot + c0, nt, NB,
+                                                                    AB, out);
+      else
+        lind_series_kernel<false><<<(unsigned)cnt, 256, ssmem, st>>>(n, ws.E1, EB, E0, ws.r0, ws.ov, w + c0, slot + c0, nt, NB,
+                                                                     AB, out);
       ++*launches;
     }
     e = cudaGetLastError();

@@ -102,8 +102,10 @@ def test_edge_cases():
 
     t = np.linspace(0, 10, 100)
     # empty system: constant 0.5 (tests/test_experiment.py:117-133)
-    got, _ = _run({"spins": ["e", "mu"], "time": t})
+    got, _ = _run({"spins": ["e", "mu"], "time": t}, polar=2)
     assert np.max(np.abs(got - 0.5)) < 1e-14
+    got, _ = _run({"spins": ["e", "mu"], "time": t})  # NUFFT path: aliasing error ~1e-11 * sum|w_ij|
+    assert np.max(np.abs(got - 0.5)) < 1e-10
     # single spin, single time point ... and 1025 time points (two a-blocks in the factorised kernel)
     zee = [{"type": "zeeman", "i": 2, "value": [0, 0, 1.0 / mo.MU_GAMMA]}]
     for n in (2, 33, 1025, 2500):
@@ -144,10 +146,12 @@ def test_two_lanes_match_single_stream():
 
     spec = workloads.c2_hfine_powder(n_orient=1500, nt=200, n_h=2)
     a, _ = _run(spec, lanes=2, chunk=200)  # 8 launch groups through 2 lanes
-    b, _ = _run(spec, lanes=1)
+    b, _ = _run(spec, lanes=1, polar=2)     # same polarisation kernel (two lanes use the DMMA one)
     assert np.max(np.abs(a - b)) < 1e-12
+    b, _ = _run(spec, lanes=1)              # default: NUFFT polarisation
+    assert np.max(np.abs(a - b)) < 1e-10
     c, _ = _run(dict(spec, temperature=[0.7]), lanes=2, chunk=300)
-    d, _ = _run(dict(spec, temperature=[0.7]), lanes=1)
+    d, _ = _run(dict(spec, temperature=[0.7]), lanes=1, polar=2)
     assert np.max(np.abs(c - d)) < 1e-12
 
 
@@ -174,6 +178,33 @@ def test_d128_system_matches_oracle(temperature):
     got, _ = _run(spec)
     assert np.max(np.abs(got - want)) < TOL
     spec_i = dict(spec, y_axis="integral", x_axis="field", field=[[0.0, 0.0, 0.01], [0.0, 0.0, 0.3]])
+    want = mo.run_spec(spec_i)
+    got, _ = _run(spec_i)
+    assert np.max(np.abs(got - want)) < TOL
+
+
+@pytest.mark.parametrize("spins,temperature", [(["mu", "e", "H"], 1.0), (["mu", "e", "14N"], np.inf),
+                                               (["mu", "e", "H", "H"], 0.5)])
+def test_lindbladian_beyond_shared_memory_matches_oracle(spins, temperature):
+    """d = 8 keeps the 64 x 64 super-operator in shared memory; d = 12 (n = 144) and d = 16
+    (n = 256) read it in place from global memory.  Evolution and integral against the oracle
+    (which diagonalises L like the reference, lindbladian.py:87-99)."""
+    from muspinsim_b200 import workloads
+    from oracle import muspin_oracle as mo
+
+    rng = np.random.default_rng(len(spins))
+    cpl = [{"type": "hyperfine", "i": 1, "value": np.array([[5.0, 2, 3], [2, 5, 2], [3, 2, 5]])}]
+    for k in range(3, len(spins) + 1):
+        cpl.append({"type": "hyperfine", "i": k, "j": 2, "value": workloads._sym(rng, 3.0)})
+    cpl.append({"type": "dissipation", "i": 1, "value": 0.2})
+    cpl.append({"type": "dissipation", "i": 3, "value": 0.05})
+    spec = {"name": "lind", "spins": spins, "couplings": cpl, "field": [[0.0, 0.0, 0.02]],
+            "temperature": [temperature], "time": np.linspace(0.0, 4.0, 130),
+            "orientation": workloads._euler_rows(np.random.default_rng(3), 3)}
+    want = mo.run_spec(spec)
+    got, _ = _run(spec)
+    assert np.max(np.abs(got - want)) < TOL
+    spec_i = dict(spec, y_axis="integral", x_axis="field", field=[[0.0, 0.0, 0.01], [0.0, 0.0, 0.05]])
     want = mo.run_spec(spec_i)
     got, _ = _run(spec_i)
     assert np.max(np.abs(got - want)) < TOL
