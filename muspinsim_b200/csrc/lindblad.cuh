@@ -353,6 +353,27 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
   }
 }
 
+// Arbitrary time arrays: one time point per launch, P = Re( o^T E v0 ) with E = exp(2 pi L t_k)
+// already formed by the batched matrix exponential.  One CTA per configuration.
+__global__ void __launch_bounds__(256)
+lind_point_kernel(int n, const cplx *__restrict__ E, const cplx *__restrict__ r0, const cplx *__restrict__ ov,
+                  const double *__restrict__ wgt, const int *__restrict__ slot, int nt, int k,
+                  double *__restrict__ out) {
+  __shared__ double red[34];
+  const size_t cfg = blockIdx.x;
+  const cplx *Ec = E + cfg * (size_t)n * n;
+  const cplx *v = r0 + cfg * n, *o = ov + cfg * n;
+  double acc = 0.0;
+  // sum_ij o_i E_ij v_j: thread per (i, j) element, coalesced over j
+  for (size_t idx = threadIdx.x; idx < (size_t)n * n; idx += 256) {
+    const int i = (int)(idx / n), j = (int)(idx - (size_t)i * n);
+    const cplx ev = cmul(Ec[idx], v[j]);
+    acc += o[i].x * ev.x - o[i].y * ev.y;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(&out[(size_t)slot[cfg] * nt + k], wgt[cfg] * acc);
+}
+
 inline size_t lind_series_smem(int n, int AB = 32, bool gmem = false) {
   return ((gmem ? 0 : (size_t)n * n + (size_t)n * (n + 1)) + 2 * (size_t)AB * n + n) * sizeof(cplx);
 }
@@ -583,8 +604,8 @@ struct LindCtx {
 };
 
 inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const double *B, const double *p,
-                        const double *T, const double *w, const int32_t *slot, int nt, bool uniform, double t0,
-                        double dt, double tau, double *out, LindWs &ws, long chunk_opt, int *status,
+                        const double *T, const double *w, const int32_t *slot, int nt, const double *times_host,
+                        bool uniform, double t0, double dt, double tau, double *out, LindWs &ws, long chunk_opt, int *status,
                         cudaStream_t st, int64_t *launches, Profiler *prof, std::string &err) {
   const int d = ctx.P.d, n = d * d;
   const int nops = 2 * ctx.P.n_diss + ctx.P.n_explicit;
@@ -597,9 +618,9 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
     err = "Lindbladian path supports d <= 32 (and fewer dissipators at d = 32: operators are built in shared memory)";
     return -5;
   }
-  if (!integral && !uniform) {
-    err = "Lindbladian evolution needs a uniform time grid (non-uniform grids: planned)";
-    return -5;
+  if (!integral && !uniform && !times_host) {
+    err = "Lindbladian evolution on a non-uniform time grid needs the host time array";
+    return -1;
   }
   // n <= 76: super-operator resident in shared memory; above that the series / solve kernels read
   // the matrices in place from global memory and keep only AB + AB + 1 vectors on chip
@@ -650,6 +671,22 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
       }
       double norm;
       memcpy(&norm, &bits, sizeof norm);
+      if (!uniform) {
+        // arbitrary time rows (the reference evaluates exp(mu_k t) for any t, lindbladian.py:103-108):
+        // one matrix exponential per time point, O(nt n^3) -- correct, not fast
+        for (int k = 0; k < nt; ++k) {
+          const double tk = times_host[k];
+          lind_expm(ws, n, cnt, twopi * tk, norm * twopi * fabs(tk), ws.E1, st, launches);
+          lind_point_kernel<<<(unsigned)cnt, 256, 0, st>>>(n, ws.E1, ws.r0, ws.ov, w + c0, slot + c0, nt, k, out);
+          ++*launches;
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+          err = std::string("Lindblad launch: ") + cudaGetErrorString(e);
+          return -2;
+        }
+        continue;
+      }
       // E1 = exp(2 pi dt L); EB = E1^NB; E0 = exp(2 pi t0 L) if t0 != 0
       lind_expm(ws, n, cnt, twopi * dt, norm * twopi * fabs(dt), ws.E1, st, launches);
       cplx *cur = ws.E1, *EB = ws.E1;

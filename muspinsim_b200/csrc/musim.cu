@@ -475,7 +475,7 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
     if (!h->rho0_explicit && !h->thermal_ok)
       return set_err(h, MUSIM_EINVAL, "thermal rho0 needs a muon (dimension 2) and spins with 2I+1 <= 10; pass rho0");
     CK(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
-    int rc = lindblad_run(ctx, integral, n_cfg, B, p, T, w, slot, nt, tg.uniform, tg.t0, tg.dt, tau, out, h->lws,
+    int rc = lindblad_run(ctx, integral, n_cfg, B, p, T, w, slot, nt, times, tg.uniform, tg.t0, tg.dt, tau, out, h->lws,
                           h->opt_chunk, h->status, st, &h->launches, &h->prof, h->err);
     return rc;
   }

@@ -208,3 +208,16 @@ def test_lindbladian_beyond_shared_memory_matches_oracle(spins, temperature):
     want = mo.run_spec(spec_i)
     got, _ = _run(spec_i)
     assert np.max(np.abs(got - want)) < TOL
+
+
+def test_lindbladian_nonuniform_times_match_oracle():
+    """The reference evaluates the dissipative evolution at arbitrary time rows
+    (lindbladian.py:103-108); the GPU path then forms one matrix exponential per time point."""
+    from muspinsim_b200 import workloads
+    from oracle import muspin_oracle as mo
+
+    spec = workloads.c4_fmuf_dissipation(n_orient=4, nt=10)
+    spec["time"] = np.array([0.0, 0.013, 0.2, 0.21, 0.9, 1.7, 3.0, 3.001, 6.5, 8.0])
+    want = mo.run_spec(spec)
+    got, _ = _run(spec)
+    assert np.max(np.abs(got - want)) < TOL
