@@ -72,7 +72,7 @@ struct musim_handle {
   void *stage = nullptr;
   size_t stage_bytes = 0;
   // options
-  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_lanes = 1;
+  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_lanes = 1, opt_rho0_dense = 0;
   cudaEvent_t evIn = nullptr;
   // bookkeeping
   int64_t launches = 0;
@@ -167,6 +167,8 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->opt_lanes = value < 1 ? 1 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "polar_mma"))  // 1 (default): DMMA polarisation kernel, 0: vector-FMA version
     h->opt_polar_mma = value;
+  else if (!strcmp(key, "rho0_dense"))  // 1: form the dense thermal rho0 and multiply (cross-check of the factored kernel)
+    h->opt_rho0_dense = value;
   else if (!strcmp(key, "sorted"))  // 1: keep eigenpairs sorted inside the pipeline (slower replay kernel)
     h->opt_sorted = value;
   else
@@ -563,7 +565,19 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
     if (general) {
       const cplx *R = h->rho0_explicit;
       size_t rs = 0;
-      if (!R) {
+      bool have_t1 = false;
+      if (!R && h->opt_rho0_dense == 0) {
+        // thermal product state: T1 = rho0 U applied factor by factor, rho0 is never formed
+        ProfScope pt(&h->prof, st, PH_RHO0);
+        const size_t sm = rho0_apply_smem(d, h->tab);
+        CK(cudaFuncSetAttribute(rho0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        const int64_t nthr = n * h->tab.n_spins;
+        rho0_factors_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>(n, dd, h->tab, B + 3 * c0, p + 3 * c0, T + c0,
+                                                                            L.Oc);
+        rho0_apply_kernel<<<(unsigned)n, 256, sm, st>>>(d, h->tab, L.Oc, dd, L.U, L.T1);
+        h->launches += 2;
+        have_t1 = true;
+      } else if (!R) {
         ProfScope pt(&h->prof, st, PH_RHO0);
         rho0_kernel<<<(unsigned)n, 128, 0, st>>>(d, h->tab, B + 3 * c0, p + 3 * c0, T + c0, L.Oc);
         ++h->launches;
@@ -573,11 +587,14 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       ProfScope pt(&h->prof, st, PH_ROTATE);
       if (mma) {
         // rho' = U^H (rho0 U);  W = rho' .* conj(O')  in the epilogue
-        launch_zgemm_dmma<false, 0, false>(d, n, R, rs, L.U, dd, L.T1, 1.0, nullptr, h->mu, nullptr, st);
+        if (!have_t1) {
+          launch_zgemm_dmma<false, 0, false>(d, n, R, rs, L.U, dd, L.T1, 1.0, nullptr, h->mu, nullptr, st);
+          ++h->launches;
+        }
         launch_zgemm_dmma<true, 3, false>(d, n, L.U, dd, L.T1, dd, L.W, 1.0, L.Y, h->mu, nullptr, st, upper);
-        h->launches += 2;
+        ++h->launches;
       } else {
-        launch_gemm<false, 0>(d, n, R, rs, L.U, dd, L.T1, 1.0, st, &h->launches);
+        if (!have_t1) launch_gemm<false, 0>(d, n, R, rs, L.U, dd, L.T1, 1.0, st, &h->launches);
         launch_gemm<true, 0>(d, n, L.U, dd, L.T1, dd, L.X, 1.0, st, &h->launches);
         const size_t tot = (size_t)n * dd;
         weights_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, L.X, L.Y, L.W);

@@ -94,6 +94,14 @@ __device__ inline void thermal_factor(int n, double gamma, double bx, double by,
     for (int a = 0; a < n; ++a) rho[a * n + a] = make_c(1.0 / n, 0.0);
     return;
   }
+  if (n == 2) {  // spin 1/2: P_+- = 1/2 +- n.S, so rho = 1/2 + (p_+ - p_-) n.S
+    spin_dot(2, bx / Bn, by / Bn, bz / Bn, rho);
+    const double dp = pm[0] - pm[1];
+    for (int i = 0; i < 4; ++i) rho[i] = cscale(dp, rho[i]);
+    rho[0].x += 0.5;
+    rho[3].x += 0.5;
+    return;
+  }
   cplx h[MUSIM_MAX_SDIM * MUSIM_MAX_SDIM], P[MUSIM_MAX_SDIM * MUSIM_MAX_SDIM],
       Q[MUSIM_MAX_SDIM * MUSIM_MAX_SDIM];
   spin_dot(n, bx / Bn, by / Bn, bz / Bn, h);
@@ -168,6 +176,142 @@ __global__ void rho0_kernel(int d, SpinTable tab, const double *__restrict__ Bf,
     }
     R[cfg * dd + idx] = v;
   }
+}
+
+// X <- (1 (x) f (x) 1) X for one single-spin factor f (n x n) on a tile of 32 columns: lane = column,
+// the warps stride over the d / n row groups {hi*n*stride + a*stride + lo, a = 0 .. n-1}.
+// N > 0: compile-time spin dimension (factor and inputs in registers), N = 0: run-time n.
+template <int N>
+__device__ __forceinline__ void kron_factor_apply(int d, int stride, const cplx *f, cplx *X, int n_rt = 0) {
+  const int n = N > 0 ? N : n_rt;
+  const int groups = d / n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  cplx fr[N > 0 ? N * N : 1];
+  if (N > 0) {
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) fr[i] = f[i];
+  }
+  for (int gi = warp; gi < groups; gi += nw) {
+    const int hi = gi / stride, lo = gi - hi * stride;
+    cplx *x0 = X + ((size_t)hi * n * stride + lo) * 32 + lane;
+    const size_t rs = (size_t)stride * 32;
+    if (N > 0) {
+      cplx xin[N > 0 ? N : 1];
+#pragma unroll
+      for (int b = 0; b < N; ++b) xin[b] = x0[b * rs];
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+        cplx acc = make_c(0.0, 0.0);
+#pragma unroll
+        for (int b = 0; b < N; ++b) cfma(acc, fr[a * N + b], xin[b]);
+        x0[a * rs] = acc;
+      }
+    } else {
+      cplx xin[MUSIM_MAX_SDIM];
+      for (int b = 0; b < n; ++b) xin[b] = x0[b * rs];
+      for (int a = 0; a < n; ++a) {
+        cplx acc = make_c(0.0, 0.0);
+        for (int b = 0; b < n; ++b) cfma(acc, f[a * n + b], xin[b]);
+        x0[a * rs] = acc;
+      }
+    }
+  }
+}
+
+// T1 = rho0 U without forming rho0: rho0 = (x)_s f_s is a Kronecker product of single-spin
+// density matrices (experiment.py:170-236, spinop.py:266-295), so it is applied factor by factor,
+//   X <- (1 (x) f_s (x) 1) X    for s = 0 .. n_spins-1,
+// at d^2 * sum_s n_s complex FMAs instead of the d^3 of the dense product (7x fewer at d = 96),
+// and the d x d matrix rho0 never exists in memory.  One CTA per configuration; U is processed
+// in tiles of 32 columns held in shared memory (lane = column).
+// Single-spin factors of the thermal product state, one THREAD per (configuration, spin): the
+// Lagrange-projector arithmetic is serial per spin and would otherwise sit in front of every
+// CTA of rho0_apply_kernel.  F[cfg][off_s .. off_s + n_s^2), off_s = sum_{q<s} n_q^2  (<= d^2 entries).
+__global__ void rho0_factors_kernel(int64_t n_cfg, size_t fstride, SpinTable tab, const double *__restrict__ Bf,
+                                    const double *__restrict__ pf, const double *__restrict__ Tf,
+                                    cplx *__restrict__ F) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cfg * tab.n_spins) return;
+  const int64_t cfg = t / tab.n_spins;
+  const int s = (int)(t - cfg * tab.n_spins);
+  int off = 0;
+  for (int q = 0; q < s; ++q) off += tab.dims[q] * tab.dims[q];
+  const int n = tab.dims[s];
+  cplx fac[MUSIM_MAX_SDIM * MUSIM_MAX_SDIM];
+  if (s == tab.muon_index) {
+    // pure state along p:  1/2 + p_hat . S   (DensityOperator.from_vectors, spinop.py:455-530)
+    double px = pf[cfg * 3], py = pf[cfg * 3 + 1], pz = pf[cfg * 3 + 2];
+    const double pn = sqrt(px * px + py * py + pz * pz);
+    if (pn > 0.0) {
+      px /= pn;
+      py /= pn;
+      pz /= pn;
+    }
+    spin_dot(2, px, py, pz, fac);
+    fac[0].x += 0.5;
+    fac[3].x += 0.5;
+  } else {
+    thermal_factor(n, tab.gammas[s], Bf[cfg * 3], Bf[cfg * 3 + 1], Bf[cfg * 3 + 2], Tf[cfg], fac);
+  }
+  for (int i = 0; i < n * n; ++i) F[cfg * fstride + off + i] = fac[i];
+}
+
+__global__ void __launch_bounds__(256, 4)
+rho0_apply_kernel(int d, SpinTable tab, const cplx *__restrict__ F, size_t fstride,
+                  const cplx *__restrict__ U, cplx *__restrict__ T1) {
+  extern __shared__ __align__(16) unsigned char rho_smem[];
+  cplx *X = reinterpret_cast<cplx *>(rho_smem);  // [d][32]
+  cplx *facs = X + (size_t)d * 32;                // single-spin factors, packed (sum_s n_s^2 entries)
+  const size_t cfg = blockIdx.x;
+  int nfac = 0;
+  for (int s = 0; s < tab.n_spins; ++s) nfac += tab.dims[s] * tab.dims[s];
+  for (int i = threadIdx.x; i < nfac; i += blockDim.x) facs[i] = F[cfg * fstride + i];
+  __syncthreads();
+  const size_t dd = (size_t)d * d;
+  const cplx *Uc = U + cfg * dd;
+  cplx *Tc = T1 + cfg * dd;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c0 = 0; c0 < d; c0 += 32) {
+    const bool col_ok = c0 + lane < d;
+    for (int i = warp; i < d; i += nw) X[(size_t)i * 32 + lane] = col_ok ? Uc[(size_t)i * d + c0 + lane] : make_c(0.0, 0.0);
+    __syncthreads();
+    int stride = d, foff = 0;
+    for (int s = 0; s < tab.n_spins; ++s) {
+      const int n = tab.dims[s];
+      stride /= n;  // product of the dimensions after spin s
+      const cplx *f = facs + foff;
+      foff += n * n;
+      // a real multiple of the identity (T = inf, B = 0) only scales
+      bool ident = f[0].y == 0.0;
+      for (int a = 0; a < n && ident; ++a)
+        for (int b = 0; b < n; ++b)
+          if (a != b ? (f[a * n + b].x != 0.0 || f[a * n + b].y != 0.0) : (f[a * n + a].x != f[0].x || f[a * n + a].y != 0.0))
+            ident = false;
+      if (ident) {
+        const double sc = f[0].x;
+        if (sc != 1.0)
+          for (int i = warp; i < d; i += nw) X[(size_t)i * 32 + lane] = cscale(sc, X[(size_t)i * 32 + lane]);
+      } else if (n == 2) {
+        kron_factor_apply<2>(d, stride, f, X);
+      } else if (n == 3) {
+        kron_factor_apply<3>(d, stride, f, X);
+      } else if (n == 4) {
+        kron_factor_apply<4>(d, stride, f, X);
+      } else {
+        kron_factor_apply<0>(d, stride, f, X, n);
+      }
+      __syncthreads();
+    }
+    if (col_ok)
+      for (int i = warp; i < d; i += nw) Tc[(size_t)i * d + c0 + lane] = X[(size_t)i * 32 + lane];
+    __syncthreads();
+  }
+}
+
+inline size_t rho0_apply_smem(int d, const SpinTable &tab) {  // one tile of 32 columns + the packed factors
+  size_t nfac = 0;
+  for (int s = 0; s < tab.n_spins; ++s) nfac += (size_t)tab.dims[s] * tab.dims[s];
+  return ((size_t)d * 32 + nfac) * sizeof(cplx);
 }
 
 // ---------------------------------------------------------------------------------------
