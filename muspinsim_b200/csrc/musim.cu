@@ -540,7 +540,7 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
         if (!general)  // fast path: W = |O'|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
           launch_zgemm_dmma<true, 1, true>(d, n, L.U, dd, L.U, dd, L.W, sc, nullptr, h->mu, p + 3 * c0, st, upper);
         else
-          launch_zgemm_dmma<true, 0, true>(d, n, L.U, dd, L.U, dd, L.Y, 1.0, nullptr, h->mu, p + 3 * c0, st);
+          launch_zgemm_dmma<true, 0, true>(d, n, L.U, dd, L.U, dd, L.Y, 1.0, nullptr, h->mu, p + 3 * c0, st, upper);  // only the tiles W needs
         ++h->launches;
       } else {
         dim3 g1((unsigned)((dd + 255) / 256), (unsigned)n);
