@@ -167,6 +167,8 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->opt_lanes = value < 1 ? 1 : (value > 2 ? 2 : value);
   else if (!strcmp(key, "polar_mma"))  // 1 (default): DMMA polarisation kernel, 0: vector-FMA version
     h->opt_polar_mma = value;
+  else if (!strcmp(key, "zgemm_pipe"))
+    g_zgemm_pipe = value != 0;
   else if (!strcmp(key, "rho0_dense"))  // 1: form the dense thermal rho0 and multiply (cross-check of the factored kernel)
     h->opt_rho0_dense = value;
   else if (!strcmp(key, "sorted"))  // 1: keep eigenpairs sorted inside the pipeline (slower replay kernel)

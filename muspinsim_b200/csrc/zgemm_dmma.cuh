@@ -23,32 +23,39 @@
 namespace musim {
 
 #define ZG_KS 16
+static bool g_zgemm_pipe = true;  // option "zgemm_pipe": 12-warp register-prefetch variant for upper-triangle outputs at d in (64, 96]
 
 struct MuonObs {   // O = [[pz/2, (px - i py)/2], [(px + i py)/2, -pz/2]] on the muon index
   int stride;      // product of the dimensions of the spins after the muon
   int enabled;
 };
 
-template <int T, bool CONJ_A, int EPI, bool B_MUON>
-__global__ void __launch_bounds__(64 * T * T, (T == 3 ? 1 : (T == 2 ? 2 : 8)))
+// PIPE (T = 3, upper only): 12 warps, one per LIVE tile (the 6 tiles strictly below the diagonal
+// are not assigned at all), which lifts the register cap from 112 to 168 and leaves room to
+// prefetch the next K slab into registers while the DMMAs of the current one run.
+template <int T, bool CONJ_A, int EPI, bool B_MUON, bool PIPE = false>
+__global__ void __launch_bounds__(PIPE ? 384 : 64 * T * T, (T == 3 ? 1 : (T == 2 ? 2 : 8)))
 zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx *__restrict__ B,
                   size_t b_stride, cplx *C, double scale, const cplx *D, MuonObs mu,
                   const double *__restrict__ pvec, int upper) {
   constexpr int DP = 32 * T;     // padded dimension
   constexpr int LD = DP + 4;     // = 4 (mod 16)
   constexpr int LDK = ZG_KS + 4; // for the non-transposed A slab [m][k]
-  constexpr int NT = 64 * T * T;
+  constexpr int NT = PIPE ? 384 : 64 * T * T;
+  static_assert(!PIPE || T == 3, "PIPE is the T = 3 upper-triangle variant");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sAr = reinterpret_cast<double *>(smem_raw);
   double *sAi = sAr + (CONJ_A ? ZG_KS * LD : DP * LDK);
   double *sBr = sAi + (CONJ_A ? ZG_KS * LD : DP * LDK);
   double *sBi = sBr + ZG_KS * LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp / (2 * T), wn = warp % (2 * T);  // this warp's 32 (rows) x 16 (columns) tile
+  // this warp's 32 (rows) x 16 (columns) tile; PIPE: the 12 tiles with 16 wn + 15 >= 32 wm
+  const int wm = PIPE ? (warp < 6 ? 0 : (warp < 10 ? 1 : 2)) : warp / (2 * T);
+  const int wn = PIPE ? (warp < 6 ? warp : (warp < 10 ? warp - 4 : warp - 6)) : warp % (2 * T);
   const int fr = lane >> 2, fk = lane & 3;
   // upper: the consumer reads C[i][j] for i <= j only (Hermitian result): warps whose tile lies
   // strictly below the diagonal only help staging
-  const bool tile_live = !upper || (wn * 16 + 15 >= wm * 32);
+  const bool tile_live = PIPE || !upper || (wn * 16 + 15 >= wm * 32);
   const size_t cfg = blockIdx.x;
   const size_t dd = (size_t)d * d;
   const cplx *Ab = A + cfg * a_stride;
@@ -65,6 +72,107 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
 #pragma unroll
     for (int j = 0; j < 2; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
 
+  if (PIPE) {
+    // element e of a slab: A element (k = e / DP, m = e % DP) [CONJ_A] and B element (k, n) likewise;
+    // thread t owns e = t, t + NT, ... (4 of each)
+    constexpr int EPT = (ZG_KS * DP + NT - 1) / NT;
+    cplx ra[EPT], rb[EPT];
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int q = 0; q < EPT; ++q) {
+        const int e = tid + q * NT;
+        ra[q] = make_c(0.0, 0.0);
+        rb[q] = make_c(0.0, 0.0);
+        if (e < ZG_KS * DP) {
+          if (CONJ_A) {
+            const int k = e / DP, m = e - k * DP;
+            if (k0 + k < d && m < d) ra[q] = Ab[(size_t)(k0 + k) * d + m];
+          } else {
+            const int m = e / ZG_KS, k = e - m * ZG_KS;
+            if (k0 + k < d && m < d) ra[q] = Ab[(size_t)m * d + k0 + k];
+          }
+          const int k = e / DP, n = e - k * DP;
+          const int kk = k0 + k;
+          if (kk < d && n < d) {
+            if (B_MUON) {
+              const int m = (kk / mu.stride) & 1;
+              const cplx u0 = Bb[(size_t)kk * d + n];
+              const cplx u1 = Bb[(size_t)(m ? kk - mu.stride : kk + mu.stride) * d + n];
+              const double dg = m ? -pz : pz;
+              const double oy = m ? py : -py;
+              rb[q].x = dg * u0.x + px * u1.x - oy * u1.y;
+              rb[q].y = dg * u0.y + px * u1.y + oy * u1.x;
+            } else {
+              rb[q] = Bb[(size_t)kk * d + n];
+            }
+          }
+        }
+      }
+    };
+    auto deposit = [&]() {
+#pragma unroll
+      for (int q = 0; q < EPT; ++q) {
+        const int e = tid + q * NT;
+        if (e < ZG_KS * DP) {
+          if (CONJ_A) {
+            const int k = e / DP, m = e - k * DP;
+            sAr[k * LD + m] = ra[q].x;
+            sAi[k * LD + m] = ra[q].y;
+          } else {
+            const int m = e / ZG_KS, k = e - m * ZG_KS;
+            sAr[m * LDK + k] = ra[q].x;
+            sAi[m * LDK + k] = ra[q].y;
+          }
+          const int k = e / DP, n = e - k * DP;
+          sBr[k * LD + n] = rb[q].x;
+          sBi[k * LD + n] = rb[q].y;
+        }
+      }
+    };
+    fetch(0);
+    deposit();
+    __syncthreads();
+    for (int k0 = 0; k0 < d; k0 += ZG_KS) {
+      const bool more = k0 + ZG_KS < d;
+      if (more) fetch(k0 + ZG_KS);  // global loads in flight during the DMMAs below
+#pragma unroll
+      for (int ks = 0; ks < ZG_KS; ks += 4) {
+        double ar[4], ai[4], br[2], bi[2], nb[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = wm * 32 + i * 8 + fr;
+          if (CONJ_A) {
+            ar[i] = sAr[(ks + fk) * LD + m];
+            ai[i] = -sAi[(ks + fk) * LD + m];  // conj
+          } else {
+            ar[i] = sAr[m * LDK + ks + fk];
+            ai[i] = sAi[m * LDK + ks + fk];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int n = wn * 16 + j * 8 + fr;
+          br[j] = sBr[(ks + fk) * LD + n];
+          bi[j] = sBi[(ks + fk) * LD + n];
+          nb[j] = -bi[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+            dmma884(cr[i][j][0], cr[i][j][1], ai[i], nb[j]);
+            dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+            dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+          }
+      }
+      __syncthreads();
+      if (more) {
+        deposit();
+        __syncthreads();
+      }
+    }
+  } else {
   for (int k0 = 0; k0 < d; k0 += ZG_KS) {
     // ---- stage the K slab (planar re / im) ----
     if (CONJ_A) {
@@ -141,6 +249,7 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
     }
     __syncthreads();
   }
+  }
   if (!tile_live) return;
   // ---- epilogue ----
 #pragma unroll
@@ -186,6 +295,11 @@ inline bool launch_zgemm_dmma(int d, int64_t n, const cplx *A, size_t as, const 
     zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON><<<(unsigned)n, 256, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
   } else {
     const size_t sm = zgemm_dmma_smem<3, CONJ_A>();
+    if (upper && g_zgemm_pipe) {
+      cudaFuncSetAttribute(zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON, true><<<(unsigned)n, 384, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, 1);
+      return true;
+    }
     cudaFuncSetAttribute(zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON><<<(unsigned)n, 576, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
   }
