@@ -16,6 +16,7 @@ namespace musim {
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
 static bool g_tridiag_warp = true; // option "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
+static bool g_small24 = true;      // option "small24": D = 16 / 24 instantiations of the replay / reflector kernels for d <= 16 / 24 (else D = 32)
 static bool g_tridiag_wreg = false; // option "tridiag_wreg": ... with the matrix rows in registers (measured slower: 34 vs 23 ms per 10^6 d = 24 matrices; dead columns and jump-table picks cost more than the shared-memory traffic saved)
 static bool g_tridiag_phases = true;  // option "tridiag_phases": K1 in up to three launches of decreasing size
 static bool g_apply_warp = true;   // option "apply_warp": rotation replay with one warp per CTA (d > 32)
@@ -259,7 +260,7 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     ProfScope ps(prof, st, PH_EIGH_TQL);
     int nt = g_tql_threads;
     while (nt > 8 && hql_tql_smem(d, nt) > 200 * 1024) nt >>= 1;  // (d, e) of nt matrices per CTA in shared memory
-    const int dpad = (!sorted && d <= 96) ? (d <= 32 ? 32 : (d <= 64 ? 64 : 96)) : 0;  // register replay kernel follows
+    const int dpad = (!sorted && d <= 96) ? (d <= 16 && g_small24 ? 16 : (d <= 24 && g_small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)))) : 0;  // register replay kernel follows
     const unsigned tb = (unsigned)((n + nt - 1) / nt);
     const size_t sm = hql_tql_smem(d, nt);
 #define TQL_LAUNCH(NT)                                                                                       \
@@ -283,8 +284,8 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   const int ath = std::min(128, (d + 31) & ~31);
   if (!sorted && d <= 96) {
     // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
-    const int D = d <= 32 ? 32 : (d <= 64 ? 64 : 96);
-    const int nth = g_apply_warp ? 32 : D;  // option "apply_warp": one warp (32 rows of Z) per CTA
+    const int D = d <= 16 && g_small24 ? 16 : (d <= 24 && g_small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)));
+    const int nth = D < 32 ? D : (g_apply_warp ? 32 : D);  // option "apply_warp": one warp (32 rows of Z) per CTA
     const size_t rsmem = hql_apply_reg_smem(D, nth, ws.swp_cap);
     const dim3 grid((unsigned)n, D / nth);
     ProfScope ps(prof, st, PH_EIGH_APPLY);
@@ -293,7 +294,9 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     cudaFuncSetAttribute(hql_apply_reg_kernel<DD, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem); \
     hql_apply_reg_kernel<DD, NTH><<<grid, NTH, rsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.Zt); \
   }
-    if (D == 32) APPLY_LAUNCH(32, 32)
+    if (D == 16) APPLY_LAUNCH(16, 16)
+    else if (D == 24) APPLY_LAUNCH(24, 24)
+    else if (D == 32) APPLY_LAUNCH(32, 32)
     else if (D == 64 && nth == 32) APPLY_LAUNCH(64, 32)
     else if (D == 64) APPLY_LAUNCH(64, 64)
     else if (nth == 32) APPLY_LAUNCH(96, 32)
@@ -317,7 +320,15 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     if (use_reflect(d)) {
       if (d <= 32) {
         const size_t sm = hql_reflect_smem(32);
-        if (d <= 24) {  // one thread per column (warp per matrix): the dot products are thread-local
+        if (d <= 16 && g_small24) {
+          const size_t sm16 = hql_reflect_smem(16);
+          cudaFuncSetAttribute(hql_reflect_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
+          hql_reflect_kernel<16, 1><<<(unsigned)n, 16, sm16, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        } else if (d <= 24 && g_small24) {  // D = 24 instantiation: 24 rows per thread instead of 32 (fewer registers, more warps)
+          const size_t sm24 = hql_reflect_smem(24);
+          cudaFuncSetAttribute(hql_reflect_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm24);
+          hql_reflect_kernel<24, 1><<<(unsigned)n, 24, sm24, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        } else if (d <= 24) {  // one thread per column (warp per matrix): the dot products are thread-local
           cudaFuncSetAttribute(hql_reflect_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
           hql_reflect_kernel<32, 1><<<(unsigned)n, 32, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
         } else {
