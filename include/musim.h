@@ -105,6 +105,25 @@ int musim_run_host(musim_handle *h, int mode, int64_t n_cfg, const double *B, co
                    const double *T, const double *w, const int32_t *slot, int nt,
                    const double *times, double tau, int n_slots, double *out);
 
+/* Same as musim_run_host, but the configuration table is EXPANDED ON THE DEVICE from the axis
+ * tables instead of being passed as n_cfg-long arrays (the reference builds one namedtuple per
+ * configuration, MuSpinConfig.__getitem__ simconfig.py:497-519, and rotates B and p one at a time,
+ * ExperimentRunner.load_config experiment.py:384-432; at 10^7 configurations that host step costs
+ * more than the GPU evaluation).  Configuration i = 0 .. n_cfg-1 of this call is the global
+ * configuration c = first + i * step (step = number of ranks, experiment.py:369) and
+ *   idx_a = (c / div[a]) % len[a]      a = 0 polarisation, 1 field, 2 intrinsic field,
+ *                                          3 orientation, 4 temperature
+ *   B = R(q) B_lab + B_int,  p = R(q) p_lab,  T = Tv[idx_4],  w = ow[idx_3],
+ *   slot = sum_a idx_a * slot_mult[a]
+ * pol[len0,3] unit vectors, Blab[len1,3], Bint[len2,3], quat[len3,4] conjugate orientation
+ * quaternions (w,x,y,z) (simconfig.py:596-613), ow[len3] orientation weights already divided by
+ * avg_N, Tv[len4].  All pointers are HOST pointers. */
+int musim_run_axes_host(musim_handle *h, int mode, int64_t n_cfg, int64_t first, int64_t step,
+                        const int64_t *len, const int64_t *div, const int64_t *slot_mult,
+                        const double *pol, const double *Blab, const double *Bint, const double *quat,
+                        const double *ow, const double *Tv, int nt, const double *times, double tau,
+                        int n_slots, double *out);
+
 /* Batched complex-Hermitian eigensolver on its own (replaces np.linalg.eigh in
  * Hermitian.diag, spinop.py:69).  A[batch,d,d] complex row-major (only read), evals[batch,d]
  * ascending, evecs[batch,d,d] complex row-major with eigenvectors in COLUMNS (numpy

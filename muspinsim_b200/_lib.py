@@ -26,6 +26,7 @@ EXPORTS = [
     "musim_set_option",
     "musim_run",
     "musim_run_host",
+    "musim_run_axes_host",
     "musim_eigh",
     "musim_launch_count",
     "musim_phase_ms",
@@ -69,6 +70,8 @@ def load():
     lib.musim_run.restype = i32
     lib.musim_run_host.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32, vp, dbl, i32, vp]
     lib.musim_run_host.restype = i32
+    lib.musim_run_axes_host.argtypes = [vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, dbl, i32, vp]
+    lib.musim_run_axes_host.restype = i32
     lib.musim_eigh.argtypes = [i32, i32, i64, vp, vp, vp, i32, vp]
     lib.musim_eigh.restype = i32
     lib.musim_launch_count.argtypes = [vp]
@@ -184,6 +187,23 @@ class Handle:
         rc = self._lib.musim_run_host(
             self._h, int(mode), n, _ptr(B), _ptr(p), _ptr(T), _ptr(w), _ptr(slot), nt, _ptr(times),
             float(tau), out.shape[0], _ptr(out),
+        )
+        self._check(rc)
+        return out
+
+    def run_axes_host(self, mode, n_cfg, first, step, axes, times, tau, out):
+        """Configurations first, first + step, ... (n_cfg of them) of the table described by
+        `axes` (ConfigTable.axes_descriptor()), expanded on the device; `out` as in run_host."""
+        times = _f64(times) if times is not None else None
+        if not (out.flags.c_contiguous and out.dtype == np.float64 and out.ndim == 2):
+            raise ValueError("out must be a C-contiguous float64 [n_slots, nt] array")
+        nt = len(times) if times is not None else 1
+        keep = [np.ascontiguousarray(axes[k], dtype=np.int64) for k in ("len", "div", "slot_mult")]
+        tabs = [_f64(axes[k]) for k in ("pol", "Blab", "Bint", "quat", "ow", "Tv")]
+        rc = self._lib.musim_run_axes_host(
+            self._h, int(mode), int(n_cfg), int(first), int(step), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]),
+            _ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(tabs[4]), _ptr(tabs[5]),
+            nt, _ptr(times), float(tau), out.shape[0], _ptr(out),
         )
         self._check(rc)
         return out

@@ -135,6 +135,18 @@ def _vec3_rows(rows):
     return np.array(out)
 
 
+def expand_from_axes(ax, n_cfg, first=0, step=1):
+    """What expand_configs_kernel (csrc/musim.cu) computes, in numpy: configurations
+    c = first + i * step -> (B[n,3], p[n,3], T[n], w[n], slot[n])."""
+    c = first + step * np.arange(n_cfg, dtype=np.int64)
+    idx = [(c // ax["div"][a]) % ax["len"][a] for a in range(5)]
+    R = quat_rotation_matrices(ax["quat"])[idx[3]]
+    B = np.einsum("nij,nj->ni", R, ax["Blab"][idx[1]]) + ax["Bint"][idx[2]]
+    p = np.einsum("nij,nj->ni", R, ax["pol"][idx[0]])
+    slot = sum(idx[a] * ax["slot_mult"][a] for a in range(5))
+    return B, p, ax["Tv"][idx[4]], ax["ow"][idx[3]], np.asarray(slot, dtype=np.int32)
+
+
 class ConfigTable:
     """All configurations of one simulation as arrays.
 
@@ -194,7 +206,6 @@ class ConfigTable:
         return self
 
     def _build(self, vals, ow, xname, avg):
-        q = vals["orient"]
         t = vals["t"]
         # classify ranges in the reference's keyword order
         self.x_name = xname
@@ -227,40 +238,114 @@ class ConfigTable:
         for k, n in self.avg_ranges.items():
             axes.append((k, n, "a"))
         axes.append((xname, x_len, "x"))
-        loop_axes = [(k, n, kind) for (k, n, kind) in axes if k != "t"]
-        shape = [n for (_, n, _) in loop_axes]
-        n_cfg = int(np.prod(shape)) if shape else 1
-        grids = np.unravel_index(np.arange(n_cfg), shape) if shape else ()
-        idx = {k: np.zeros(n_cfg, dtype=np.int64) for k in _KEYS.values()}
-        for (k, _, _), g in zip(loop_axes, grids):
-            idx[k] = g
-        self.n_cfg = n_cfg
+        self._loop_axes = [(k, n, kind) for (k, n, kind) in axes if k != "t"]
+        shape = [n for (_, n, _) in self._loop_axes]
+        self.n_cfg = int(np.prod(shape)) if shape else 1
         self.avg_N = int(np.prod([n for (k, n, kind) in axes if kind == "a" and k != "t"])) if axes else 1
         # (if time is an averaged axis the reference counts it as ONE average configuration,
         #  because make_configs gives [slice(None)] for it, and averages the slice instead)
 
         # slot: index into the non-time dimensions of `results`, in results order
-        slot_dims = [(k, n) for (k, n, kind) in axes if kind in "fx" and k != "t"]
-        self._slot_shape = tuple(n for (_, n) in slot_dims) or (1,)
-        slot = np.zeros(n_cfg, dtype=np.int64)
-        for k, n in slot_dims:
-            slot = slot * n + idx[k]
-        self.slot = slot.astype(np.int32)
+        self._slot_dims = [(k, n) for (k, n, kind) in axes if kind in "fx" and k != "t"]
+        self._slot_shape = tuple(n for (_, n) in self._slot_dims) or (1,)
         self.n_slots = int(np.prod(self._slot_shape))
         # where the time axis sits in `results`
         names_f = list(self.file_ranges.keys())
         self._t_pos = names_f.index("t") if "t" in names_f else None
+        self._vals = vals
+        self._ow = np.asarray(ow, dtype=float)
+        self._arrays = None  # B, p, T, w, slot, fast: built on first use (see axes_descriptor)
 
+    # ---- per-configuration arrays (host expansion; the GPU path can expand on the device) ----
+    def _materialise(self):
+        if self._arrays is not None:
+            return self._arrays
+        vals, ow = self._vals, self._ow
+        shape = [n for (_, n, _) in self._loop_axes]
+        n_cfg = self.n_cfg
+        grids = np.unravel_index(np.arange(n_cfg), shape) if shape else ()
+        idx = {k: np.zeros(n_cfg, dtype=np.int64) for k in _KEYS.values()}
+        for (k, _, _), g in zip(self._loop_axes, grids):
+            idx[k] = g
+        slot = np.zeros(n_cfg, dtype=np.int64)
+        for k, n in self._slot_dims:
+            slot = slot * n + idx[k]
         # rotate lab-frame field and polarisation by the stored (conjugate) quaternion
-        R = quat_rotation_matrices(q)[idx["orient"]]
-        self.B = np.einsum("nij,nj->ni", R, vals["B"][idx["B"]]) + vals["intrinsic_B"][idx["intrinsic_B"]]
-        self.p = np.einsum("nij,nj->ni", R, vals["mupol"][idx["mupol"]])
-        self.T = vals["T"][idx["T"]].astype(float)
-        self.w = ow[idx["orient"]] / self.avg_N
-        Bn = np.linalg.norm(self.B, axis=1)
+        R = quat_rotation_matrices(vals["orient"])[idx["orient"]]
+        B = np.einsum("nij,nj->ni", R, vals["B"][idx["B"]]) + vals["intrinsic_B"][idx["intrinsic_B"]]
+        p = np.einsum("nij,nj->ni", R, vals["mupol"][idx["mupol"]])
+        T = vals["T"][idx["T"]].astype(float)
+        w = ow[idx["orient"]] / self.avg_N
+        Bn = np.linalg.norm(B, axis=1)
         with np.errstate(divide="ignore", invalid="ignore"):
-            check = (cnst.e * (cnst.hbar**2) * Bn) / (2 * cnst.m_p * cnst.k * self.T)
-        self.fast = check == 0  # experiment.py:413-418
+            check = (cnst.e * (cnst.hbar**2) * Bn) / (2 * cnst.m_p * cnst.k * T)
+        self._arrays = {"B": B, "p": p, "T": T, "w": w, "slot": slot.astype(np.int32), "fast": check == 0}
+        return self._arrays
+
+    B = property(lambda self: self._materialise()["B"])
+    p = property(lambda self: self._materialise()["p"])
+    T = property(lambda self: self._materialise()["T"])
+    w = property(lambda self: self._materialise()["w"])
+    slot = property(lambda self: self._materialise()["slot"])
+    fast = property(lambda self: self._materialise()["fast"])  # experiment.py:413-418
+
+    def uniform_fast(self):
+        """True / False if EVERY configuration takes / does not take the reference's T = inf | B = 0
+        fast path (experiment.py:413-418), None if they differ or it cannot be told from the axis
+        tables alone (then the per-configuration arrays are needed)."""
+        T = self._vals["T"]
+        if np.all(np.isinf(T) & (T > 0)):
+            return True
+        if np.any(self._vals["intrinsic_B"] != 0.0):
+            return None  # |R B_lab + B_int| depends on the orientation
+        Bn = np.linalg.norm(self._vals["B"], axis=1)  # |R B_lab| = |B_lab|
+        with np.errstate(divide="ignore", invalid="ignore"):
+            check = (cnst.e * (cnst.hbar**2) * Bn[:, None]) / (2 * cnst.m_p * cnst.k * T[None, :])
+        f = check == 0
+        # |R B| is |B| only up to rounding: a field whose rotated norm could round to exactly 0 is 0
+        if f.all():
+            return True
+        if not f.any():
+            return False
+        return None
+
+    def axes_descriptor(self):
+        """Axis tables for the device-side expansion (musim_run_axes_host): global configuration
+        c -> idx_a = (c // div[a]) % len[a] for a = (mupol, B, intrinsic_B, orient, T), enumerated
+        with the file axes slowest, then the x axis, then the averaged axes (so that the output
+        row index is non-decreasing in c), and slot = sum_a idx_a * slot_mult[a]."""
+        names = ["mupol", "B", "intrinsic_B", "orient", "T"]
+        order = [(k, n) for (k, n, kind) in self._loop_axes if kind == "f"]
+        order += [(k, n) for (k, n, kind) in self._loop_axes if kind == "x"]
+        order += [(k, n) for (k, n, kind) in self._loop_axes if kind == "a"]
+        ln = {k: 1 for k in names}
+        div = {k: 1 for k in names}
+        acc = 1
+        for k, n in reversed(order):
+            ln[k] = n
+            div[k] = acc
+            acc *= n
+        smul = {k: 0 for k in names}
+        acc = 1
+        for k, n in reversed(self._slot_dims):
+            smul[k] = acc
+            acc *= n
+        v = self._vals
+        return {
+            "len": np.array([ln[k] for k in names], dtype=np.int64),
+            "div": np.array([div[k] for k in names], dtype=np.int64),
+            "slot_mult": np.array([smul[k] for k in names], dtype=np.int64),
+            "pol": np.ascontiguousarray(v["mupol"], dtype=float),
+            "Blab": np.ascontiguousarray(v["B"], dtype=float),
+            "Bint": np.ascontiguousarray(v["intrinsic_B"], dtype=float),
+            "quat": np.ascontiguousarray(v["orient"], dtype=float),
+            "ow": np.ascontiguousarray(self._ow / self.avg_N, dtype=float),
+            "Tv": np.ascontiguousarray(v["T"], dtype=float),
+        }
+
+    def expand_axes(self, first=0, step=1):
+        """numpy restatement of the device expansion kernel (tests; same enumeration order)."""
+        return expand_from_axes(self.axes_descriptor(), len(range(first, self.n_cfg, step)), first, step)
 
     def finish(self, out):
         """[n_slots, nt] accumulation buffer -> the reference's results array layout."""

@@ -714,6 +714,126 @@ extern "C" int musim_run_host(musim_handle *h, int mode, int64_t n_cfg, const do
 }
 
 // ---------------------------------------------------------------------------------------
+// Configuration expansion on the device.
+//
+// The reference materialises one namedtuple per configuration (MuSpinConfig.__getitem__,
+// simconfig.py:497-519) and rotates field and polarisation one at a time (load_config,
+// experiment.py:384-432); the numpy restatement in configs.py still needs ~3 s for the 10^7
+// configurations of an ALC scan -- four times the GPU time of the whole scan.  Here configuration c
+// is decoded from the axis tables inside a kernel:
+//   idx_a = (c / div_a) % len_a,   axes a = 0 polarisation, 1 field, 2 intrinsic field,
+//                                           3 orientation, 4 temperature
+//   B = R(q) B_lab + B_int,  p = R(q) p_lab   (q = conjugate orientation quaternion, simconfig.py:608-613),
+//   w = w_orient / avg_N,  slot = sum_a idx_a * slot_mult_a
+// ---------------------------------------------------------------------------------------
+struct AxisDesc {
+  long long len[5], div[5], smul[5];
+};
+
+__global__ void expand_configs_kernel(int64_t n, int64_t first, int64_t step, AxisDesc ax,
+                                      const double *__restrict__ pol, const double *__restrict__ Blab,
+                                      const double *__restrict__ Bint, const double *__restrict__ quat,
+                                      const double *__restrict__ ow, const double *__restrict__ Tv,
+                                      double *__restrict__ B, double *__restrict__ p, double *__restrict__ T,
+                                      double *__restrict__ w, int32_t *__restrict__ slot) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long c = first + i * step;
+  long long idx[5];
+  long long sl = 0;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    idx[a] = (c / ax.div[a]) % ax.len[a];
+    sl += idx[a] * ax.smul[a];
+  }
+  const double *q = quat + 4 * idx[3];
+  const double qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+  // rotation matrix of the quaternion (ase.quaternions.Quaternion.rotate; configs.quat_rotation_matrices)
+  const double r00 = qw * qw + qx * qx - qy * qy - qz * qz, r01 = 2 * (qx * qy - qw * qz), r02 = 2 * (qx * qz + qw * qy);
+  const double r10 = 2 * (qx * qy + qw * qz), r11 = qw * qw - qx * qx + qy * qy - qz * qz, r12 = 2 * (qy * qz - qw * qx);
+  const double r20 = 2 * (qx * qz - qw * qy), r21 = 2 * (qy * qz + qw * qx), r22 = qw * qw - qx * qx - qy * qy + qz * qz;
+  const double *bl = Blab + 3 * idx[1], *bi = Bint + 3 * idx[2], *pl = pol + 3 * idx[0];
+  B[3 * i + 0] = r00 * bl[0] + r01 * bl[1] + r02 * bl[2] + bi[0];
+  B[3 * i + 1] = r10 * bl[0] + r11 * bl[1] + r12 * bl[2] + bi[1];
+  B[3 * i + 2] = r20 * bl[0] + r21 * bl[1] + r22 * bl[2] + bi[2];
+  p[3 * i + 0] = r00 * pl[0] + r01 * pl[1] + r02 * pl[2];
+  p[3 * i + 1] = r10 * pl[0] + r11 * pl[1] + r12 * pl[2];
+  p[3 * i + 2] = r20 * pl[0] + r21 * pl[1] + r22 * pl[2];
+  T[i] = Tv[idx[4]];
+  w[i] = ow[idx[3]];
+  slot[i] = (int32_t)sl;
+}
+
+extern "C" int musim_run_axes_host(musim_handle *h, int mode, int64_t n_cfg, int64_t first, int64_t step,
+                                   const int64_t *len, const int64_t *div, const int64_t *slot_mult,
+                                   const double *pol, const double *Blab, const double *Bint, const double *quat,
+                                   const double *ow, const double *Tv, int nt, const double *times, double tau,
+                                   int n_slots, double *out) {
+  if (!h) return MUSIM_EINVAL;
+  if (n_cfg < 0 || n_slots < 1 || !out || step < 1 || first < 0) return set_err(h, MUSIM_EINVAL, "invalid sizes");
+  if (n_cfg == 0) return MUSIM_OK;
+  if (!len || !div || !slot_mult || !pol || !Blab || !Bint || !quat || !ow || !Tv)
+    return set_err(h, MUSIM_EINVAL, "null axis tables");
+  AxisDesc ax;
+  for (int a = 0; a < 5; ++a) {
+    if (len[a] < 1 || div[a] < 1) return set_err(h, MUSIM_EINVAL, "invalid axis descriptor");
+    ax.len[a] = len[a];
+    ax.div[a] = div[a];
+    ax.smul[a] = slot_mult[a];
+  }
+  CK(cudaSetDevice(h->device));
+  const bool integral = (mode == MUSIM_MODE_INTEGRAL || mode == MUSIM_MODE_LINDBLAD_INT ||
+                         mode == MUSIM_MODE_INTEGRAL_FAST);
+  const int ntx = integral ? 1 : nt;
+  if (ntx < 1) return set_err(h, MUSIM_EINVAL, "times must be an array of values in microseconds");
+  const size_t n = (size_t)n_cfg;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t bB = al(n * 3 * sizeof(double)), bT = al(n * sizeof(double)), bS = al(n * sizeof(int32_t));
+  const size_t bO = al((size_t)n_slots * ntx * sizeof(double));
+  const size_t tP = al((size_t)len[0] * 3 * 8), tB = al((size_t)len[1] * 3 * 8), tI = al((size_t)len[2] * 3 * 8),
+               tQ = al((size_t)len[3] * 4 * 8), tW = al((size_t)len[3] * 8), tT = al((size_t)len[4] * 8);
+  const size_t total = 2 * bB + 2 * bT + bS + bO + tP + tB + tI + tQ + tW + tT;
+  if (total > h->stage_bytes) {
+    cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    CK(cudaMalloc(&h->stage, total));
+    h->stage_bytes = total;
+  }
+  char *base = (char *)h->stage;
+  double *dB = (double *)base;
+  double *dp = (double *)(base + bB);
+  double *dT = (double *)(base + 2 * bB);
+  double *dw = (double *)(base + 2 * bB + bT);
+  int32_t *ds = (int32_t *)(base + 2 * bB + 2 * bT);
+  double *dout = (double *)(base + 2 * bB + 2 * bT + bS);
+  char *tb = base + 2 * bB + 2 * bT + bS + bO;
+  double *dpol = (double *)tb, *dBl = (double *)(tb + tP), *dBi = (double *)(tb + tP + tB),
+         *dq = (double *)(tb + tP + tB + tI), *dow = (double *)(tb + tP + tB + tI + tQ),
+         *dTv = (double *)(tb + tP + tB + tI + tQ + tW);
+  cudaStream_t st = 0;
+  CK(cudaMemcpyAsync(dpol, pol, (size_t)len[0] * 24, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dBl, Blab, (size_t)len[1] * 24, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dBi, Bint, (size_t)len[2] * 24, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dq, quat, (size_t)len[3] * 32, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dow, ow, (size_t)len[3] * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dTv, Tv, (size_t)len[4] * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dout, out, (size_t)n_slots * ntx * sizeof(double), cudaMemcpyHostToDevice, st));
+  expand_configs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_cfg, first, step, ax, dpol, dBl, dBi, dq, dow,
+                                                                     dTv, dB, dp, dT, dw, ds);
+  ++h->launches;
+  CK(cudaGetLastError());
+  int rc = musim_run(h, mode, n_cfg, dB, dp, dT, dw, ds, nt, times, tau, n_slots, dout, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, dout, (size_t)n_slots * ntx * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int hstat[4];
+  CK(cudaMemcpy(hstat, h->status, sizeof hstat, cudaMemcpyDeviceToHost));
+  if (hstat[0] != 0) return set_err(h, MUSIM_ENOTCONV, "eigensolver did not converge");
+  return MUSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // FP64 peak micro-benchmarks
 // ---------------------------------------------------------------------------------------
 extern "C" int musim_fp64_peak(int device, int kind, double *tflops) {

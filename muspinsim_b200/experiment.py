@@ -44,6 +44,7 @@ class ExperimentRunner:
         self._handle = None
         self.results = None
         self.options = {}
+        self.device_expand = True  # expand the configuration table on the device when all configurations share a mode
 
     @property
     def system(self):
@@ -104,6 +105,18 @@ class ExperimentRunner:
             out.append((_lib.MODE_INTEGRAL, sel[~fast]))
         return out
 
+    def _uniform_mode(self):
+        """The one mode all configurations take, or None if they differ (experiment.py:449-496)."""
+        tab = self._table
+        if len(self._dissip) > 0:
+            return _lib.MODE_LINDBLAD if tab.y == "asymmetry" else _lib.MODE_LINDBLAD_INT
+        fast = tab.uniform_fast()
+        if fast is None:
+            return None
+        if tab.y == "asymmetry":
+            return _lib.MODE_FAST if fast else _lib.MODE_EVOLVE
+        return _lib.MODE_INTEGRAL_FAST if fast else _lib.MODE_INTEGRAL
+
     def run_partial(self, rank=0, size=1):
         """Accumulate this rank's share of the configurations (the reference's
         `self._config[mpi.rank :: mpi.size]`, experiment.py:369) and return the local
@@ -113,6 +126,16 @@ class ExperimentRunner:
             raise ValueError("times must be an array of values in microseconds")
         nt = 1 if tab.y == "integral" else len(tab.times)
         out = np.zeros((tab.n_slots, nt))
+        if self.device_expand and hasattr(self.handle, "run_axes_host"):
+            # every configuration takes the same reference function: expand the configuration
+            # table on the device from the axis tables (no n_cfg-long host arrays at all)
+            mode = self._uniform_mode()
+            if mode is not None:
+                n_loc = len(range(rank, tab.n_cfg, size))
+                if n_loc:
+                    self.handle.run_axes_host(mode, n_loc, rank, size, tab.axes_descriptor(),
+                                              None if tab.y == "integral" else tab.times, MU_TAU, out)
+                return out
         sel = np.arange(tab.n_cfg)[rank::size]
         if len(sel) == 0:
             return out

@@ -16,6 +16,12 @@ class OracleHandle:
     def set_option(self, k, v):
         pass
 
+    def run_axes_host(self, mode, n_cfg, first, step, axes, times, tau, out):
+        from muspinsim_b200.configs import expand_from_axes
+
+        B, p, T, w, slot = expand_from_axes(axes, n_cfg, first, step)
+        return self.run_host(mode, B, p, T, w, slot, times, tau, out)
+
     def run_host(self, mode, B, p, T, w, slot, times, tau, out):
         s = self.sys
         self.calls.append((mode, len(B)))

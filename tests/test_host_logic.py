@@ -152,3 +152,37 @@ def test_adapter_from_reference_runner(name):
     ours = system_from_spec(spec)[0]
     assert np.allclose(r.system.hamiltonian, ours.hamiltonian, atol=1e-12)
     assert np.allclose(r.system.zeeman_operators(), ours.zeeman_operators(), atol=1e-9, rtol=1e-15)
+
+
+def test_axes_descriptor_matches_materialised_table():
+    """Device-side expansion (musim_run_axes_host): the axis descriptor enumerates exactly the
+    configurations of the materialised table (as a multiset of (B, p, T, w, slot) rows), with
+    non-decreasing output rows, and the strided shards of two ranks partition it."""
+    from muspinsim_b200.configs import ConfigTable
+
+    rng = np.random.default_rng(0)
+    spec = {
+        "spins": ["mu", "e"],
+        "polarization": [[1, 0, 0], [0, 1, 1]],
+        "field": [[0.0, 0.0, b] for b in (0.0, 0.1, 0.25)],
+        "intrinsic_field": [[0.0, 0.0, 0.0], [0.01, 0.0, 0.0]],
+        "orientation": np.column_stack([rng.uniform(0, 6, 5), rng.uniform(0, 3, 5), rng.uniform(0, 6, 5), rng.uniform(0.5, 2, 5)]),
+        "temperature": [np.inf, 1.0],
+        "time": np.linspace(0, 1, 7),
+        "x_axis": "field",
+        "average_axes": ["orientation", "intrinsic_field"],
+    }
+    tab = ConfigTable(spec)
+    B, p, T, w, slot = tab.expand_axes()
+    assert len(B) == tab.n_cfg and np.all(np.diff(slot) >= 0)
+    key = lambda B, p, T, w, s: sorted(map(tuple, np.round(np.column_stack([B, p, np.where(np.isinf(T), -1, T), w, s]), 12)))
+    assert key(B, p, T, w, slot) == key(tab.B, tab.p, tab.T, tab.w, tab.slot)
+    parts = [tab.expand_axes(r, 2) for r in range(2)]
+    assert sum(len(x[0]) for x in parts) == tab.n_cfg
+    assert key(*[np.concatenate([a[i] for a in parts]) for i in range(5)]) == key(B, p, T, w, slot)
+    assert tab.uniform_fast() is None  # mixed temperatures / fields
+    assert ConfigTable(dict(spec, temperature=[np.inf])).uniform_fast() is True
+    assert ConfigTable(dict(spec, temperature=[2.0], field=[[0, 0, 0.1], [0, 0, 0.2]],
+                            intrinsic_field=[[0, 0, 0]], average_axes=["orientation"])).uniform_fast() is False
+    assert ConfigTable(dict(spec, temperature=[2.0], field=[[0, 0, 0.0], [0, 0, 0.2]],
+                            intrinsic_field=[[0, 0, 0]], average_axes=["orientation"])).uniform_fast() is None
