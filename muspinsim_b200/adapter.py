@@ -63,12 +63,18 @@ def table_from_reference(cfg):
     return ConfigTable.from_values(vals, ow, x_name, avg, cfg._y_axis)
 
 
+# device handles shared by all runners built from reference objects: FittingRunner creates a new
+# reference ExperimentRunner per function evaluation (fitting.py:126-135); with the cache only
+# H0 / Z are re-uploaded and the workspaces stay resident
+_HANDLES = {}
+
+
 def runner_from_reference(ref_runner, device=None, comm=None):
     if getattr(ref_runner.config, "celio_k", 0):
         raise NotImplementedError("Celio's method stays on the reference path")
     dissip = {int(i): float(a) for i, a in ref_runner.config.dissipation_terms.items()}
     return ExperimentRunner(system=system_from_reference(ref_runner), table=table_from_reference(ref_runner.config),
-                            dissipation=dissip, device=device, comm=comm)
+                            dissipation=dissip, device=device, comm=comm, handle_cache=_HANDLES)
 
 
 def run_reference_runner(ref_runner, device=None, comm=None):

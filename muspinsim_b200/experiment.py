@@ -19,13 +19,20 @@ from .spinsys import MuonSpinSystem, system_from_spec
 
 
 class ExperimentRunner:
-    def __init__(self, spec=None, system=None, table=None, dissipation=None, device=None, comm=None):
+    def __init__(self, spec=None, system=None, table=None, dissipation=None, device=None, comm=None,
+                 handle_cache=None):
         """
         spec        dict of `.in` keywords (spins, couplings, field, ..., see configs.default_spec)
         system      alternatively a prebuilt MuonSpinSystem (+ `table`, `dissipation`)
         device      CUDA device index (default: LOCAL_RANK or 0)
         comm        a `dist.Communicator` (shards configurations over ranks, one reduce at the
                     end -- the role of mpi.py in the reference); None = single process
+        handle_cache  dict shared between runners: a runner whose spin system has the same spins
+                    (dimensions, gyromagnetic ratios, muon, dissipation) as an earlier one reuses
+                    that runner's device handle -- workspaces stay allocated, only H0 / Z are
+                    re-uploaded (musim_update_system).  This is the resident-system fitting loop:
+                    FittingRunner builds a new ExperimentRunner per function evaluation
+                    (fitting.py:126-135)
         """
         if spec is not None:
             system, dissipation = system_from_spec({**{"spins": ["mu", "e"], "couplings": []}, **spec})
@@ -42,6 +49,7 @@ class ExperimentRunner:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self._device = device
         self._handle = None
+        self._handle_cache = handle_cache
         self.results = None
         self.options = {}
         self.device_expand = True  # expand the configuration table on the device when all configurations share a mode
@@ -56,6 +64,16 @@ class ExperimentRunner:
 
     @property
     def handle(self):
+        if self._handle is None and self._handle_cache is not None:
+            key = (self._device, tuple(int(x) for x in self._system.dimension),
+                   tuple(float(g) for g in self._system.gammas), int(self._system.muon_index),
+                   tuple(sorted((int(k), float(v)) for k, v in self._dissip.items())))
+            h = self._handle_cache.get(key)
+            if h is not None:
+                self._handle = h
+                for k, v in self.options.items():
+                    h.set_option(k, v)
+                return h
         if self._handle is None:
             ds = list(self._dissip.keys())
             dr = [self._dissip[k] for k in ds]
@@ -72,6 +90,10 @@ class ExperimentRunner:
             )
             for k, v in self.options.items():
                 self._handle.set_option(k, v)
+            if self._handle_cache is not None:
+                if len(self._handle_cache) >= 4:  # a fit varies couplings, not the spin list
+                    self._handle_cache.pop(next(iter(self._handle_cache)))
+                self._handle_cache[key] = self._handle
         return self._handle
 
     def set_option(self, key, value):
@@ -126,6 +148,9 @@ class ExperimentRunner:
             raise ValueError("times must be an array of values in microseconds")
         nt = 1 if tab.y == "integral" else len(tab.times)
         out = np.zeros((tab.n_slots, nt))
+        if self._handle_cache is not None and hasattr(self.handle, "update_system"):
+            # a shared (cached) handle may hold another runner's couplings: re-upload H0 / Z
+            self.handle.update_system(self._system.hamiltonian, self._system.zeeman_operators())
         if self.device_expand and hasattr(self.handle, "run_axes_host"):
             # every configuration takes the same reference function: expand the configuration
             # table on the device from the axis tables (no n_cfg-long host arrays at all)

@@ -97,3 +97,27 @@ def test_lindbladian_closed_forms():
         Lindbladian.from_hamiltonian(sz)
     with pytest.raises(ValueError):
         L.evolve(np.eye(3), t, sx)
+
+
+def test_resident_handle_across_runners_with_different_couplings():
+    """Fitting loop (fitting.py:126-135 builds a new runner per function evaluation): runners
+    sharing a handle cache reuse ONE device handle, re-uploading only H0 / Z; results equal
+    those of fresh handles, also when the runners are used alternately."""
+    import numpy as np
+
+    from muspinsim_b200 import ExperimentRunner, workloads
+
+    cache = {}
+    specs = []
+    for scale in (1.0, 1.3, 0.6):
+        spec = workloads.c2_hfine_powder(n_orient=9, nt=100, n_h=1)
+        for c in spec["couplings"]:
+            c["value"] = np.asarray(c["value"]) * scale
+        specs.append(spec)
+    runners = [ExperimentRunner(s, device=0, handle_cache=cache) for s in specs]
+    got = [r.run() for r in runners]
+    assert len(cache) == 1 and all(r.handle is runners[0].handle for r in runners)
+    for s, g in zip(specs, got):
+        assert np.max(np.abs(ExperimentRunner(s, device=0).run() - g)) < 1e-13
+    assert np.max(np.abs(runners[0].run() - got[0])) < 1e-13  # first runner again after the others
+    assert np.max(np.abs(got[0] - got[1])) > 1e-3
