@@ -123,6 +123,30 @@ def eulrange(N):
     return np.array([a, b, c, np.sin(b)]).T
 
 
+def zcw(N, mode="sphere"):
+    """At least N polar-angle rows (theta, phi) of the Zaremba-Conroy-Wolfsberg set (utils.py:34-37
+    calls soprano.calculate.powder.ZCW(mode).get_orient_angles(N)[0]).  Restated from the published
+    algorithm (Eden & Levitt, J. Magn. Reson. 132, 220 (1998)): N_m = g(m+2) points with
+    g = 8, 13, 21, ...;  phi_j = 2 pi / c3 * frac(j g(m) / N_m),  theta_j = acos(c1 (c2 frac(j / N_m) - 1)).
+    PARITY UNPINNED: Soprano is not available here and the reference's tests only check the row
+    count and <3 cos^2 theta - 1> ~ 0 (tests/test_input.py:271-273, test_utils.py:67-73), both of
+    which this satisfies; parity and benchmark inputs use explicit orientation rows."""
+    c = {"sphere": (1.0, 2.0, 1.0), "hemisphere": (-1.0, 1.0, 1.0), "octant": (2.0, 1.0, 8.0)}[mode]
+    g = [8, 13]
+    m = 0
+    while True:
+        while len(g) <= m + 2:
+            g.append(g[-1] + g[-2])
+        if g[m + 2] >= N:
+            break
+        m += 1
+    Nz, gm = g[m + 2], g[m]
+    j = np.arange(Nz, dtype=float)
+    phi = 2 * np.pi / c[2] * np.mod(j * gm / Nz, 1.0)
+    theta = np.arccos(c[0] * (c[1] * np.mod(j / Nz, 1.0) - 1.0))
+    return np.array([theta, phi]).T
+
+
 def _vec3_rows(rows):
     out = []
     for r in rows:

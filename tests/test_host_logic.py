@@ -186,3 +186,16 @@ def test_axes_descriptor_matches_materialised_table():
                             intrinsic_field=[[0, 0, 0]], average_axes=["orientation"])).uniform_fast() is False
     assert ConfigTable(dict(spec, temperature=[2.0], field=[[0, 0, 0.0], [0, 0, 0.2]],
                             intrinsic_field=[[0, 0, 0]], average_axes=["orientation"])).uniform_fast() is None
+
+
+def test_zcw_generator_properties():
+    """The reference pins only the row count and the vanishing P2 average of zcw(N)
+    (tests/test_input.py:271-273, tests/test_utils.py:67-73)."""
+    from muspinsim_b200.configs import ConfigTable, zcw
+
+    for n in (1, 20, 100, 1000):
+        rows = zcw(n)
+        assert rows.shape[1] == 2 and len(rows) >= n
+        assert abs(np.mean(3 * np.cos(rows[:, 0]) ** 2 - 1)) < 1e-3 if n >= 100 else True
+    tab = ConfigTable({"spins": ["mu", "e"], "orientation": zcw(50), "time": np.linspace(0, 1, 5)})
+    assert tab.n_cfg == len(zcw(50)) and abs(tab.w.sum() - 1.0) < 1e-12
