@@ -17,6 +17,7 @@ enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
 static bool g_tridiag_warp = true; // option "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
 static bool g_small24 = true;      // option "small24": D = 16 / 24 instantiations of the replay / reflector kernels for d <= 16 / 24 (else D = 32)
+static bool g_tridiag_fused = true; // option "tridiag_fused": warp kernel with the update of step k fused into the product of step k+1
 static bool g_tridiag_wreg = false; // option "tridiag_wreg": ... with the matrix rows in registers (measured slower: 34 vs 23 ms per 10^6 d = 24 matrices; dead columns and jump-table picks cost more than the shared-memory traffic saved)
 static bool g_tridiag_phases = true;  // option "tridiag_phases": K1 in up to three launches of decreasing size
 static bool g_apply_warp = true;   // option "apply_warp": rotation replay with one warp per CTA (d > 32)
@@ -167,6 +168,11 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
       else
         hql_tridiag_wreg_kernel<32><<<gb, 32, 0, st>>>(d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf],
                                                                  ws.vcap, ws.tauv[buf]);
+    } else if (use_reflect(d) && g_tridiag_warp && g_tridiag_fused && d <= 32) {
+      const size_t sm = hql_tridiag_warpf_smem(d);
+      cudaFuncSetAttribute(hql_tridiag_warpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      hql_tridiag_warpf_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
+          d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
     } else if (use_reflect(d) && g_tridiag_warp && d <= 32) {
       const size_t sm = hql_tridiag_warp_smem(d);
       cudaFuncSetAttribute(hql_tridiag_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

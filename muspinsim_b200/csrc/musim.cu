@@ -159,6 +159,8 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     g_tql_threads = (value == 8 || value == 16) ? (int)value : 32;
   else if (!strcmp(key, "tridiag_warp"))  // 0: CTA-per-matrix kernels also for d <= 32
     g_tridiag_warp = value != 0;
+  else if (!strcmp(key, "tridiag_fused"))
+    g_tridiag_fused = value != 0;
   else if (!strcmp(key, "small24"))
     g_small24 = value != 0;
   else if (!strcmp(key, "tridiag_wreg"))  // 0: warp-per-matrix kernel with A in shared memory instead of registers
