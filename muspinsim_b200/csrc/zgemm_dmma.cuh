@@ -77,7 +77,38 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
     // thread t owns e = t, t + NT, ... (4 of each)
     constexpr int EPT = (ZG_KS * DP + NT - 1) / NT;
     cplx ra[EPT], rb[EPT];
+    // PAIRED (C = U^H (O U) with A and B the same matrix U): the K rows of a slab are taken as 8
+    // rows with muon index 0 plus their 8 partner rows (muon index 1), so that both U rows a
+    // B-operand element needs are A-operand elements of the SAME thread (elements q and q ^ 2):
+    // one global load per element instead of three.
+    const bool paired = B_MUON && CONJ_A && EPT == 4 && 2 * NT == 8 * DP && (const void *)Ab == (const void *)Bb &&
+                        (mu.stride % 8) == 0 && (d % (2 * mu.stride)) == 0;
+    auto fetch_paired = [&](int k0) {
+      const int r0 = k0 >> 1;  // first of the 8 muon-index-0 rows of this slab, counted among those rows only
+      const int blk = r0 / mu.stride, within = r0 - blk * mu.stride;
+      const int row0 = blk * 2 * mu.stride + within;
+#pragma unroll
+      for (int q = 0; q < EPT; ++q) {
+        const int e = tid + q * NT;
+        const int k = e / DP, m = e - k * DP;
+        const int row = row0 + (k & 7) + ((k >> 3) ? mu.stride : 0);
+        ra[q] = (m < d) ? Ab[(size_t)row * d + m] : make_c(0.0, 0.0);
+      }
+#pragma unroll
+      for (int q = 0; q < EPT; ++q) {
+        const int mi = q >> 1;  // elements 0, 1: muon index 0; elements 2, 3: their partners
+        const cplx u0 = ra[q], u1 = ra[q ^ 2];
+        const double dg = mi ? -pz : pz;
+        const double oy = mi ? py : -py;
+        rb[q].x = dg * u0.x + px * u1.x - oy * u1.y;
+        rb[q].y = dg * u0.y + px * u1.y + oy * u1.x;
+      }
+    };
     auto fetch = [&](int k0) {
+      if (paired) {
+        fetch_paired(k0);
+        return;
+      }
 #pragma unroll
       for (int q = 0; q < EPT; ++q) {
         const int e = tid + q * NT;
