@@ -854,9 +854,9 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
     // (k+1, d) run without per-row predicates.  vv[] holds v (1 at row k+1, 0 outside the
     // reflector) for the update pass.
     cplx vv[KEEPV ? RPT : 1];
-    cplx u[CPT];
+    cplx u[CPT], ub[CPT];  // two partial dot products per column (even / odd rows): half the dependent chain
 #pragma unroll
-    for (int cc = 0; cc < CPT; ++cc) u[cc] = make_c(0.0, 0.0);
+    for (int cc = 0; cc < CPT; ++cc) u[cc] = ub[cc] = make_c(0.0, 0.0);
 #pragma unroll
     for (int b = 0; b < RPT / 4; ++b) {
       if (BR * b + BR - 1 >= k + 1 && BR * b < d) {
@@ -867,7 +867,12 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
             const cplx v = vb[TPC * J];
             if (KEEPV) vv[J] = v;
 #pragma unroll
-            for (int cc = 0; cc < CPT; ++cc) ccfma(u[cc], v, x[cc][J]);
+            for (int cc = 0; cc < CPT; ++cc) {
+              if (q & 1)
+                ccfma(ub[cc], v, x[cc][J]);
+              else
+                ccfma(u[cc], v, x[cc][J]);
+            }
           }
         } else {
 #pragma unroll
@@ -881,7 +886,12 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
               v = make_c(1.0, 0.0);
             if (KEEPV) vv[J] = v;
 #pragma unroll
-            for (int cc = 0; cc < CPT; ++cc) ccfma(u[cc], v, x[cc][J]);
+            for (int cc = 0; cc < CPT; ++cc) {
+              if (q & 1)
+                ccfma(ub[cc], v, x[cc][J]);
+              else
+                ccfma(u[cc], v, x[cc][J]);
+            }
           }
         }
       }
@@ -889,6 +899,7 @@ hql_reflect_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict_
     cplx tu[CPT];
 #pragma unroll
     for (int cc = 0; cc < CPT; ++cc) {
+      u[cc] = cadd(u[cc], ub[cc]);
 #pragma unroll
       for (int o = 1; o < TPC; o <<= 1) {
         u[cc].x += __shfl_xor_sync(0xffffffffu, u[cc].x, o);
