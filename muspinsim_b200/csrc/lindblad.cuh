@@ -267,6 +267,10 @@ __global__ void lind_scale_kernel(size_t total, double s, const cplx *__restrict
 
 // Uniform-grid time series, one CTA (256 threads) per configuration.
 //   v_a = EB^a v0 (v0 = E0 r0 or r0), o_b^T = o^T E1^b, P[a,b] = Re(o_b . v_a)
+__device__ __forceinline__ cplx shfl_xor_c4(cplx v, int m) {
+  return make_c(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
 template <bool GMEM>
 __global__ void __launch_bounds__(256)
 lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ EB,
@@ -281,17 +285,19 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
   const size_t nn = (size_t)n * n;
   if (!GMEM) AB = 32;  // compile-time constant on the shared-memory path
   cplx *sm0 = reinterpret_cast<cplx *>(smem_raw);
-  const cplx *s1 = GMEM ? E1 + cfg * nn : sm0;                     // E1 [n][n]
-  const int ldB = GMEM ? n : n + 1;
-  const cplx *sB = GMEM ? EB + cfg * nn : sm0 + nn;                // EB [n][ldB] (padded in smem: read by rows)
-  cplx *sO = GMEM ? sm0 : sm0 + nn + (size_t)n * (n + 1);          // OB [AB][n]
-  cplx *sV = sO + (size_t)AB * n;                                  // VA [AB][n]  (column a stored as a row)
+  const int ldB = GMEM ? n : n + 1;                                // both matrices padded in shared memory
+  const size_t npad = (size_t)n * (n + 1);
+  const cplx *s1 = GMEM ? E1 + cfg * nn : sm0;                     // E1 [n][ldB]
+  const cplx *sB = GMEM ? EB + cfg * nn : sm0 + npad;              // EB [n][ldB]
+  const int ldO = n + 1;  // padded: in the P[a,b] loop the lanes of a warp read DIFFERENT rows of OB at the same j
+  cplx *sO = GMEM ? sm0 : sm0 + 2 * npad;                          // OB [AB][ldO]
+  cplx *sV = sO + (size_t)AB * ldO;                                // VA [AB][n]  (column a stored as a row)
   cplx *sv = sV + (size_t)AB * n;                                  // [n] scratch
   if (!GMEM) {
     for (int idx = tid; idx < nn; idx += 256) {
-      sm0[idx] = E1[cfg * nn + idx];
       const int r = idx / n, c = idx - r * n;
-      sm0[nn + r * (n + 1) + c] = EB[cfg * nn + idx];
+      sm0[r * (n + 1) + c] = E1[cfg * nn + idx];
+      sm0[npad + r * (n + 1) + c] = EB[cfg * nn + idx];
     }
   }
   for (int i = tid; i < n; i += 256) {
@@ -309,13 +315,20 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
     for (int i = tid; i < n; i += 256) sV[i] = sv[i];
   }
   __syncthreads();
-  // o_b = o_{b-1} E1 :  thread per column j (coalesced / conflict-free over j)
+  // o_b = o_{b-1} E1.  FOUR threads per output element (inner index q, q + 4, ...; combined with
+  // two shuffles): with one thread per element only n of the 256 threads work and each runs a
+  // chain of 4 n dependent FMAs (ncu: this kernel was 36 % of the C4 step).
+  const int tq = tid & 3, tj = tid >> 2;
   for (int b = 1; b < NB; ++b) {
-    for (int j = tid; j < n; j += 256) {
+    const cplx *o = sO + (size_t)(b - 1) * ldO;
+    for (int j0 = 0; j0 < n; j0 += 64) {
+      const int j = j0 + tj;
       cplx acc = make_c(0, 0);
-      const cplx *o = sO + (size_t)(b - 1) * n;
-      for (int i = 0; i < n; ++i) cfma(acc, o[i], s1[(size_t)i * n + j]);
-      sO[(size_t)b * n + j] = acc;
+      if (j < n)
+        for (int i = tq; i < n; i += 4) cfma(acc, o[i], s1[(size_t)i * ldB + j]);
+      acc = cadd(acc, shfl_xor_c4(acc, 1));
+      acc = cadd(acc, shfl_xor_c4(acc, 2));
+      if (j < n && tq == 0) sO[(size_t)b * ldO + j] = acc;
     }
     __syncthreads();
   }
@@ -324,14 +337,19 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
   const int sl = slot[cfg];
   for (int a0 = 0; a0 < NA_total; a0 += AB) {
     const int na = min(AB, NA_total - a0);
-    // v_a = EB v_{a-1}: thread per row i
+    // v_a = EB v_{a-1}: four threads per row i
     for (int a = (a0 == 0 ? 1 : 0); a < na; ++a) {
       const cplx *vp = (a == 0) ? sv : sV + (size_t)(a - 1) * n;
-      for (int i = tid; i < n; i += 256) {
+      for (int i0 = 0; i0 < n; i0 += 64) {
+        const int i = i0 + tj;
         cplx acc = make_c(0, 0);
-        const cplx *row = sB + (size_t)i * ldB;
-        for (int k = 0; k < n; ++k) cfma(acc, row[k], vp[k]);
-        sV[(size_t)a * n + i] = acc;
+        if (i < n) {
+          const cplx *row = sB + (size_t)i * ldB;
+          for (int k = tq; k < n; k += 4) cfma(acc, row[k], vp[k]);
+        }
+        acc = cadd(acc, shfl_xor_c4(acc, 1));
+        acc = cadd(acc, shfl_xor_c4(acc, 2));
+        if (i < n && tq == 0) sV[(size_t)a * n + i] = acc;
       }
       __syncthreads();
     }
@@ -341,7 +359,7 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
       const long k = (long)(a0 + a) * NB + b;
       if (k < nt) {
         double acc = 0.0;
-        const cplx *o = sO + (size_t)b * n, *v = sV + (size_t)a * n;
+        const cplx *o = sO + (size_t)b * ldO, *v = sV + (size_t)a * n;
         for (int j = 0; j < n; ++j) acc += o[j].x * v[j].x - o[j].y * v[j].y;
         atomicAdd(&out[(size_t)sl * nt + k], wc * acc);
       }
@@ -375,7 +393,7 @@ lind_point_kernel(int n, const cplx *__restrict__ E, const cplx *__restrict__ r0
 }
 
 inline size_t lind_series_smem(int n, int AB = 32, bool gmem = false) {
-  return ((gmem ? 0 : (size_t)n * n + (size_t)n * (n + 1)) + 2 * (size_t)AB * n + n) * sizeof(cplx);
+  return ((gmem ? 0 : 2 * (size_t)n * (n + 1)) + (size_t)AB * (2 * n + 1) + n) * sizeof(cplx);
 }
 
 // Integral: solve (I/tau - 2 pi L) x = r0 by LU with partial pivoting; val = Re(o . x)/tau.
