@@ -72,7 +72,7 @@ struct musim_handle {
   void *stage = nullptr;
   size_t stage_bytes = 0;
   // options
-  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_lanes = 1, opt_rho0_dense = 0;
+  long opt_eigh = 0, opt_polar = 0, opt_chunk = 0, opt_profile = 0, opt_gemm = 0, opt_sorted = 0, opt_polar_mma = 1, opt_lanes = 1, opt_rho0_dense = 0, opt_int_fused = 1;
   cudaEvent_t evIn = nullptr;
   // bookkeeping
   int64_t launches = 0;
@@ -175,6 +175,8 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->opt_polar_mma = value;
   else if (!strcmp(key, "zgemm_pipe"))
     g_zgemm_pipe = value != 0;
+  else if (!strcmp(key, "int_fused"))  // 0: store the weights and run integral_kernel (cross-check of the fused epilogue)
+    h->opt_int_fused = value;
   else if (!strcmp(key, "rho0_dense"))  // 1: form the dense thermal rho0 and multiply (cross-check of the factored kernel)
     h->opt_rho0_dense = value;
   else if (!strcmp(key, "sorted"))  // 1: keep eigenpairs sorted inside the pipeline (slower replay kernel)
@@ -540,12 +542,22 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
     }
     const bool mma = (h->opt_gemm != 1) && d <= 96;  // FP64 tensor-pipe GEMMs (option "gemm" = 1: vector-FMA kernels)
     const bool upper = !integral;  // the polarisation kernels read W[i][j] for i <= j only
+    bool integral_done = false;     // the integral was accumulated by a GEMM epilogue (EPI 4 / 5)
+    IntEpi ie;
+    ie.lam = L.lam;
+    ie.wgt = w + c0;
+    ie.slot = slot + c0;
+    ie.it = integral ? 1.0 / tau : 0.0;
+    ie.out = out;
     {
       ProfScope pt(&h->prof, st, PH_ROTATE);
       const double sc = 1.0 / d_other;
       if (mma && h->mu.enabled) {
         // O' = U^H (O U) with O U formed on the fly from the muon operator's two non-zeros per row
-        if (!general)  // fast path: W = |O'|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
+        if (!general && integral && h->opt_int_fused) {  // ALC fast path: the integral is summed in the GEMM epilogue
+          launch_zgemm_dmma<true, 4, true>(d, n, L.U, dd, L.U, dd, L.W, sc, nullptr, h->mu, p + 3 * c0, st, false, ie);
+          integral_done = true;
+        } else if (!general)  // fast path: W = |O'|^2 / d_other   (hamiltonian.py:204-217; parallel.pyx:56-67)
           launch_zgemm_dmma<true, 1, true>(d, n, L.U, dd, L.U, dd, L.W, sc, nullptr, h->mu, p + 3 * c0, st, upper);
         else
           launch_zgemm_dmma<true, 0, true>(d, n, L.U, dd, L.U, dd, L.Y, 1.0, nullptr, h->mu, p + 3 * c0, st, upper);  // only the tiles W needs
@@ -599,7 +611,12 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
           launch_zgemm_dmma<false, 0, false>(d, n, R, rs, L.U, dd, L.T1, 1.0, nullptr, h->mu, nullptr, st);
           ++h->launches;
         }
-        launch_zgemm_dmma<true, 3, false>(d, n, L.U, dd, L.T1, dd, L.W, 1.0, L.Y, h->mu, nullptr, st, upper);
+        if (integral && h->opt_int_fused) {
+          launch_zgemm_dmma<true, 5, false>(d, n, L.U, dd, L.T1, dd, L.W, 1.0, L.Y, h->mu, nullptr, st, false, ie);
+          integral_done = true;
+        } else {
+          launch_zgemm_dmma<true, 3, false>(d, n, L.U, dd, L.T1, dd, L.W, 1.0, L.Y, h->mu, nullptr, st, upper);
+        }
         ++h->launches;
       } else {
         if (!have_t1) launch_gemm<false, 0>(d, n, R, rs, L.U, dd, L.T1, 1.0, st, &h->launches);
@@ -610,9 +627,11 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
       }
     }
     if (integral) {
-      ProfScope pt(&h->prof, st, PH_INTEGRAL);
-      integral_kernel<<<(unsigned)n, 128, 0, st>>>(d, L.W, L.lam, w + c0, slot + c0, tau, out);
-      ++h->launches;
+      if (!integral_done) {
+        ProfScope pt(&h->prof, st, PH_INTEGRAL);
+        integral_kernel<<<(unsigned)n, 128, 0, st>>>(d, L.W, L.lam, w + c0, slot + c0, tau, out);
+        ++h->launches;
+      }
     } else {
       ProfScope pt(&h->prof, st, PH_POLAR);
       if ((h->opt_polar == 2 || h->opt_polar == 3) && !tg.uniform)

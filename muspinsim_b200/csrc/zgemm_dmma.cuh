@@ -13,7 +13,12 @@
 // B_MUON: B is not read from memory but formed on the fly as O U with the muon observable
 // O = sum_a p_a S_mu^a (x) 1 (two non-zeros per row: spinsys.py:707-732), which removes the
 // T = O U product and its HBM round trip from the fast path.
-// EPI: 0 store C; 1 store (|C|^2 scale, 0); 2 store C + D; 3 store C .* conj(D).
+// EPI: 0 store C; 1 store (|C|^2 scale, 0); 2 store C + D; 3 store C .* conj(D);
+//      4 / 5: the weights of 1 / 3 are not stored but summed into the decaying integral
+//      out[slot] += weight/tau * Re sum_ab w_ab / (1/tau + 2 pi i (l_a - l_b))
+//      (Hamiltonian.integrate_decaying, hamiltonian.py:150-162; experiment.py:492-496) -- the
+//      ALC modes then never write or re-read the d x d weight matrix (9 KB per configuration at
+//      d = 24, the HBM traffic that bounded integral_kernel).
 // upper: only the tiles that touch i <= j are computed and stored (the polarisation kernels read
 // the upper triangle of the Hermitian weight matrix only).
 #pragma once
@@ -24,6 +29,13 @@ namespace musim {
 
 #define ZG_KS 16
 static bool g_zgemm_pipe = true;  // option "zgemm_pipe": 12-warp register-prefetch variant for upper-triangle outputs at d in (64, 96]
+
+struct IntEpi {  // arguments of the integral epilogues (EPI 4 / 5)
+  const double *lam = nullptr, *wgt = nullptr;
+  const int *slot = nullptr;
+  double it = 0.0;  // 1 / tau
+  double *out = nullptr;
+};
 
 struct MuonObs {   // O = [[pz/2, (px - i py)/2], [(px + i py)/2, -pz/2]] on the muon index
   int stride;      // product of the dimensions of the spins after the muon
@@ -37,7 +49,7 @@ template <int T, bool CONJ_A, int EPI, bool B_MUON, bool PIPE = false>
 __global__ void __launch_bounds__(PIPE ? 384 : 64 * T * T, (T == 3 ? 1 : (T == 2 ? 2 : 8)))
 zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx *__restrict__ B,
                   size_t b_stride, cplx *C, double scale, const cplx *D, MuonObs mu,
-                  const double *__restrict__ pvec, int upper) {
+                  const double *__restrict__ pvec, int upper, IntEpi ie = IntEpi()) {
   constexpr int DP = 32 * T;     // padded dimension
   constexpr int LD = DP + 4;     // = 4 (mod 16)
   constexpr int LDK = ZG_KS + 4; // for the non-transposed A slab [m][k]
@@ -281,6 +293,44 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
     __syncthreads();
   }
   }
+  if (EPI >= 4) {
+    // ---- integral epilogue (all tiles are live: the callers pass upper = 0) ----
+    const double twopi = 6.283185307179586476925286766559;
+    const double *lc = ie.lam + cfg * d;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int m = wm * 32 + i * 8 + fr;
+        const int n = wn * 16 + j * 8 + fk * 2;
+        if (m < d) {
+          const double lm = lc[m];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (n + e < d) {
+              cplx v = make_c(cr[i][j][e], ci[i][j][e]);
+              if (EPI == 4)
+                v = make_c(cnorm2(v) * scale, 0.0);
+              else
+                v = cmulc(v, D[cfg * dd + (size_t)m * d + n + e]);
+              const double om = twopi * (lm - lc[n + e]);
+              acc += (v.x * ie.it + v.y * om) / (ie.it * ie.it + om * om);
+            }
+          }
+        }
+      }
+    acc = warp_sum(acc);
+    double *red = sAr;  // the K loop ended with a barrier: the staging buffers are free
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int q = 0; q < NT / 32; ++q) t += red[q];
+      atomicAdd(&ie.out[ie.slot[cfg]], ie.wgt[cfg] * t * ie.it);
+    }
+    return;
+  }
   if (!tile_live) return;
   // ---- epilogue ----
 #pragma unroll
@@ -315,24 +365,24 @@ inline size_t zgemm_dmma_smem() {
 template <bool CONJ_A, int EPI, bool B_MUON>
 inline bool launch_zgemm_dmma(int d, int64_t n, const cplx *A, size_t as, const cplx *B, size_t bs, cplx *C,
                               double scale, const cplx *D, MuonObs mu, const double *pvec, cudaStream_t st,
-                              bool upper = false) {
+                              bool upper = false, IntEpi ie = IntEpi()) {
   if (d > 96) return false;
   if (d <= 32) {
     const size_t sm = zgemm_dmma_smem<1, CONJ_A>();
-    zgemm_dmma_kernel<1, CONJ_A, EPI, B_MUON><<<(unsigned)n, 64, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
+    zgemm_dmma_kernel<1, CONJ_A, EPI, B_MUON><<<(unsigned)n, 64, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0, ie);
   } else if (d <= 64) {
     const size_t sm = zgemm_dmma_smem<2, CONJ_A>();
     cudaFuncSetAttribute(zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON><<<(unsigned)n, 256, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
+    zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON><<<(unsigned)n, 256, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0, ie);
   } else {
     const size_t sm = zgemm_dmma_smem<3, CONJ_A>();
-    if (upper && g_zgemm_pipe) {
+    if (upper && g_zgemm_pipe && EPI < 4) {
       cudaFuncSetAttribute(zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON, true><<<(unsigned)n, 384, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, 1);
       return true;
     }
     cudaFuncSetAttribute(zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON><<<(unsigned)n, 576, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0);
+    zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON><<<(unsigned)n, 576, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0, ie);
   }
   return true;
 }
