@@ -271,6 +271,9 @@ __device__ __forceinline__ cplx shfl_xor_c4(cplx v, int m) {
   return make_c(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 
+// Shared-memory path (GMEM = false): ONE padded matrix buffer, holding E1 while the o_b are built and
+// then EB for the v_a chain, plus AB = 16 vectors of each kind: 101 KB at n = 64, so two
+// configurations share an SM (the mat-vec chains are latency bound).
 template <bool GMEM>
 __global__ void __launch_bounds__(256)
 lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ EB,
@@ -283,21 +286,20 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
   const int tid = threadIdx.x;
   const size_t cfg = blockIdx.x;
   const size_t nn = (size_t)n * n;
-  if (!GMEM) AB = 32;  // compile-time constant on the shared-memory path
+  if (!GMEM) AB = 16;  // compile-time constant on the shared-memory path
   cplx *sm0 = reinterpret_cast<cplx *>(smem_raw);
-  const int ldB = GMEM ? n : n + 1;                                // both matrices padded in shared memory
+  const int ldB = GMEM ? n : n + 1;                                // padded in shared memory
   const size_t npad = (size_t)n * (n + 1);
   const cplx *s1 = GMEM ? E1 + cfg * nn : sm0;                     // E1 [n][ldB]
-  const cplx *sB = GMEM ? EB + cfg * nn : sm0 + npad;              // EB [n][ldB]
+  const cplx *sB = GMEM ? EB + cfg * nn : sm0;                     // EB [n][ldB] (same buffer, loaded after the o_b)
   const int ldO = n + 1;  // padded: in the P[a,b] loop the lanes of a warp read DIFFERENT rows of OB at the same j
-  cplx *sO = GMEM ? sm0 : sm0 + 2 * npad;                          // OB [AB][ldO]
+  cplx *sO = GMEM ? sm0 : sm0 + npad;                              // OB [AB][ldO]
   cplx *sV = sO + (size_t)AB * ldO;                                // VA [AB][n]  (column a stored as a row)
   cplx *sv = sV + (size_t)AB * n;                                  // [n] scratch
   if (!GMEM) {
     for (int idx = tid; idx < nn; idx += 256) {
       const int r = idx / n, c = idx - r * n;
       sm0[r * (n + 1) + c] = E1[cfg * nn + idx];
-      sm0[npad + r * (n + 1) + c] = EB[cfg * nn + idx];
     }
   }
   for (int i = tid; i < n; i += 256) {
@@ -329,6 +331,13 @@ lind_series_kernel(int n, const cplx *__restrict__ E1, const cplx *__restrict__ 
       acc = cadd(acc, shfl_xor_c4(acc, 1));
       acc = cadd(acc, shfl_xor_c4(acc, 2));
       if (j < n && tq == 0) sO[(size_t)b * ldO + j] = acc;
+    }
+    __syncthreads();
+  }
+  if (!GMEM) {  // E1 is done: the buffer now takes EB
+    for (int idx = tid; idx < nn; idx += 256) {
+      const int r = idx / n, c = idx - r * n;
+      sm0[r * (n + 1) + c] = EB[cfg * nn + idx];
     }
     __syncthreads();
   }
@@ -392,8 +401,8 @@ lind_point_kernel(int n, const cplx *__restrict__ E, const cplx *__restrict__ r0
   if (threadIdx.x == 0) atomicAdd(&out[(size_t)slot[cfg] * nt + k], wgt[cfg] * acc);
 }
 
-inline size_t lind_series_smem(int n, int AB = 32, bool gmem = false) {
-  return ((gmem ? 0 : 2 * (size_t)n * (n + 1)) + (size_t)AB * (2 * n + 1) + n) * sizeof(cplx);
+inline size_t lind_series_smem(int n, int AB = 16, bool gmem = false) {
+  return ((gmem ? 0 : (size_t)n * (n + 1)) + (size_t)AB * (2 * n + 1) + n) * sizeof(cplx);
 }
 
 // Integral: solve (I/tau - 2 pi L) x = r0 by LU with partial pivoting; val = Re(o . x)/tau.
@@ -643,7 +652,7 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
   // n <= 76: super-operator resident in shared memory; above that the series / solve kernels read
   // the matrices in place from global memory and keep only AB + AB + 1 vectors on chip
   const bool gmem = lind_series_smem(n) > 227 * 1024 || lind_solve_smem(n) > 227 * 1024;
-  int AB = 32;
+  int AB = gmem ? 32 : 16;
   while (gmem && AB > 2 && lind_series_smem(n, AB, true) > 200 * 1024) AB >>= 1;
   const size_t nn = (size_t)n * n;
   const int nbuf = integral ? 2 : 11;
