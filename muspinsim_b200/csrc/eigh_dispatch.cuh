@@ -22,7 +22,7 @@ static bool g_tridiag_wreg = false; // option "tridiag_wreg": ... with the matri
 static bool g_tridiag_phases = true;  // option "tridiag_phases": K1 in up to three launches of decreasing size
 static bool g_apply_warp = true;   // option "apply_warp": rotation replay with one warp per CTA (d > 32)
 static int g_reflect_cpt = 2;      // option "reflect_cpt": columns per thread of the d > 64 reflector kernel (1 or 2)
-static int g_tql_threads = 16;    // option "tql_threads": matrices per block of the QL kernel (8, 16 or 32)
+static int g_tql_threads = 0;     // option "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
 static bool g_tridiag_rw = true;   // option "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96)
 static bool g_tridiag_reg = false;  // option "tridiag_reg": register-resident tridiagonalisation (slower)
 
@@ -264,7 +264,7 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   cudaError_t e;
   {
     ProfScope ps(prof, st, PH_EIGH_TQL);
-    int nt = g_tql_threads;
+    int nt = g_tql_threads ? g_tql_threads : (d <= 32 ? 32 : 16);  // measured: C3 (d = 24) 12.0 -> 10.2 ms per 10^6 with 32
     while (nt > 8 && hql_tql_smem(d, nt) > 200 * 1024) nt >>= 1;  // (d, e) of nt matrices per CTA in shared memory
     const int dpad = (!sorted && d <= 96) ? (d <= 16 && g_small24 ? 16 : (d <= 24 && g_small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)))) : 0;  // register replay kernel follows
     const unsigned tb = (unsigned)((n + nt - 1) / nt);

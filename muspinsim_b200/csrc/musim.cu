@@ -156,7 +156,7 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
   else if (!strcmp(key, "reflect_cpt"))
     g_reflect_cpt = value == 1 ? 1 : 2;
   else if (!strcmp(key, "tql_threads"))
-    g_tql_threads = (value == 8 || value == 16) ? (int)value : 32;
+    g_tql_threads = (value == 0 || value == 8 || value == 16) ? (int)value : 32;
   else if (!strcmp(key, "tridiag_warp"))  // 0: CTA-per-matrix kernels also for d <= 32
     g_tridiag_warp = value != 0;
   else if (!strcmp(key, "tridiag_fused"))
