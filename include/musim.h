@@ -131,6 +131,12 @@ int musim_run_axes_host(musim_handle *h, int mode, int64_t n_cfg, int64_t first,
 int musim_eigh(int device, int d, int64_t batch, const double *A, double *evals, double *evecs,
                int method, void *cuda_stream);
 
+/* Host-side tables of the type-1 NUFFT polarisation kernel (polar_nufft.cuh), computed without a
+ * GPU: fine-grid size *M for nt time points, spreading width *w, polynomial degree *deg,
+ * coef[w*(deg+1)] (per-tap monomial coefficients in y = 2x of the "exponential of semicircle"
+ * kernel) and deconv[nt] (1 / kernel Fourier transform at mode k - nt/2).  Any pointer may be NULL. */
+int musim_nufft_tables(int nt, int *M, int *w, int *deg, double *coef, double *deconv);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t musim_launch_count(musim_handle *h);
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "musim_run",
     "musim_run_host",
     "musim_run_axes_host",
+    "musim_nufft_tables",
     "musim_eigh",
     "musim_launch_count",
     "musim_phase_ms",
@@ -72,6 +73,8 @@ def load():
     lib.musim_run_host.restype = i32
     lib.musim_run_axes_host.argtypes = [vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, dbl, i32, vp]
     lib.musim_run_axes_host.restype = i32
+    lib.musim_nufft_tables.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.musim_nufft_tables.restype = i32
     lib.musim_eigh.argtypes = [i32, i32, i64, vp, vp, vp, i32, vp]
     lib.musim_eigh.restype = i32
     lib.musim_launch_count.argtypes = [vp]
@@ -224,6 +227,19 @@ class Handle:
 
     def phase_ms(self, name):
         return float(self._lib.musim_phase_ms(self._h, name.encode()))
+
+
+def nufft_tables(nt):
+    """(M, w, deg, coef[w, deg+1], deconv[nt]) of the NUFFT polarisation kernel (host only)."""
+    lib = load()
+    M, w, deg = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.musim_nufft_tables(int(nt), ctypes.byref(M), ctypes.byref(w), ctypes.byref(deg), None, None)
+    if rc:
+        raise ValueError("musim_nufft_tables failed (%d)" % rc)
+    coef = np.zeros((w.value, deg.value + 1))
+    dec = np.zeros(int(nt))
+    lib.musim_nufft_tables(int(nt), None, None, None, coef.ctypes.data, dec.ctypes.data)
+    return M.value, w.value, deg.value, coef, dec
 
 
 def fp64_peak(device=0, kind=0):

@@ -734,6 +734,28 @@ extern "C" int musim_run_host(musim_handle *h, int mode, int64_t n_cfg, const do
   return MUSIM_OK;
 }
 
+// Host-side tables of the NUFFT polarisation kernel (no GPU needed): the fine-grid size M for nt
+// time points, the per-tap polynomial coefficients coef[NU_W][NU_DEG+1] (monomials in y = 2x) and
+// the deconvolution factors deconv[nt] = 1 / phi^(k - nt/2).  For tests and external checks.
+extern "C" int musim_nufft_tables(int nt, int *M_out, int *w_out, int *deg_out, double *coef, double *deconv) {
+  if (nt < 1) return MUSIM_EINVAL;
+  const int M = nu_grid_size(nt);
+  if (M_out) *M_out = M;
+  if (w_out) *w_out = NU_W;
+  if (deg_out) *deg_out = NU_DEG;
+  if (coef) {
+    double c[NU_W][NU_DEG + 1];
+    nu_build_coef(c);
+    memcpy(coef, c, sizeof c);
+  }
+  if (deconv) {
+    std::vector<double> dec;
+    nu_build_deconv(nt, M, dec);
+    memcpy(deconv, dec.data(), (size_t)nt * sizeof(double));
+  }
+  return MUSIM_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Configuration expansion on the device.
 //

@@ -199,3 +199,36 @@ def test_zcw_generator_properties():
         assert abs(np.mean(3 * np.cos(rows[:, 0]) ** 2 - 1)) < 1e-3 if n >= 100 else True
     tab = ConfigTable({"spins": ["mu", "e"], "orientation": zcw(50), "time": np.linspace(0, 1, 5)})
     assert tab.n_cfg == len(zcw(50)) and abs(tab.w.sum() - 1.0) < 1e-12
+
+
+def test_nufft_tables_reproduce_the_transform_on_the_host():
+    """The library's NUFFT tables (per-tap kernel polynomials, deconvolution factors), used in a
+    numpy restatement of the spread + FFT steps of polar_nufft.cuh, reproduce the direct sum
+    sum_p c_p exp(i k theta_p) to 1e-11 * sum|c| -- no GPU involved."""
+    from muspinsim_b200 import _lib
+
+    rng = np.random.default_rng(3)
+    for nt in (100, 1000):
+        M, w, deg, coef, dec = _lib.nufft_tables(nt)
+        assert M >= 2 * nt and M & (M - 1) == 0 and w == 12
+        npt = 3000
+        f = rng.normal(0, 200.0, npt)
+        f[:300] = np.round(f[:300])  # exact grid hits and clusters
+        c = rng.normal(size=npt) + 1j * rng.normal(size=npt)
+        c /= np.abs(c).sum()
+        dt = 0.01
+        u = np.rint(f * dt) - f * dt  # cycles per step in [-1/2, 1/2]
+        k = np.arange(nt)
+        want = (c[None, :] * np.exp(2j * np.pi * np.outer(k, u))).sum(1)
+        pos = np.where(u < 0, u * M + M, u * M)
+        fl = np.minimum(np.floor(pos), M - 1)
+        y = 2.0 * (pos - fl) - 1.0
+        base = (fl.astype(np.int64) - (w // 2 - 1)) % M
+        cp = c * np.exp(2j * np.pi * (nt // 2) * u)
+        grid = np.zeros(M, complex)
+        for l in range(w):
+            phi = np.polynomial.polynomial.polyval(y, coef[l], tensor=False)
+            np.add.at(grid, (base + l) % M, cp * phi)
+        F = np.fft.ifft(grid) * M
+        got = F[(k - nt // 2) % M] * dec
+        assert np.max(np.abs(got - want)) < 1e-11
