@@ -21,7 +21,7 @@ static bool g_tridiag_fused = true; // option "tridiag_fused": warp kernel with 
 static bool g_tridiag_wreg = false; // option "tridiag_wreg": ... with the matrix rows in registers (measured slower: 34 vs 23 ms per 10^6 d = 24 matrices; dead columns and jump-table picks cost more than the shared-memory traffic saved)
 static bool g_tridiag_phases = true;  // option "tridiag_phases": K1 in up to three launches of decreasing size
 static bool g_apply_warp = true;   // option "apply_warp": rotation replay with one warp per CTA (d > 32)
-static int g_reflect_cpt = 2;      // option "reflect_cpt": columns per thread of the d > 64 reflector kernel (1 or 2)
+static int g_reflect_cpt = 2;      // option "reflect_cpt": columns per thread of the d > 64 reflector kernel (1, 2 or 3; 3 = 8 warps x 250 registers: 12.7 vs 12.6 ms)
 static int g_tql_threads = 0;     // option "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
 static bool g_tridiag_rw = true;   // option "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96)
 static bool g_tridiag_reg = false;  // option "tridiag_reg": register-resident tridiagonalisation (slower)
@@ -347,7 +347,10 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
         hql_reflect_kernel<64, 4><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
       } else {
         const size_t sm = hql_reflect_smem(96);
-        if (g_reflect_cpt == 2) {
+        if (g_reflect_cpt == 3) {
+          cudaFuncSetAttribute(hql_reflect_kernel<96, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+          hql_reflect_kernel<96, 8, 3><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        } else if (g_reflect_cpt == 2) {
           cudaFuncSetAttribute(hql_reflect_kernel<96, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
           hql_reflect_kernel<96, 8, 2><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
         } else {

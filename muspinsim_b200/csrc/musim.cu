@@ -154,7 +154,7 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
   else if (!strcmp(key, "apply_warp"))
     g_apply_warp = value != 0;
   else if (!strcmp(key, "reflect_cpt"))
-    g_reflect_cpt = value == 1 ? 1 : 2;
+    g_reflect_cpt = (value == 1 || value == 3) ? (int)value : 2;
   else if (!strcmp(key, "tql_threads"))
     g_tql_threads = (value == 0 || value == 8 || value == 16) ? (int)value : 32;
   else if (!strcmp(key, "tridiag_warp"))  // 0: CTA-per-matrix kernels also for d <= 32
