@@ -77,3 +77,53 @@ if __name__ == "__main__":
         for deg in range(7, 14):
             got = nufft1(theta, c, N, M, w, deg)
             print("w=%2d deg=%s  max err / sum|c| = %.2e" % (w, deg, np.max(np.abs(got - ref))))
+
+
+def nufft1_real_folded(theta, c, N, M, w=12, deg=10):
+    """Re of the type-1 transform with a HERMITIAN-FOLDED fine grid (groundwork for the next
+    step of polar_nufft.cuh): only Re(sum_m g[m] e^{2 pi i k' m / M}) is needed, which equals the
+    transform of h[m] = (g[m] + conj g[M-m]) / 2, and h is Hermitian, so cells 0 .. M/2 suffice
+    (half the shared memory per warp).  A window cell m > M/2 is stored at M - m conjugated;
+    cells 0 and M/2 keep only their real part at reconstruction."""
+    beta = 2.30 * w
+    th = np.mod(theta, 2 * np.pi)
+    cp = c * np.exp(1j * (N // 2) * th)
+    g = th * M / (2 * np.pi)
+    fl = np.minimum(np.floor(g), M - 1)
+    x = g - fl - 0.5
+    coef = tap_polys(w, beta, deg)
+    half = np.zeros(M // 2 + 1, complex)
+    for l in range(w):
+        ph = np.polynomial.polynomial.polyval(x, coef[l], tensor=False)
+        m = (fl.astype(np.int64) - (w // 2 - 1) + l) % M
+        fold = m > M // 2
+        j = np.where(fold, M - m, m)
+        v = cp * ph
+        np.add.at(half, j, np.where(fold, np.conj(v), v))
+    h = np.zeros(M, complex)
+    h[1 : M // 2] = half[1 : M // 2] / 2
+    h[M // 2 + 1 :] = np.conj(half[1 : M // 2][::-1]) / 2
+    h[0] = half[0].real
+    h[M // 2] = half[M // 2].real
+    ks = np.arange(N) - N // 2
+    F = np.fft.ifft(h) * M
+    return (F[ks % M] / kernel_ft(w, beta, M, ks)).real
+
+
+def check_folded():
+    rng = np.random.default_rng(1)
+    N, M, npt = 1000, 2048, 20000
+    f = rng.normal(0, 300.0, npt)
+    f[:2000] = np.round(f[:2000])
+    f[2000:2100] = 50.0 + rng.normal(0, 1e-3, 100)  # u = -0.5: windows straddling M/2
+    c = rng.normal(size=npt) + 1j * rng.normal(size=npt)
+    c /= np.sum(np.abs(c))
+    theta = -2 * np.pi * f * 0.01
+    k = np.arange(N)
+    ref = (c[None, :] * np.exp(1j * np.outer(k, theta))).sum(1).real
+    got = nufft1_real_folded(theta, c, N, M)
+    print("folded grid: max err / sum|c| = %.2e" % np.max(np.abs(got - ref)))
+
+
+if __name__ == "__main__":
+    check_folded()
