@@ -34,3 +34,8 @@ def test_version_and_argument_validation_without_gpu():
     assert lib.musim_run(None, 0, 0, None, None, None, None, None, 0, None, 1.0, 1, None, None) == -1
     assert lib.musim_eigh(0, 0, 0, None, None, None, 0, None) == -1
     assert lib.musim_destroy(None) == 0
+    assert lib.musim_run_axes_host(None, 0, 0, 0, 1, None, None, None, None, None, None, None, None, None, 0, None,
+                                   1.0, 1, None) == -1
+    assert lib.musim_nufft_tables(0, None, None, None, None, None) == -1
+    M = ctypes.c_int()
+    assert lib.musim_nufft_tables(1000, ctypes.byref(M), None, None, None, None) == 0 and M.value == 2048
