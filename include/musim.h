@@ -69,6 +69,11 @@ int musim_create(musim_handle **h, int device, int d, int n_spins, const int *di
  * evaluation, fitting.py:126-135; here only the coupling-dependent matrices are re-uploaded). */
 int musim_update_system(musim_handle *h, const double *H0, const double *Z);
 
+/* Replace the three observable components M[3][d][d] (HOST): one device handle then serves every
+ * operator of a per-call Hamiltonian.evolve / integrate_decaying(rho0, ..., operators)
+ * (hamiltonian.py:40-164), which the reference evaluates operator by operator. */
+int musim_update_observables(musim_handle *h, const double *M);
+
 /* Use an explicit initial density matrix (d*d complex, HOST) for every configuration instead
  * of the thermal product state of ExperimentRunner.rho0 (experiment.py:170-236).  This is the
  * per-call boundary Hamiltonian.evolve(rho0, times, operators) (hamiltonian.py:40).  NULL
@@ -141,7 +146,10 @@ int musim_nufft_tables(int nt, int *M, int *w, int *deg, double *coef, double *d
 int64_t musim_launch_count(musim_handle *h);
 
 /* Milliseconds of device time spent in the named phase ("eigh", "rotate", "polar", ...)
- * during the last musim_run_host / musim_run with profiling enabled (option "profile" = 1). */
+ * during the last musim_run_host / musim_run with profiling enabled (option "profile" = 1).
+ * The pseudo-phase "axes_resident_hits" returns a counter instead: how many musim_run_axes_host
+ * calls found their configuration table already expanded on the device (resident-system
+ * fitting, fitting.py:126-151). */
 double musim_phase_ms(musim_handle *h, const char *phase);
 
 /* FP64 peak micro-benchmarks used as roofline denominators (MEASURED_PEAKS.json has no FP64
@@ -151,6 +159,10 @@ int musim_fp64_peak(int device, int kind, double *tflops);
 const char *musim_last_error(musim_handle *h);
 int musim_destroy(musim_handle *h);
 int musim_version(void);
+
+/* Number of CUDA devices visible to the process (0 if there is none): lets the reference-side
+ * adapter map an MPI rank of `mpirun -n N muspinsim.mpi` (mpi.py:18-27) to a device without torch. */
+int musim_device_count(void);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ _ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ENOTCONV", -5: "EUNSUP"
 EXPORTS = [
     "musim_create",
     "musim_update_system",
+    "musim_update_observables",
     "musim_set_rho0",
     "musim_set_dissipators",
     "musim_set_option",
@@ -32,6 +33,7 @@ EXPORTS = [
     "musim_launch_count",
     "musim_phase_ms",
     "musim_fp64_peak",
+    "musim_device_count",
     "musim_last_error",
     "musim_destroy",
     "musim_version",
@@ -61,6 +63,8 @@ def load():
     lib.musim_create.restype = i32
     lib.musim_update_system.argtypes = [vp, vp, vp]
     lib.musim_update_system.restype = i32
+    lib.musim_update_observables.argtypes = [vp, vp]
+    lib.musim_update_observables.restype = i32
     lib.musim_set_rho0.argtypes = [vp, vp]
     lib.musim_set_rho0.restype = i32
     lib.musim_set_dissipators.argtypes = [vp, i32, vp, vp]
@@ -83,6 +87,8 @@ def load():
     lib.musim_phase_ms.restype = dbl
     lib.musim_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(dbl)]
     lib.musim_fp64_peak.restype = i32
+    lib.musim_device_count.argtypes = []
+    lib.musim_device_count.restype = i32
     lib.musim_last_error.argtypes = [vp]
     lib.musim_last_error.restype = ctypes.c_char_p
     lib.musim_destroy.argtypes = [vp]
@@ -177,6 +183,12 @@ class Handle:
         Z = _c128(Z) if Z is not None else None
         self._check(self._lib.musim_update_system(self._h, _ptr(H0), _ptr(Z)))
 
+    def update_observables(self, M):
+        M = _c128(M)
+        if M.shape != (3, self.d, self.d):
+            raise ValueError("M must be (3,d,d)")
+        self._check(self._lib.musim_update_observables(self._h, _ptr(M)))
+
     def run_host(self, mode, B, p, T, w, slot, times, tau, out):
         """All numpy (host) arrays; `out` [n_slots, nt] float64 is accumulated into in place."""
         B, p, w = _f64(B), _f64(p), _f64(w)
@@ -184,8 +196,12 @@ class Handle:
         T = _f64(T) if T is not None else None
         slot = np.ascontiguousarray(slot, dtype=np.int32)
         times = _f64(times) if times is not None else None
+        if B.shape != (n, 3) or p.shape != (n, 3) or w.shape != (n,) or slot.shape != (n,) or (T is not None and T.shape != (n,)):
+            raise ValueError("B and p must be [n,3]; T, w and slot must be [n]")
         if not (out.flags.c_contiguous and out.dtype == np.float64 and out.ndim == 2):
             raise ValueError("out must be a C-contiguous float64 [n_slots, nt] array")
+        if n and (slot.min() < 0 or slot.max() >= out.shape[0]):
+            raise ValueError("slot indices must lie in [0, n_slots)")
         nt = len(times) if times is not None else 1
         rc = self._lib.musim_run_host(
             self._h, int(mode), n, _ptr(B), _ptr(p), _ptr(T), _ptr(w), _ptr(slot), nt, _ptr(times),
@@ -240,6 +256,11 @@ def nufft_tables(nt):
     dec = np.zeros(int(nt))
     lib.musim_nufft_tables(int(nt), None, None, None, coef.ctypes.data, dec.ctypes.data)
     return M.value, w.value, deg.value, coef, dec
+
+
+def device_count():
+    """Number of CUDA devices visible to the process (0 without a driver / GPU)."""
+    return int(load().musim_device_count())
 
 
 def fp64_peak(device=0, kind=0):

@@ -77,10 +77,32 @@ def runner_from_reference(ref_runner, device=None, comm=None):
                             dissipation=dissip, device=device, comm=comm, handle_cache=_HANDLES)
 
 
-def run_reference_runner(ref_runner, device=None, comm=None):
-    """What the patched `ExperimentRunner.run` does: GPU evaluation, then the reference's own
-    post-processing (experiment.py:373-382)."""
-    results = runner_from_reference(ref_runner, device, comm).run()
+def local_device():
+    """CUDA device of this process: its node-local rank under torchrun / Open MPI / MVAPICH / Slurm
+    (the reference's own launcher is `mpirun -n N muspinsim.mpi`), modulo the device count."""
+    import os
+
+    from . import _lib
+
+    n = max(1, _lib.device_count())
+    for key in ("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"):
+        if key in os.environ:
+            return int(os.environ[key]) % n
+    return 0
+
+
+def run_reference_runner(ref_runner, device=None, comm=None, mpi=None):
+    """What the patched `ExperimentRunner.run` does: GPU evaluation of this rank's share of the
+    configurations, the reference's own reduction (`mpi.sum_data`, mpi.py:104-112) and its own
+    post-processing (experiment.py:373-382).  `mpi` is the reference's MPIController (rank, size,
+    sum_data); None = single process."""
+    runner = runner_from_reference(ref_runner, device if device is not None else local_device(), comm)
+    if mpi is not None and getattr(mpi, "size", 1) > 1 and comm is None:
+        out = runner.run_partial(mpi.rank, mpi.size)  # cfg[rank::size], experiment.py:369
+        out = mpi.sum_data(out)
+        results = runner.config.finish(out)
+    else:
+        results = runner.run()
     if not ref_runner._variables:
         results = ref_runner.apply_results_function(results, {})
     ref_runner._config.results = results
@@ -96,7 +118,16 @@ def patch_reference():
     def run(self):
         if getattr(self.config, "celio_k", 0):
             return original(self)
-        return run_reference_runner(self)
+        return run_reference_runner(self, mpi=getattr(mexp, "mpi", None))
 
+    run._musim_original = original
     mexp.ExperimentRunner.run = run
     return original
+
+
+def unpatch_reference():
+    import muspinsim.experiment as mexp
+
+    orig = getattr(mexp.ExperimentRunner.run, "_musim_original", None)
+    if orig is not None:
+        mexp.ExperimentRunner.run = orig

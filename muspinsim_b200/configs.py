@@ -377,7 +377,12 @@ class ConfigTable:
         if self.y == "integral":
             return out.reshape(self.results_shape)
         if self.time_isavg:
-            return out.mean(axis=1).reshape(self.results_shape)  # simconfig.py:364-365
+            avg = out.mean(axis=1)  # simconfig.py:364-365
+            if self.x_name == "t":
+                # time is both the x axis and an averaged axis: the reference stores the time average
+                # in every x column (store_time_slice broadcasts the scalar over the slice)
+                return np.repeat(avg[:, None], self.x_len, axis=1).reshape(self.results_shape)
+            return avg.reshape(self.results_shape)
         if self.x_name == "t":
             return out.reshape(self.results_shape)
         if self._t_pos is None:

@@ -2,8 +2,8 @@
 #pragma once
 #include "eigh_hql.cuh"
 #include "eigh_jacobi.cuh"
+#include "eigh_backwy.cuh"
 #include "eigh_large.cuh"
-#include "eigh_tridiag_reg.cuh"
 #include "eigh_tridiag_rw.cuh"
 #include "eigh_tridiag_warp.cuh"
 #include "profiler.cuh"
@@ -14,25 +14,26 @@ namespace musim {
 #define MUSIM_MAX_SMEM_OPTIN (227 * 1024)
 
 enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
-static bool g_reflect = true;      // option "reflect": K4 applies the reflectors to Zt (d <= 96) instead of Q + GEMM
-static bool g_tridiag_warp = true; // option "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
-static bool g_small24 = true;      // option "small24": D = 16 / 24 instantiations of the replay / reflector kernels for d <= 16 / 24 (else D = 32)
-static bool g_tridiag_fused = true; // option "tridiag_fused": warp kernel with the update of step k fused into the product of step k+1
-static bool g_tridiag_wreg = false; // option "tridiag_wreg": ... with the matrix rows in registers (measured slower: 34 vs 23 ms per 10^6 d = 24 matrices; dead columns and jump-table picks cost more than the shared-memory traffic saved)
-static bool g_tridiag_phases = true;  // option "tridiag_phases": K1 in up to three launches of decreasing size
-static bool g_apply_warp = true;   // option "apply_warp": rotation replay with one warp per CTA (d > 32)
-static int g_reflect_cpt = 2;      // option "reflect_cpt": columns per thread of the d > 64 reflector kernel (1, 2 or 3; 3 = 8 warps x 250 registers: 12.7 vs 12.6 ms)
-static int g_tql_threads = 0;     // option "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
-static bool g_tridiag_rw = true;   // option "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96)
-static bool g_tridiag_reg = false;  // option "tridiag_reg": register-resident tridiagonalisation (slower)
+// Kernel-selection options of the eigensolver (per handle; musim_set_option).  The defaults are the
+// measured-fastest variants; the others stay as independent cross-checks covered by the parity tests.
+struct EighOpts {
+  bool reflect = true;         // "reflect": K4 applies the reflectors to Zt (d <= 96); 0: Q formed in K1 + GEMM
+  bool back_wy = true;         // "back_wy": K4 in compact-WY blocks on the FP64 tensor pipe (32 < d <= 96); 0: level-2 reflector kernel
+  bool tridiag_warp = true;    // "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
+  bool small24 = true;         // "small24": D = 16 / 24 instantiations of the replay / reflector kernels for d <= 16 / 24 (else D = 32)
+  bool tridiag_fused = true;   // "tridiag_fused": warp kernel with the update of step k fused into the product of step k+1
+  bool tridiag_phases = true;  // "tridiag_phases": K1 in up to three launches of decreasing size
+  bool apply_warp = true;      // "apply_warp": rotation replay with one warp per CTA (d > 32)
+  int tql_threads = 0;         // "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
+  bool tridiag_rw = true;      // "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96); 0: shared-memory kernel
+  bool use_reflect(int d) const { return reflect && d >= 3 && d <= 96; }
+};
 
 inline int pick_eigh(long opt, int d) {
   if (opt == EIGH_JACOBI) return EIGH_JACOBI;
   if (opt == EIGH_HQL) return hql_supported(d) ? EIGH_HQL : EIGH_JACOBI;
   return hql_supported(d) ? EIGH_HQL : EIGH_JACOBI;
 }
-
-inline bool use_reflect(int d) { return g_reflect && !g_tridiag_reg && d >= 3 && d <= 96; }
 
 struct EighWs {
   int64_t cap = 0;
@@ -131,7 +132,7 @@ struct EighWs {
 // (For Jacobi, stage A is the whole solver.)  Returns 0, a cudaError_t (> 0), or -5.
 inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
                               const cplx *Ain, double *lam, cplx *U, EighWs &ws, int buf, int *status,
-                              cudaStream_t st, int64_t *launches, Profiler *prof) {
+                              cudaStream_t st, int64_t *launches, Profiler *prof, const EighOpts &o) {
   cudaError_t e;
   if (method == EIGH_HQL) {
     if (!hql_supported(d)) return -5;
@@ -157,28 +158,17 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
     const size_t smem = hql_tridiag_smem(d, g);
     if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
     ProfScope ps(prof, st, PH_EIGH_TRIDIAG);
-    if (use_reflect(d) && g_tridiag_warp && g_tridiag_wreg && d <= 32) {
-      const unsigned gb = (unsigned)n;
-      if (d <= 16)
-        hql_tridiag_wreg_kernel<16><<<gb, 32, 0, st>>>(d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf],
-                                                                 ws.vcap, ws.tauv[buf]);
-      else if (d <= 24)
-        hql_tridiag_wreg_kernel<24><<<gb, 32, 0, st>>>(d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf],
-                                                                 ws.vcap, ws.tauv[buf]);
-      else
-        hql_tridiag_wreg_kernel<32><<<gb, 32, 0, st>>>(d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf],
-                                                                 ws.vcap, ws.tauv[buf]);
-    } else if (use_reflect(d) && g_tridiag_warp && g_tridiag_fused && d <= 32) {
+    if (o.use_reflect(d) && o.tridiag_warp && o.tridiag_fused && d <= 32) {
       const size_t sm = hql_tridiag_warpf_smem(d);
       cudaFuncSetAttribute(hql_tridiag_warpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       hql_tridiag_warpf_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
           d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
-    } else if (use_reflect(d) && g_tridiag_warp && d <= 32) {
+    } else if (o.use_reflect(d) && o.tridiag_warp && d <= 32) {
       const size_t sm = hql_tridiag_warp_smem(d);
       cudaFuncSetAttribute(hql_tridiag_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       hql_tridiag_warp_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
           d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
-    } else if (use_reflect(d) && g_tridiag_rw) {
+    } else if (o.use_reflect(d) && o.tridiag_rw) {
       double *dd_ = ws.dbuf[buf], *ee_ = ws.ebuf[buf];
       cplx *vp_ = ws.Vp[buf], *tt_ = ws.tauv[buf];
       // phase buffers for the trailing blocks (Q is not used on the reflector path)
@@ -186,7 +176,7 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
       const unsigned g = (unsigned)n;
       if (d <= 32) {
         hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-      } else if (!g_tridiag_phases) {
+      } else if (!o.tridiag_phases) {
         if (d <= 64)
           hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
         else
@@ -203,31 +193,16 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
         hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(32, d, k1 + 32, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
         *launches += 2;
       }
-    } else if (d <= 96 && g_tridiag_reg) {
-      // register-resident A (eigh_tridiag_reg.cuh): R = d rounded up to 32 / 64 / 96
-      if (d <= 32) {
-        const size_t sm = hql_tridiag_reg_smem<32>();
-        cudaFuncSetAttribute(hql_tridiag_reg_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_tridiag_reg_kernel<32, 8><<<(unsigned)n, 128, sm, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf]);
-      } else if (d <= 64) {
-        const size_t sm = hql_tridiag_reg_smem<64>();
-        cudaFuncSetAttribute(hql_tridiag_reg_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_tridiag_reg_kernel<64, 16><<<(unsigned)n, 256, sm, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf]);
-      } else {
-        const size_t sm = hql_tridiag_reg_smem<96>();
-        cudaFuncSetAttribute(hql_tridiag_reg_kernel<96, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_tridiag_reg_kernel<96, 24><<<(unsigned)n, 384, sm, st>>>(d, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf]);
-      }
     } else if (Ain) {
       e = cudaFuncSetAttribute(hql_tridiag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       hql_tridiag_kernel<false><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf],
-                                                                  use_reflect(d) ? ws.Vp[buf] : nullptr, ws.vcap, ws.tauv[buf]);
+                                                                  o.use_reflect(d) ? ws.Vp[buf] : nullptr, ws.vcap, ws.tauv[buf]);
     } else {
       e = cudaFuncSetAttribute(hql_tridiag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
       hql_tridiag_kernel<true><<<(unsigned)n, g.nth, smem, st>>>(d, g.R, g.G, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Q[buf],
-                                                                 use_reflect(d) ? ws.Vp[buf] : nullptr, ws.vcap, ws.tauv[buf]);
+                                                                 o.use_reflect(d) ? ws.Vp[buf] : nullptr, ws.vcap, ws.tauv[buf]);
     }
     ++*launches;
     return (int)cudaGetLastError();
@@ -259,14 +234,14 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
 
 // Stage B (Householder+QL only): QL on (d, e), rotation replay, back-transformation U = Q Zt.
 inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U, EighWs &ws, int buf, int *status,
-                              cudaStream_t st, int64_t *launches, Profiler *prof, bool sorted) {
+                              cudaStream_t st, int64_t *launches, Profiler *prof, bool sorted, const EighOpts &o) {
   if (method != EIGH_HQL) return 0;
   cudaError_t e;
   {
     ProfScope ps(prof, st, PH_EIGH_TQL);
-    int nt = g_tql_threads ? g_tql_threads : (d <= 32 ? 32 : 16);  // measured: C3 (d = 24) 12.0 -> 10.2 ms per 10^6 with 32
+    int nt = o.tql_threads ? o.tql_threads : (d <= 32 ? 32 : 16);  // measured: C3 (d = 24) 12.0 -> 10.2 ms per 10^6 with 32
     while (nt > 8 && hql_tql_smem(d, nt) > 200 * 1024) nt >>= 1;  // (d, e) of nt matrices per CTA in shared memory
-    const int dpad = (!sorted && d <= 96) ? (d <= 16 && g_small24 ? 16 : (d <= 24 && g_small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)))) : 0;  // register replay kernel follows
+    const int dpad = (!sorted && d <= 96) ? (d <= 16 && o.small24 ? 16 : (d <= 24 && o.small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)))) : 0;  // register replay kernel follows
     const unsigned tb = (unsigned)((n + nt - 1) / nt);
     const size_t sm = hql_tql_smem(d, nt);
 #define TQL_LAUNCH(NT)                                                                                       \
@@ -290,8 +265,8 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   const int ath = std::min(128, (d + 31) & ~31);
   if (!sorted && d <= 96) {
     // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
-    const int D = d <= 16 && g_small24 ? 16 : (d <= 24 && g_small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)));
-    const int nth = D < 32 ? D : (g_apply_warp ? 32 : D);  // option "apply_warp": one warp (32 rows of Z) per CTA
+    const int D = d <= 16 && o.small24 ? 16 : (d <= 24 && o.small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)));
+    const int nth = D < 32 ? D : (o.apply_warp ? 32 : D);  // option "apply_warp": one warp (32 rows of Z) per CTA
     const size_t rsmem = hql_apply_reg_smem(D, nth, ws.swp_cap);
     const dim3 grid((unsigned)n, D / nth);
     ProfScope ps(prof, st, PH_EIGH_APPLY);
@@ -323,14 +298,24 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   ++*launches;
   {
     ProfScope ps(prof, st, PH_EIGH_BACK);
-    if (use_reflect(d)) {
+    if (o.use_reflect(d) && o.back_wy && d > 32) {
+      if (d <= 64) {
+        const size_t sm = BackWyGeom<64>::smem_bytes;
+        cudaFuncSetAttribute(hql_backwy_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_backwy_kernel<64><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+      } else {
+        const size_t sm = BackWyGeom<96>::smem_bytes;
+        cudaFuncSetAttribute(hql_backwy_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_backwy_kernel<96><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+      }
+    } else if (o.use_reflect(d)) {
       if (d <= 32) {
         const size_t sm = hql_reflect_smem(32);
-        if (d <= 16 && g_small24) {
+        if (d <= 16 && o.small24) {
           const size_t sm16 = hql_reflect_smem(16);
           cudaFuncSetAttribute(hql_reflect_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16);
           hql_reflect_kernel<16, 1><<<(unsigned)n, 16, sm16, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
-        } else if (d <= 24 && g_small24) {  // D = 24 instantiation: 24 rows per thread instead of 32 (fewer registers, more warps)
+        } else if (d <= 24 && o.small24) {  // D = 24 instantiation: 24 rows per thread instead of 32 (fewer registers, more warps)
           const size_t sm24 = hql_reflect_smem(24);
           cudaFuncSetAttribute(hql_reflect_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm24);
           hql_reflect_kernel<24, 1><<<(unsigned)n, 24, sm24, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
@@ -347,16 +332,8 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
         hql_reflect_kernel<64, 4><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
       } else {
         const size_t sm = hql_reflect_smem(96);
-        if (g_reflect_cpt == 3) {
-          cudaFuncSetAttribute(hql_reflect_kernel<96, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-          hql_reflect_kernel<96, 8, 3><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
-        } else if (g_reflect_cpt == 2) {
-          cudaFuncSetAttribute(hql_reflect_kernel<96, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-          hql_reflect_kernel<96, 8, 2><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
-        } else {
-          cudaFuncSetAttribute(hql_reflect_kernel<96, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-          hql_reflect_kernel<96, 8><<<(unsigned)n, 768, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
-        }
+        cudaFuncSetAttribute(hql_reflect_kernel<96, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_reflect_kernel<96, 8, 2><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
       }
     } else {
       dim3 grid((d + 31) / 32, (d + 31) / 32, (unsigned)n);
@@ -371,14 +348,14 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
 // `sorted`, U row-major with eigenvectors in columns.  Returns 0, a cudaError_t (> 0), or -5.
 inline int launch_eigh(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
                        const cplx *Ain, double *lam, cplx *U, EighWs &ws, int *status, cudaStream_t st,
-                       int64_t *launches, Profiler *prof, bool sorted = true) {
+                       int64_t *launches, Profiler *prof, bool sorted = true, const EighOpts &o = EighOpts()) {
   int64_t dummy = 0;
   if (!launches) launches = &dummy;
   cudaError_t e = ws.ensure(method, d, n);
   if (e != cudaSuccess) return (int)e;
-  int rc = launch_eigh_stageA(method, d, n, H0, Z, B, Ain, lam, U, ws, 0, status, st, launches, prof);
+  int rc = launch_eigh_stageA(method, d, n, H0, Z, B, Ain, lam, U, ws, 0, status, st, launches, prof, o);
   if (rc) return rc;
-  return launch_eigh_stageB(method, d, n, lam, U, ws, 0, status, st, launches, prof, sorted);
+  return launch_eigh_stageB(method, d, n, lam, U, ws, 0, status, st, launches, prof, sorted, o);
 }
 
 }  // namespace musim

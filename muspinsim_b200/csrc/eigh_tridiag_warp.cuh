@@ -310,170 +310,6 @@ inline size_t hql_tridiag_warpf_smem(int d) {
   return (size_t)TRW_WARPS * ((size_t)d * (d | 1) + 96) * sizeof(cplx);
 }
 
-// ---------------------------------------------------------------------------------------
-// Register-resident variant: lane r keeps ROW r of A in registers (D complex numbers, static
-// column indices: the column loops are fully unrolled with warp-uniform guards), only v and w go
-// through a per-warp shared-memory line (broadcast reads).  ncu on the shared-memory kernel above
-// at d = 24: LSU 78 % busy (every element of A is loaded and stored once per step), FP64 43 %.
-// Element (r, k) with a run-time k is fetched through a jump table.
-// ---------------------------------------------------------------------------------------
-template <int D>
-__device__ __forceinline__ cplx trw_pick(const cplx (&a)[D], int k) {
-  cplx x = make_c(0.0, 0.0);
-  switch (k) {
-#define TRW_CASE(c) \
-  case c:           \
-    if (c < D) x = a[c < D ? c : 0]; \
-    break;
-    TRW_CASE(0) TRW_CASE(1) TRW_CASE(2) TRW_CASE(3) TRW_CASE(4) TRW_CASE(5) TRW_CASE(6) TRW_CASE(7)
-    TRW_CASE(8) TRW_CASE(9) TRW_CASE(10) TRW_CASE(11) TRW_CASE(12) TRW_CASE(13) TRW_CASE(14) TRW_CASE(15)
-    TRW_CASE(16) TRW_CASE(17) TRW_CASE(18) TRW_CASE(19) TRW_CASE(20) TRW_CASE(21) TRW_CASE(22) TRW_CASE(23)
-    TRW_CASE(24) TRW_CASE(25) TRW_CASE(26) TRW_CASE(27) TRW_CASE(28) TRW_CASE(29) TRW_CASE(30) TRW_CASE(31)
-#undef TRW_CASE
-    default:
-      break;
-  }
-  return x;
-}
-
-template <int D>
-__global__ void __launch_bounds__(32)
-hql_tridiag_wreg_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cplx *__restrict__ Z,
-                        const double *__restrict__ Bf, const cplx *__restrict__ Ain,
-                        double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Vp,
-                        size_t vcap, cplx *__restrict__ tauout) {
-  // one warp per CTA: the register file then fills with whole warps (9 at D = 32, 11 at D = 24)
-  __shared__ __align__(16) cplx svw[2][32];
-  const int lane = threadIdx.x;
-  cplx *sv = svw[0], *sw = svw[1];
-  const int64_t cfg = blockIdx.x;
-  if (cfg >= n) return;  // whole warp
-  const size_t dd = (size_t)d * d;
-  const int r = lane;  // my row
-  cplx a[D];
-  {
-    double bx = 0, by = 0, bz = 0;
-    if (!Ain) {
-      bx = Bf[cfg * 3 + 0];
-      by = Bf[cfg * 3 + 1];
-      bz = Bf[cfg * 3 + 2];
-    }
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      cplx v = make_c(0.0, 0.0);
-      if (r < d && c < d) {
-        const size_t idx = (size_t)r * d + c;
-        if (Ain) {
-          v = Ain[cfg * dd + idx];
-        } else {
-          v = H0[idx];
-          const cplx z0 = Z[idx], z1 = Z[dd + idx], z2 = Z[2 * dd + idx];
-          v.x += bx * z0.x + by * z1.x + bz * z2.x;
-          v.y += bx * z0.y + by * z1.y + bz * z2.y;
-        }
-        if (r == c) v.y = 0.0;
-      }
-      a[c] = v;
-    }
-  }
-  for (int k = 0; k < d - 1; ++k) {
-    const int mk = d - k - 2;
-    const size_t voff = (size_t)mk * (mk - 1) / 2;
-    const cplx ak = trw_pick<D>(a, k);  // A(r, k)
-    // column k (rows > k); lanes <= k and >= d hold zero
-    const cplx x = (r > k && r < d) ? ak : make_c(0.0, 0.0);
-    double xn = (r >= k + 2) ? cnorm2(x) : 0.0;
-    xn = warp_sum(xn);
-    const cplx alpha = make_c(__shfl_sync(0xffffffffu, x.x, k + 1), __shfl_sync(0xffffffffu, x.y, k + 1));
-    if (lane == k) dout[cfg * d + k] = ak.x;
-    if (xn == 0.0 && alpha.y == 0.0) {  // H_k = I
-      if (lane == 0) {
-        eout[cfg * d + k] = alpha.x;
-        tauout[cfg * d + k] = make_c(0.0, 0.0);
-      }
-      for (int i = lane; i < mk; i += 32) Vp[cfg * vcap + voff + i] = make_c(0.0, 0.0);
-      continue;
-    }
-    const double s2 = alpha.x * alpha.x + alpha.y * alpha.y + xn;
-    const double ri = rsqrt(s2);
-    const double sg = (alpha.x >= 0.0) ? -1.0 : 1.0;
-    const double beta = sg * (s2 * ri);
-    const double ib = sg * ri;
-    const cplx tau = make_c((beta - alpha.x) * ib, -alpha.y * ib);
-    const double ar = alpha.x - beta, ai = alpha.y;
-    const double den = __drcp_rn(ar * ar + ai * ai);
-    const cplx scale = make_c(ar * den, -ai * den);
-    cplx v = make_c(0.0, 0.0);
-    if (r == k + 1)
-      v = make_c(1.0, 0.0);
-    else if (r > k + 1)
-      v = cmul(scale, x);
-    if (lane == 0) {
-      eout[cfg * d + k] = beta;
-      tauout[cfg * d + k] = tau;
-    }
-    sv[r] = v;
-    if (r >= k + 2 && r < d) Vp[cfg * vcap + voff + (r - k - 2)] = v;
-    __syncwarp();
-    // p = tau A22 v: row r times v.  v (and w below) are ZERO outside the trailing block, so the
-    // column loops need no per-column guard: blocks of 8 columns run as straight-line code (8-fold
-    // ILP under the broadcast-load latency) and only whole dead blocks are skipped.
-    cplx y = make_c(0.0, 0.0), y1 = make_c(0.0, 0.0);
-#pragma unroll
-    for (int b = 0; b < (D + 7) / 8; ++b) {
-      if (8 * b + 7 > k && 8 * b < d) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int c = 8 * b + q;
-          if (c < D) {
-            if (q & 1)
-              cfma(y1, a[c], sv[c]);
-            else
-              cfma(y, a[c], sv[c]);
-          }
-        }
-      }
-    }
-    y = cadd(y, y1);
-    if (!(r > k && r < d)) y = make_c(0.0, 0.0);
-    const cplx p = cmul(tau, y);
-    cplx dot = ccmul(p, v);  // conj(p) v  (v = 0 outside the trailing block)
-    dot.x = warp_sum(dot.x);
-    dot.y = warp_sum(dot.y);
-    const cplx a2 = cscale(-0.5, cmul(tau, dot));
-    const cplx w = cadd(p, cmul(a2, v));
-    sw[r] = w;
-    __syncwarp();
-    // A22 -= v w^H + w v^H   (v = w = 0 on the rows and columns outside the trailing block)
-#pragma unroll
-    for (int b = 0; b < (D + 7) / 8; ++b) {
-      if (8 * b + 7 > k && 8 * b < d) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int c = 8 * b + q;
-          if (c < D) {
-            const cplx wc = sw[c], vc = sv[c];
-            a[c].x = fma(-v.x, wc.x, a[c].x);
-            a[c].y = fma(-v.y, wc.x, a[c].y);
-            a[c].x = fma(-v.y, wc.y, a[c].x);
-            a[c].y = fma(v.x, wc.y, a[c].y);
-            a[c].x = fma(-w.x, vc.x, a[c].x);
-            a[c].y = fma(-w.y, vc.x, a[c].y);
-            a[c].x = fma(-w.y, vc.y, a[c].x);
-            a[c].y = fma(w.x, vc.y, a[c].y);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
-  const cplx al = trw_pick<D>(a, d - 1);
-  if (lane == d - 1) {
-    dout[cfg * d + d - 1] = al.x;
-    eout[cfg * d + d - 1] = 0.0;
-  }
-}
-
 inline size_t hql_tridiag_warp_smem(int d) {
   return (size_t)TRW_WARPS * ((size_t)d * (d | 1) + 64) * sizeof(cplx);
 }

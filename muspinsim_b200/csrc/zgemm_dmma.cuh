@@ -28,7 +28,6 @@
 namespace musim {
 
 #define ZG_KS 16
-static bool g_zgemm_pipe = true;  // option "zgemm_pipe": 12-warp register-prefetch variant for upper-triangle outputs at d in (64, 96]
 
 struct IntEpi {  // arguments of the integral epilogues (EPI 4 / 5)
   const double *lam = nullptr, *wgt = nullptr;
@@ -365,7 +364,8 @@ inline size_t zgemm_dmma_smem() {
 template <bool CONJ_A, int EPI, bool B_MUON>
 inline bool launch_zgemm_dmma(int d, int64_t n, const cplx *A, size_t as, const cplx *B, size_t bs, cplx *C,
                               double scale, const cplx *D, MuonObs mu, const double *pvec, cudaStream_t st,
-                              bool upper = false, IntEpi ie = IntEpi()) {
+                              bool upper = false, IntEpi ie = IntEpi(), bool pipe = true) {
+  // pipe (option "zgemm_pipe"): 12-warp register-prefetch variant for upper-triangle outputs at d in (64, 96]
   if (d > 96) return false;
   if (d <= 32) {
     const size_t sm = zgemm_dmma_smem<1, CONJ_A>();
@@ -376,7 +376,7 @@ inline bool launch_zgemm_dmma(int d, int64_t n, const cplx *A, size_t as, const 
     zgemm_dmma_kernel<2, CONJ_A, EPI, B_MUON><<<(unsigned)n, 256, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, upper ? 1 : 0, ie);
   } else {
     const size_t sm = zgemm_dmma_smem<3, CONJ_A>();
-    if (upper && g_zgemm_pipe && EPI < 4) {
+    if (upper && pipe && EPI < 4) {
       cudaFuncSetAttribute(zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       zgemm_dmma_kernel<3, CONJ_A, EPI, B_MUON, true><<<(unsigned)n, 384, sm, st>>>(d, A, as, B, bs, C, scale, D, mu, pvec, 1);
       return true;

@@ -71,6 +71,7 @@ class ExperimentRunner:
             h = self._handle_cache.get(key)
             if h is not None:
                 self._handle = h
+                h.set_option("defaults", 1)  # an earlier runner's kernel options do not leak into this one
                 for k, v in self.options.items():
                     h.set_option(k, v)
                 return h

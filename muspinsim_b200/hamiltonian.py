@@ -42,6 +42,7 @@ class Hamiltonian:
             raise ValueError("Matrix size is not compatible with the dimension tuple")
         self._device = device
         self._eigh = None
+        self._handles = {}
 
     @property
     def matrix(self):
@@ -66,37 +67,65 @@ class Hamiltonian:
             self._eigh = (ev[0].cpu().numpy(), U[0].cpu().numpy())
         return self._eigh
 
-    def _handle(self, ops, muon_first_dims=None):
-        d = self._matrix.shape[0]
-        zeros = np.zeros((3, d, d), dtype=complex)
-        M = zeros.copy()
-        M[0] = ops
-        dims = muon_first_dims or [d]
-        return _lib.Handle(self._device, dims, np.zeros(len(dims)), 0, self._matrix, zeros, M)
+    def _get_handle(self, dims):
+        """ONE device handle per Hamiltonian and dimension tuple: H0 is uploaded once, every call
+        only replaces the observable (musim_update_observables) and rho0."""
+        key = tuple(int(x) for x in dims)
+        h = self._handles.get(key)
+        if h is None:
+            d = self._matrix.shape[0]
+            zeros = np.zeros((3, d, d), dtype=complex)
+            h = _lib.Handle(self._device, list(key), np.zeros(len(key)), 0, self._matrix, zeros, zeros)
+            self._handles[key] = h
+        return h
 
-    def _run(self, mode, rho0, times, tau, op):
-        h = self._handle(_dense(op))
+    def close(self):
+        for h in self._handles.values():
+            h.close()
+        self._handles = {}
+
+    def __del__(self):
         try:
-            if rho0 is not None:
-                h.set_rho0(rho0)
-            nt = len(times) if times is not None else 1
+            self.close()
+        except Exception:
+            pass
+
+    def _expect(self, mode, rho0, times, tau, op):
+        """<op>(t) for one operator.  The device path evaluates Re sum_ij rho'_ij O'_ji e^{..} from the
+        i <= j triangle, which is the full (real) expectation value only for Hermitian O; a
+        non-Hermitian operator (the reference's SpinOperator API allows e.g. S+) is split into its
+        Hermitian and anti-Hermitian parts, O = Oh + i Oa, and evaluated as <Oh> + i <Oa>."""
+        O = _dense(op)
+        if O.shape != self._matrix.shape:
+            raise ValueError("Incompatible operator dimension")
+        Oh, Oa = 0.5 * (O + O.conj().T), -0.5j * (O - O.conj().T)
+        parts = [Oh] if np.max(np.abs(Oa)) <= 1e-15 * max(1.0, np.max(np.abs(O))) else [Oh, Oa]
+        h = self._get_handle([self._matrix.shape[0]])
+        h.set_rho0(rho0)
+        nt = len(times) if times is not None else 1
+        res = np.zeros(nt, dtype=complex)
+        one = np.array([[1.0, 0.0, 0.0]])
+        for k, part in enumerate(parts):
+            M = np.zeros((3,) + O.shape, dtype=complex)
+            M[0] = part
+            h.update_observables(M)
             out = np.zeros((1, nt))
-            one = np.array([[1.0, 0.0, 0.0]])
             h.run_host(mode, np.zeros((1, 3)), one, np.array([np.inf]), np.array([1.0]), np.array([0]), times,
                        tau, out)
-            return out[0]
-        finally:
-            h.close()
+            res = res + (1j if k else 1.0) * out[0]
+        return res
 
     def _check_rho0(self, rho0, name="rho0"):
         r = _dense(rho0)
         if r.shape != self._matrix.shape:
             raise ValueError("Incompatible rho0 dimension")
+        # a DensityOperator is Hermitian by construction (spinop.py:431-453); the device path relies on it
+        if not np.all(np.isclose(r, r.conj().T, atol=self.herm_tol)):
+            raise ValueError("rho0 must be a Hermitian density matrix")
         return r
 
     def evolve(self, rho0, times, operators=None):
-        """hamiltonian.py:40-117: expectation values [nt, n_ops] (complex; the imaginary part
-        of a Hermitian observable's expectation is zero and is returned as such)."""
+        """hamiltonian.py:40-117: expectation values [nt, n_ops] (complex)."""
         if operators is None:
             operators = []
         times = np.array(times)
@@ -106,7 +135,7 @@ class Hamiltonian:
         if len(operators) == 0:
             raise NotImplementedError("density-matrix output (operators=None) is outside the hot path")
         r = self._check_rho0(rho0)
-        cols = [self._run(_lib.MODE_EVOLVE, r, times.astype(float), 1.0, o) for o in operators]
+        cols = [self._expect(_lib.MODE_EVOLVE, r, times.astype(float), 1.0, o) for o in operators]
         return np.array(cols).T.astype(complex)
 
     def integrate_decaying(self, rho0, tau, operators):
@@ -119,7 +148,7 @@ class Hamiltonian:
             raise ValueError("At least one SpinOperator must be present in 'operators'")
         r = self._check_rho0(rho0)
         # the ABI returns the integral divided by tau (experiment.py:492-496)
-        return np.array([self._run(_lib.MODE_INTEGRAL, r, None, float(tau), o)[0] * tau for o in operators]).astype(complex)
+        return np.array([self._expect(_lib.MODE_INTEGRAL, r, None, float(tau), o)[0] * tau for o in operators]).astype(complex)
 
     def fast_evolve(self, sigma_mu, times, other_dimension):
         """hamiltonian.py:166-217: muon first, other spins maximally mixed; result in [-0.5, 0.5]."""
@@ -129,12 +158,14 @@ class Hamiltonian:
         d = self._matrix.shape[0]
         if sig.shape != (2, 2) or 2 * int(other_dimension) != d:
             raise ValueError("sigma_mu must be 2x2 and other_dimension half the total dimension")
+        if not np.all(np.isclose(sig, sig.conj().T, atol=self.herm_tol)):
+            raise ValueError("sigma_mu must be Hermitian")
         O = np.kron(0.5 * sig, np.eye(int(other_dimension)))
-        h = self._handle(O, muon_first_dims=[2, int(other_dimension)])
-        try:
-            out = np.zeros((1, len(times)))
-            h.run_host(_lib.MODE_FAST, np.zeros((1, 3)), np.array([[1.0, 0, 0]]), None, np.array([1.0]),
-                       np.array([0]), times.astype(float), 1.0, out)
-            return out[0]
-        finally:
-            h.close()
+        h = self._get_handle([2, int(other_dimension)])
+        M = np.zeros((3, d, d), dtype=complex)
+        M[0] = O
+        h.update_observables(M)
+        out = np.zeros((1, len(times)))
+        h.run_host(_lib.MODE_FAST, np.zeros((1, 3)), np.array([[1.0, 0, 0]]), None, np.array([1.0]),
+                   np.array([0]), times.astype(float), 1.0, out)
+        return out[0]

@@ -15,6 +15,7 @@ class Lindbladian:
         self._H = H
         self._dops = [(_dense(A), float(g)) for A, g in dissipators]
         self._device = device
+        self._handle = None
 
     @classmethod
     def from_hamiltonian(cls, H, dissipators=()):
@@ -37,22 +38,45 @@ class Lindbladian:
     def dimension(self):
         return self._H.dimension * 2
 
-    def _run(self, mode, rho0, times, tau, op):
-        d = self._H.matrix.shape[0]
-        zeros = np.zeros((3, d, d), dtype=complex)
-        M = zeros.copy()
-        M[0] = _dense(op)
-        h = _lib.Handle(self._device, [d], [0.0], 0, self._H.matrix, zeros, M)
+    def _get_handle(self):
+        """ONE device handle per Lindbladian; calls only replace the observable, rho0 and jump operators."""
+        if self._handle is None:
+            d = self._H.matrix.shape[0]
+            zeros = np.zeros((3, d, d), dtype=complex)
+            self._handle = _lib.Handle(self._device, [d], [0.0], 0, self._H.matrix, zeros, zeros)
+        return self._handle
+
+    def close(self):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+
+    def __del__(self):
         try:
-            h.set_rho0(rho0)
-            h.set_dissipators([a for a, _ in self._dops], [g for _, g in self._dops])
-            nt = len(times) if times is not None else 1
+            self.close()
+        except Exception:
+            pass
+
+    def _run(self, mode, rho0, times, tau, op):
+        """<op> for one operator; non-Hermitian operators are evaluated as <Oh> + i <Oa> (the device
+        path returns the real part of the trace, see Hamiltonian._expect)."""
+        O = _dense(op)
+        Oh, Oa = 0.5 * (O + O.conj().T), -0.5j * (O - O.conj().T)
+        parts = [Oh] if np.max(np.abs(Oa)) <= 1e-15 * max(1.0, np.max(np.abs(O))) else [Oh, Oa]
+        h = self._get_handle()
+        h.set_rho0(rho0)
+        h.set_dissipators([a for a, _ in self._dops], [g for _, g in self._dops])
+        nt = len(times) if times is not None else 1
+        res = np.zeros(nt, dtype=complex)
+        for k, part in enumerate(parts):
+            M = np.zeros((3,) + O.shape, dtype=complex)
+            M[0] = part
+            h.update_observables(M)
             out = np.zeros((1, nt))
             h.run_host(mode, np.zeros((1, 3)), np.array([[1.0, 0.0, 0.0]]), np.array([np.inf]), np.array([1.0]),
                        np.array([0]), times, tau, out)
-            return out[0]
-        finally:
-            h.close()
+            res = res + (1j if k else 1.0) * out[0]
+        return res
 
     def evolve(self, rho0, times, operators=()):
         """lindbladian.py:43-111: expectation values [nt, n_ops]."""
@@ -63,6 +87,8 @@ class Lindbladian:
         r = _dense(rho0)
         if r.shape != self._H.matrix.shape:
             raise ValueError("Incompatible rho0 dimension")
+        if not np.all(np.isclose(r, r.conj().T, atol=Hamiltonian.herm_tol)):
+            raise ValueError("rho0 must be a Hermitian density matrix")
         if any(_dense(o).shape != r.shape for o in operators):
             raise ValueError("Incompatible measure operator dimension")
         if len(operators) == 0:

@@ -31,6 +31,16 @@ def test_version_and_argument_validation_without_gpu():
     h = ctypes.c_void_p()
     # invalid arguments are rejected before any CUDA call
     assert lib.musim_create(ctypes.byref(h), 0, 0, 0, None, None, 0, None, None, None, 0, None, None) == -1
+    # dissipation table: more entries than spins, or a count without arrays
+    dims = (ctypes.c_int * 1)(2)
+    gam = (ctypes.c_double * 1)(0.0)
+    mat = (ctypes.c_double * 8)()
+    m3 = (ctypes.c_double * 24)()
+    assert lib.musim_create(ctypes.byref(h), 0, 2, 1, dims, gam, 0, mat, m3, m3, 17, None, None) == -1
+    assert lib.musim_create(ctypes.byref(h), 0, 2, 1, dims, gam, 0, mat, m3, m3, 1, None, None) == -1
+    assert lib.musim_create(ctypes.byref(h), 0, 2, 1, dims, gam, 0, mat, m3, m3, -1, None, None) == -1
+    assert lib.musim_update_observables(None, None) == -1
+    assert lib.musim_device_count() >= 0
     assert lib.musim_run(None, 0, 0, None, None, None, None, None, 0, None, 1.0, 1, None, None) == -1
     assert lib.musim_eigh(0, 0, 0, None, None, None, 0, None) == -1
     assert lib.musim_destroy(None) == 0

@@ -121,3 +121,61 @@ def test_resident_handle_across_runners_with_different_couplings():
         assert np.max(np.abs(ExperimentRunner(s, device=0).run() - g)) < 1e-13
     assert np.max(np.abs(runners[0].run() - got[0])) < 1e-13  # first runner again after the others
     assert np.max(np.abs(got[0] - got[1])) > 1e-3
+
+
+def test_non_hermitian_operator_gives_the_complex_expectation_value():
+    """The reference's SpinOperator API allows non-Hermitian observables such as S+ (hamiltonian.py:
+    87-107 returns the complex trace); here they are evaluated as <Oh> + i <Oa>.  Checked against a
+    numpy evaluation of Tr(rho(t) O), also through the Lindbladian boundary; a non-Hermitian rho0
+    is rejected."""
+    from muspinsim_b200.hamiltonian import Hamiltonian
+    from muspinsim_b200.lindbladian import Lindbladian
+    from muspinsim_b200.spinsys import spin_operators
+
+    sx, sy, sz = spin_operators(0.5)
+    sp = sx + 1j * sy
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    Hm = 0.5 * (A + A.conj().T)
+    R = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    rho0 = R @ R.conj().T
+    rho0 /= np.trace(rho0).real
+    O = np.kron(sp, np.eye(2)) + 0.3 * np.kron(np.eye(2), sz)
+    t = np.linspace(0.0, 0.7, 23)
+    lam, U = np.linalg.eigh(Hm)
+    want = []
+    for tk in t:
+        E = U @ np.diag(np.exp(-2j * np.pi * lam * tk)) @ U.conj().T
+        want.append(np.trace(E @ rho0 @ E.conj().T @ O))
+    want = np.array(want)
+    H = Hamiltonian(Hm)
+    got = H.evolve(rho0, t, [O, O.conj().T])
+    assert got.shape == (23, 2)
+    assert np.max(np.abs(got[:, 0] - want)) < 1e-11 and np.max(np.abs(got[:, 1] - want.conj())) < 1e-11
+    assert np.max(np.abs(want.imag)) > 1e-3  # the case is not trivially real
+    gl = Lindbladian.from_hamiltonian(H).evolve(rho0, t, [O])
+    assert np.max(np.abs(gl[:, 0] - want)) < 1e-10
+    with pytest.raises(ValueError):
+        H.evolve(R, t, [O])  # rho0 is not Hermitian
+    assert len(H._handles) == 1  # one resident device handle served all operators
+
+
+def test_resident_configuration_table_in_a_fitting_style_loop():
+    """Runners that share a handle cache and a configuration table (a fit varies couplings only):
+    from the second run on, the expanded table is found on the device (no upload, no expansion
+    kernel), and the results equal the CPU oracle's for every coupling set."""
+    from muspinsim_b200 import ExperimentRunner, workloads
+    from oracle import muspin_oracle
+
+    cache = {}
+    hits = []
+    for scale in (1.0, 1.2, 0.8, 1.0):
+        spec = workloads.c2_hfine_powder(n_orient=11, nt=100, n_h=1)
+        for c in spec["couplings"]:
+            c["value"] = np.asarray(c["value"]) * scale
+        r = ExperimentRunner(spec, device=0, handle_cache=cache)
+        got = r.run()
+        assert np.max(np.abs(got - muspin_oracle.run_spec(spec))) < 1e-9
+        hits.append(r.handle.phase_ms("axes_resident_hits"))
+    assert len(cache) == 1
+    assert hits == [0.0, 1.0, 2.0, 3.0]

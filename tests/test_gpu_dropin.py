@@ -1,0 +1,140 @@
+"""The drop-in on hardware: the UNMODIFIED reference (oracle/_ref, travels to the GPU box) is
+driven through its own public API -- MuSpinInput -> ExperimentRunner.run() -> save_output(), and
+FittingRunner.run() -- once on its CPU path and once with `adapter.patch_reference()` routing
+`ExperimentRunner.run` (experiment.py:358-382) to the CUDA library.  The `.dat` files and the
+fitted parameters must agree.  Skipped where oracle/_ref is absent."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _need_ref():
+    from oracle import ref_driver
+
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref not present (reference install did not travel)")
+    ref_driver._import()  # puts oracle/_ref and the third-party shims on sys.path
+    return ref_driver
+
+
+def _dat_files(path):
+    out = {}
+    for f in sorted(os.listdir(path)):
+        if f.endswith(".dat"):
+            out[f] = np.loadtxt(os.path.join(path, f))
+    return out
+
+
+@pytest.mark.parametrize("name", ["hfine_powder_eulrange3", "alc_T_filerange", "c4_dissip_tf", "c2_fast_d16",
+                                  "time_averaged_vs_field"])
+def test_patched_reference_runner_writes_the_same_dat_files(name, tmp_path):
+    ref_driver = _need_ref()
+    from muspinsim_b200 import _lib, adapter
+
+    spec, want = load_golden(name)
+    cpu_dir, gpu_dir = tmp_path / "cpu", tmp_path / "gpu"
+    cpu_dir.mkdir()
+    gpu_dir.mkdir()
+    # reference, CPU path
+    r_cpu = ref_driver.make_runner(spec)
+    res_cpu = r_cpu.run()
+    r_cpu.config.save_output(name="out", path=str(cpu_dir))
+    # reference objects, CUDA path
+    created = []
+    orig_init = _lib.Handle.__init__
+
+    def counting_init(self, *a, **k):
+        created.append(1)
+        return orig_init(self, *a, **k)
+
+    _lib.Handle.__init__ = counting_init
+    adapter._HANDLES.clear()
+    adapter.patch_reference()
+    try:
+        r_gpu = ref_driver.make_runner(spec)
+        res_gpu = r_gpu.run()
+        r_gpu.config.save_output(name="out", path=str(gpu_dir))
+        h = next(iter(adapter._HANDLES.values()))
+        assert h.launches > 0  # the CUDA library did the work
+    finally:
+        adapter.unpatch_reference()
+        _lib.Handle.__init__ = orig_init
+    assert len(created) == 1
+    assert res_gpu.shape == res_cpu.shape == want.shape
+    assert np.max(np.abs(res_gpu - res_cpu)) < TOL
+    a, b = _dat_files(cpu_dir), _dat_files(gpu_dir)
+    assert list(a) == list(b) and len(a) >= 1
+    for f in a:
+        assert a[f].shape == b[f].shape
+        assert np.max(np.abs(a[f] - b[f])) < TOL, f
+
+
+def _fit_input(a_true, start, method):
+    """mu + e with an isotropic hyperfine coupling A (the variable), zero field; the 'experiment'
+    is the analytic zero-field signal of that system, 1/2 [1/2 + 1/2 cos(2 pi A t)]... evaluated by
+    the reference itself at A = a_true so that no formula of ours enters the target."""
+    ref_driver = _need_ref()
+    ms = ref_driver._import()
+    t = np.linspace(0.0, 0.12, 40)  # about one period: a single minimum between the bounds
+
+    def text(data_block, a_line, with_fit=True):
+        s = "spins\n    mu e\nhyperfine 1\n    {0} 0 0\n    0 {0} 0\n    0 0 {0}\n".format(a_line)
+        if with_fit:
+            s += "fitting_variables\n    A {0} 5.0 15.0\nfitting_method\n    {1}\nfitting_tolerance\n    1e-10\n".format(start, method)
+            s += "fitting_data\n" + data_block + "\n"
+        else:
+            s += "time\n" + "\n".join("    %.17g" % x for x in t) + "\n"
+        return s
+
+    target_runner = ms.ExperimentRunner(ms.MuSpinInput(io.StringIO(text("", "%.17g" % a_true, with_fit=False))), {})
+    y = target_runner.run()
+    block = "\n".join("    %.17g %.17g" % (a, b) for a, b in zip(t, y))
+    return ms, text(block, "A")
+
+
+@pytest.mark.parametrize("method", ["least-squares", "nelder-mead"])
+def test_fitting_runner_through_the_patched_path(method):
+    """fitting.py:67-151: FittingRunner builds a new ExperimentRunner per function evaluation; with
+    the patch every one of them runs on the SAME device handle (only H0 / Z are re-uploaded), and
+    the fit converges to the parameters of the reference's own CPU fit."""
+    from muspinsim_b200 import _lib, adapter
+
+    ms, text = _fit_input(10.0, 9.0, method)
+    sol_cpu = ms.FittingRunner(ms.MuSpinInput(io.StringIO(text))).run()
+
+    created, runs = [], []
+    orig_init, orig_axes, orig_host = _lib.Handle.__init__, _lib.Handle.run_axes_host, _lib.Handle.run_host
+
+    def counting_init(self, *a, **k):
+        created.append(1)
+        return orig_init(self, *a, **k)
+
+    def counting_axes(self, *a, **k):
+        runs.append(1)
+        return orig_axes(self, *a, **k)
+
+    def counting_host(self, *a, **k):
+        runs.append(1)
+        return orig_host(self, *a, **k)
+
+    _lib.Handle.__init__, _lib.Handle.run_axes_host, _lib.Handle.run_host = counting_init, counting_axes, counting_host
+    adapter._HANDLES.clear()
+    adapter.patch_reference()
+    try:
+        fr = ms.FittingRunner(ms.MuSpinInput(io.StringIO(text)))
+        sol_gpu = fr.run()
+    finally:
+        adapter.unpatch_reference()
+        _lib.Handle.__init__, _lib.Handle.run_axes_host, _lib.Handle.run_host = orig_init, orig_axes, orig_host
+    assert len(created) == 1, "one device handle for the whole fit"
+    assert len(runs) >= 3, "every function evaluation went through the CUDA library"
+    assert abs(sol_cpu.x[0] - 10.0) < 1e-4
+    assert abs(sol_gpu.x[0] - sol_cpu.x[0]) < 1e-6
+    assert np.max(np.abs(fr._runner.config.results - ms.FittingRunner(ms.MuSpinInput(io.StringIO(text)))._ytarg)) < 1e-6

@@ -232,3 +232,36 @@ def test_nufft_tables_reproduce_the_transform_on_the_host():
         F = np.fft.ifft(grid) * M
         got = F[(k - nt // 2) % M] * dec
         assert np.max(np.abs(got - want)) < 1e-11
+
+
+def test_time_as_x_axis_and_averaged_axis_matches_reference():
+    """x_axis = time with time ALSO in average_axes: the reference keeps t as the x range, sets
+    _time_isavg and stores the time average in every x column (simconfig.py:172-191, 364-365)."""
+    from oracle import ref_driver
+
+    spec = {"name": "t_avg_x", "spins": ["mu", "e"],
+            "couplings": [{"type": "hyperfine", "i": 1, "j": None, "value": [[5.0, 0, 0], [0, 5.0, 0], [0, 0, 5.0]]}],
+            "time": list(np.linspace(0.0, 1.0, 7)), "x_axis": "time", "average_axes": ["orientation", "time"],
+            "orientation": [[0.0, 0.0, 0.0, 1.0], [0.3, 0.4, 0.5, 1.0]]}
+    r = ExperimentRunner(spec)
+    r._handle = OracleHandle(spec)
+    got = r.run()
+    assert got.shape == (7,) and np.allclose(got, got[0])
+    if ref_driver.available():
+        want = ref_driver.run_reference(spec)
+        assert want.shape == got.shape and np.max(np.abs(got - want)) < 1e-12
+
+
+def test_run_host_validates_array_lengths_and_slots():
+    """_lib.Handle.run_host rejects ragged configuration arrays before the C call (no GPU needed:
+    the check runs on a handle-less instance)."""
+    h = _lib.Handle.__new__(_lib.Handle)
+    out = np.zeros((2, 3))
+    t = np.linspace(0, 1, 3)
+    B = np.zeros((4, 3))
+    with pytest.raises(ValueError):
+        _lib.Handle.run_host(h, 1, B, B, np.zeros(4), np.ones(3), np.zeros(4, int), t, 1.0, out)  # len(w) != n
+    with pytest.raises(ValueError):
+        _lib.Handle.run_host(h, 1, B, B, np.zeros(3), np.ones(4), np.zeros(4, int), t, 1.0, out)  # len(T) != n
+    with pytest.raises(ValueError):
+        _lib.Handle.run_host(h, 1, B, B, np.zeros(4), np.ones(4), np.array([0, 1, 2, 0]), t, 1.0, out)  # slot >= n_slots
