@@ -149,7 +149,9 @@ int64_t musim_launch_count(musim_handle *h);
  * during the last musim_run_host / musim_run with profiling enabled (option "profile" = 1).
  * The pseudo-phase "axes_resident_hits" returns a counter instead: how many musim_run_axes_host
  * calls found their configuration table already expanded on the device (resident-system
- * fitting, fitting.py:126-151). */
+ * fitting, fitting.py:126-151); "lind_gemm_cfgs" the number of (d^2 x d^2 complex GEMM,
+ * configuration) pairs the Lindbladian path has executed so far (matrix exponential by scaling
+ * and squaring: the count depends on the norm of the super-operator). */
 double musim_phase_ms(musim_handle *h, const char *phase);
 
 /* FP64 peak micro-benchmarks used as roofline denominators (MEASURED_PEAKS.json has no FP64

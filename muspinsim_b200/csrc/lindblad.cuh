@@ -533,6 +533,7 @@ struct LindWs {
   cplx *L = nullptr, *X = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *Ra = nullptr, *Rb = nullptr,
        *E1 = nullptr, *E0 = nullptr, *EBs = nullptr, *r0 = nullptr, *ov = nullptr, *gwork = nullptr;
   unsigned long long *norm = nullptr;
+  int64_t gemm_cfgs = 0;  // batched n x n complex GEMMs executed, counted per configuration (bench.py: executed-flop roofline)
   void release() {
     cplx **ps[] = {&L, &X, &X2, &X3, &X4, &Ra, &Rb, &E1, &E0, &EBs, &r0, &ov, &gwork};
     for (auto p : ps) {
@@ -621,6 +622,7 @@ inline cplx *lind_expm(LindWs &ws, int n, int64_t cnt, double scale, double norm
     other = cur;
     cur = out;
   }
+  ws.gemm_cfgs += (int64_t)(5 + s) * cnt;
   return dst;
 }
 
@@ -721,6 +723,7 @@ inline int lindblad_run(const LindCtx &ctx, bool integral, int64_t n_cfg, const 
       int flip = 0;
       for (int q = 1; q < NB; q <<= 1) {
         lind_gemm<0>(n, cnt, cur, cur, nullptr, pp[flip], st, launches);
+        ws.gemm_cfgs += cnt;
         cur = pp[flip];
         flip ^= 1;
       }

@@ -150,6 +150,7 @@ extern "C" int64_t musim_launch_count(musim_handle *h) { return h ? h->launches 
 extern "C" double musim_phase_ms(musim_handle *h, const char *phase) {
   if (!h || !phase) return -1.0;
   if (!strcmp(phase, "axes_resident_hits")) return (double)h->axes_hits;  // counter, not a time
+  if (!strcmp(phase, "lind_gemm_cfgs")) return (double)h->lws.gemm_cfgs;   // counter: Lindblad-path GEMMs x configurations
   h->prof.resolve();
   for (int i = 0; i < PH_COUNT; ++i)
     if (!strcmp(phase, kPhaseNames[i])) return h->prof.ms[i];

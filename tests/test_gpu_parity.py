@@ -219,3 +219,55 @@ def test_lindbladian_nonuniform_times_match_oracle():
     want = mo.run_spec(spec)
     got, _ = _run(spec)
     assert np.max(np.abs(got - want)) < TOL
+
+
+def _per_configuration_cpu(spec):
+    """[n_cfg, nt] signal of every configuration from the unmodified reference (oracle/_ref,
+    run_single of experiment.py:434-498) when it travelled to this box, else from the oracle port."""
+    from oracle import muspin_oracle as mo
+    from oracle import ref_driver
+
+    if ref_driver.available():
+        runner = ref_driver.make_runner(spec)
+        return "reference", np.array([np.atleast_1d(runner.run_single(snap)) for snap in runner.config[:]])
+    sys_ = mo.build_system(spec)
+    cfg = mo.OracleConfig(spec)
+    return "port", np.array([np.atleast_1d(mo.run_single(sys_, cfg, cfg.snapshot(i))) for i in range(len(cfg.configurations))])
+
+
+def _per_configuration_gpu(spec):
+    from muspinsim_b200 import ExperimentRunner
+    from muspinsim_b200.constants import MU_TAU
+
+    r = ExperimentRunner(spec, device=0)
+    tab = r.config
+    nt = 1 if tab.y == "integral" else len(tab.times)
+    out = np.zeros((tab.n_cfg, nt))
+    for mode, idx in r._modes(np.arange(tab.n_cfg)):
+        part = np.zeros((len(idx), nt))
+        r.handle.run_host(mode, tab.B[idx], tab.p[idx], tab.T[idx], tab.w[idx] * tab.avg_N, np.arange(len(idx)),
+                          None if tab.y == "integral" else tab.times, MU_TAU, part)
+        out[idx] = part
+    return out
+
+
+@pytest.mark.parametrize("case", ["c5_fast", "c5_general", "c2_fast", "c2_general", "c3_d24", "c4_lindblad"])
+def test_baseline_size_systems_per_configuration_against_the_reference(case):
+    """parity at the BASELINE systems and time grids (d = 96 / 32 / 24, nt = 1000,
+    Lindbladian d = 8), configuration by configuration -- not only the powder average -- on a
+    sample the CPU finishes in seconds."""
+    from muspinsim_b200 import workloads
+
+    spec = {
+        "c5_fast": lambda: workloads.c5_large(n_orient=48, nt=1000),
+        "c5_general": lambda: workloads.c5_large(n_orient=12, nt=1000, temperature=1.0),
+        "c2_fast": lambda: workloads.c2_hfine_powder(n_orient=64, nt=1000),
+        "c2_general": lambda: workloads.c2_hfine_powder(n_orient=24, nt=1000, temperature=1.0),
+        "c3_d24": lambda: workloads.c3_alc(n_orient=6, n_field=16),
+        "c4_lindblad": lambda: workloads.c4_fmuf_dissipation(n_orient=24, nt=1000),
+    }[case]()
+    kind, want = _per_configuration_cpu(spec)
+    got = _per_configuration_gpu(spec)
+    assert got.shape == want.shape
+    err = np.max(np.abs(got - want))
+    assert err < TOL, (case, kind, err)
