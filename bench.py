@@ -86,6 +86,7 @@ def kernel_flops(name, d, nt):
     return {
         "eigh_tridiag": (16.0 / 3) * d**3,  # zhetrd
         "eigh_tql": 30.0 * 1.2 * d * d,
+        "eigh_tdc": (8.0 / 3) * d**3,  # dstedc: leaves + two merge levels, eigenvector GEMMs (real)
         "eigh_apply": 6.0 * 1.2 * d**3,  # real Givens on d rows, ~1.2 d^2 rotations
         "eigh_back": (16.0 / 3) * d**3,  # zunmtr: reflectors applied to the real eigenvector matrix
         "eigh_jacobi": 16.0 * d**3,
@@ -99,7 +100,7 @@ def kernel_flops(name, d, nt):
 
 # phase -> kernel-name pattern, for the DRAM traffic read from the tracked ncu summary (profiles/*.json,
 # written by tools/ncu_full_summary.py from an `ncu --set full` capture of this same command)
-PHASE_KERNELS = {"eigh_tridiag": "hql_tridiag", "eigh_tql": "hql_tql|tdc_", "eigh_apply": "hql_apply", "eigh_back": "hql_backwy|hql_reflect",
+PHASE_KERNELS = {"eigh_tridiag": "hql_tridiag", "eigh_tql": "hql_tql", "eigh_tdc": "tdc_", "eigh_apply": "hql_apply", "eigh_back": "hql_backwy|hql_reflect|hql_tfactor",
                  "rotate": "zgemm_dmma", "polar": "polar_", "lindblad": "lind_|zgemm_dmma|cgemm_", "eigh_jacobi": "eigh_jacobi"}
 
 
@@ -324,7 +325,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     warm = max(args.warmup, 3)
-    PHASES = ("eigh_tridiag", "eigh_tql", "eigh_apply", "eigh_back", "eigh_jacobi", "rotate", "rho0", "polar",
+    PHASES = ("eigh_tridiag", "eigh_tdc", "eigh_tql", "eigh_apply", "eigh_back", "eigh_jacobi", "rotate", "rho0", "polar",
               "integral", "lindblad")
 
     def timed(fn, steps, warmup):

@@ -7,10 +7,10 @@
 //
 // so that every O(d^3) flop is a DMMA (mma.sync m8n8k4 f64).  The level-2 kernel it replaces
 // (hql_reflect_kernel: one reflector at a time, dot product + axpy per column) ran one dependency
-// chain per SM at 45 % of the FP64 pipe (profiles/r1_ncu_full_summary.md).
+// chain per SM at 45 % of the FP64 pipe (profiles/r1_ncu_full_summary.md): 12.6 ms at C5.
 //
-// Mapping.  One CTA per matrix, D / 8 warps; warp w owns columns 8w .. 8w+7 of C for ALL rows and
-// keeps them in registers as the accumulator fragments of C^T (tile t = rows 8t .. 8t+7):
+// Mapping.  A warp owns columns 8w .. 8w+7 of C for ALL rows and keeps them in registers as the
+// accumulator fragments of C^T (tile t = rows 8t .. 8t+7):
 //     accumulator (m = lane/4, n = 2 (lane%4) + e)   <->   C[row 8t + n][column 8w + m].
 // With C held transposed, all three products of a block are warp-local AND shuffle-free, because an
 // accumulator fragment read slot by slot IS an A-operand fragment whose reduction index is
@@ -18,16 +18,22 @@
 //   1. W^T  = C^T conj(V_b)      M = column, N = reflector, K = row        A = C^T accumulators
 //   2. W2^T = W^T T_b^T          M = column, N = reflector, K = reflector  A = W^T accumulators
 //   3. C^T -= W2^T V_b^T         M = column, N = row,       K = reflector  A = W2^T accumulators
-// Only the B operands come from shared memory.  V is staged ONCE per matrix as planar re / im
-// arrays Vs[reflector][row'] with leading dimension D + 4 (= 4 mod 16) and the rows of every group
-// of 8 stored in the order pos = (0, 6, 1, 7, 2, 4, 3, 5): with that permutation the fragment loads
-// of step 1 (rows 2j + e for j = lane%4) and of step 3 (rows lane/4, reflectors 4e + j) are both
-// bank-conflict free.  The output columns of step 2 are assigned to reflectors 4e + j for the same
-// reason (T is stored in the matching order).
+// Only the B operands come from shared memory.  V is staged once per CTA as planar re / im arrays,
+// block b as Vs_b[reflector 0..7][row' 0 .. D - 8b) with a leading dimension = 4 (mod 16) and the
+// rows of every group of 8 stored in the order pos = (0, 6, 1, 7, 2, 4, 3, 5): with that permutation
+// the fragment loads of step 1 (rows 2j + e for j = lane%4) and of step 3 (rows lane/4, reflectors
+// 4e + j) are both bank-conflict free.  The output columns of step 2 are assigned to reflectors
+// 4e + j for the same reason (T is stored in the matching order).
 //
-// T_b: warp b forms the Gram matrix G = V_b^H V_b with DMMAs (A and B fragment are the same loaded
-// value), then lane l < 8 runs row l of the zlarft recurrence
-//     T[l][l] = tau_l,   T[l][i] = -tau_i sum_{q=l}^{i-1} T[l][q] G[q][i]    (rows are independent).
+// Two CTAs per matrix (HALVES = 2: each takes half of the column tiles), two CTAs per SM: the first
+// version ran one 12-warp CTA per SM and ncu showed 17 % of the stall samples in the staging of V and
+// 12 % in the T factors with the DMMA pipe idle; with two independent CTAs on an SM one stages while
+// the other computes.  The T factors come from a separate, high-occupancy kernel:
+//
+// hql_tfactor_kernel: warp b forms the Gram matrix G = V_b^H V_b with DMMAs (A and B fragment are
+// the same loaded value), then lane l < 8 runs row l of the zlarft recurrence
+//     T[l][l] = tau_l,   T[l][i] = -tau_i sum_{q=l}^{i-1} T[l][q] G[q][i]    (rows are independent)
+// and writes T in the operand order of step 2.
 #pragma once
 #include "common.cuh"
 #include "polar.cuh"  // dmma884
@@ -36,105 +42,124 @@ namespace musim {
 
 template <int D>
 struct BackWyGeom {
-  static constexpr int NB = D / 8;    // reflector blocks = row tiles = warps
-  static constexpr int LD = D + 4;    // = 4 (mod 16) for D = 32, 64, 96
-  static constexpr int TLD = 12;      // leading dimension of the 8 x 8 T operand tiles
-  static constexpr size_t smem_bytes =
-      (size_t)2 * D * LD * sizeof(double) + (size_t)2 * NB * 8 * TLD * sizeof(double) + (size_t)NB * 64 * sizeof(cplx) +
-      (size_t)D * sizeof(cplx);
+  static constexpr int NB = D / 8;  // reflector blocks = row tiles = column tiles
+  static constexpr int TLD = 12;    // leading dimension of the 8 x 8 T operand tiles
+  static constexpr int TIMG = 2 * NB * 8 * TLD;  // doubles of the T image of one matrix (re plane, im plane)
+  __host__ __device__ static constexpr int ld(int b) { return ((D - 8 * b + 15) & ~15) + 4; }  // = 4 (mod 16)
+  __host__ __device__ static constexpr int voff(int b) {  // offset of block b in a plane (doubles)
+    int o = 0;
+    for (int q = 0; q < b; ++q) o += 8 * ld(q);
+    return o;
+  }
+  static constexpr int VPLANE = voff(NB);
+  static constexpr size_t smem_bytes = (size_t)(2 * VPLANE + TIMG) * sizeof(double);
 };
 
+// ---------------------------------------------------------------------------------------
+// T factors of all blocks of one matrix: one CTA (NB warps) per matrix.
+// ---------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(4 * D, 1)
-hql_backwy_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__ Vp, size_t vcap,
-                  const cplx *__restrict__ tau, cplx *__restrict__ U) {
+__global__ void __launch_bounds__(4 * D)
+hql_tfactor_kernel(int d, const cplx *__restrict__ Vp, size_t vcap, const cplx *__restrict__ tau,
+                   double *__restrict__ Timg) {
   using G = BackWyGeom<D>;
-  constexpr int NB = G::NB, LD = G::LD, TLD = G::TLD, NT = 4 * D;
-  static_assert(D % 32 == 0 && D <= 96, "D = 32, 64 or 96");
-  extern __shared__ __align__(16) unsigned char bw_smem[];
-  double *Vre = reinterpret_cast<double *>(bw_smem);  // [D][LD]
-  double *Vim = Vre + D * LD;
-  double *Tre = Vim + D * LD;                          // [NB][8][TLD]
-  double *Tim = Tre + NB * 8 * TLD;
-  cplx *Gs = reinterpret_cast<cplx *>(Tim + NB * 8 * TLD);  // [NB][64]
-  cplx *stau = Gs + NB * 64;                                // [D]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NB = G::NB, TLD = G::TLD;
+  __shared__ __align__(16) cplx Gs[NB][64];
+  const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
   const int fm = lane >> 2, fj = lane & 3;
   const size_t mat = blockIdx.x;
+  const int i = 8 * b + fm;  // this lane's reflector
+  const bool valid = i < d - 1;
+  const int mk = d - i - 2;
+  // v_i[r] for r > i + 1 sits at base[r]
+  const cplx *base = Vp + mat * vcap + (valid ? (size_t)mk * (mk - 1) / 2 : 0) - (i + 2);
+  double gr[2][2][2] = {}, gi[2][2][2] = {}, hr[2][2][2] = {}, hi[2][2][2] = {};  // [t parity][e][slot]: short dependent chains
+#define TF_TILE(T_, TP_)                                                     \
+  _Pragma("unroll") for (int e = 0; e < 2; ++e) {                            \
+    const int r = 8 * (T_) + 4 * e + fj;                                     \
+    cplx v = make_c(0.0, 0.0);                                               \
+    if (valid && r < d) {                                                    \
+      if (r > i + 1)                                                         \
+        v = base[r];                                                         \
+      else if (r == i + 1)                                                   \
+        v = make_c(1.0, 0.0);                                                \
+    }                                                                        \
+    dmma884(gr[TP_][e][0], gr[TP_][e][1], v.x, v.x);                         \
+    dmma884(hr[TP_][e][0], hr[TP_][e][1], v.y, v.y);                         \
+    dmma884(gi[TP_][e][0], gi[TP_][e][1], v.x, v.y);                         \
+    dmma884(hi[TP_][e][0], hi[TP_][e][1], -v.y, v.x);                        \
+  }
+  for (int t = b; t < NB; t += 2) {
+    TF_TILE(t, 0)
+    if (t + 1 < NB) {
+      TF_TILE(t + 1, 1)
+    }
+  }
+#undef TF_TILE
+  cplx *gs = Gs[b];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const double re = (gr[0][0][s] + gr[0][1][s]) + (gr[1][0][s] + gr[1][1][s]) + (hr[0][0][s] + hr[0][1][s]) + (hr[1][0][s] + hr[1][1][s]);
+    const double im = (gi[0][0][s] + gi[0][1][s]) + (gi[1][0][s] + gi[1][1][s]) + (hi[0][0][s] + hi[0][1][s]) + (hi[1][0][s] + hi[1][1][s]);
+    gs[fm * 8 + 2 * fj + s] = make_c(re, im);
+  }
+  __syncwarp();
+  double *Tre = Timg + mat * G::TIMG, *Tim = Tre + NB * 8 * TLD;
+  if (lane < 8) {
+    const int l = lane;
+    cplx T[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const cplx tc = (8 * b + c < d - 1) ? tau[mat * d + 8 * b + c] : make_c(0.0, 0.0);
+      cplx acc = make_c(0.0, 0.0);
+#pragma unroll
+      for (int q = 0; q < c; ++q)
+        if (q >= l) cfma(acc, T[q], gs[q * 8 + c]);
+      const cplx off = cmul(make_c(-tc.x, -tc.y), acc);
+      T[c] = (c == l) ? tc : ((c > l) ? off : make_c(0.0, 0.0));
+    }
+    // operand order of step 2: B[k = (j, e) <-> reflector 2j + e][n = u' <-> reflector 4 (u' % 2) + u' / 2] = T[refl(u')][2j + e]
+    const int up = 2 * (l & 3) + (l >> 2);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      Tre[(b * 8 + 4 * (c & 1) + (c >> 1)) * TLD + up] = T[c].x;
+      Tim[(b * 8 + 4 * (c & 1) + (c >> 1)) * TLD + up] = T[c].y;
+    }
+  } else if (lane < 12) {  // the padding columns of the image (never read by a fragment load, copied by the consumer)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      Tre[(b * 8 + c) * TLD + lane] = 0.0;
+      Tim[(b * 8 + c) * TLD + lane] = 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// The back-transformation proper.  HALVES CTAs per matrix, NB / HALVES warps each.
+// ---------------------------------------------------------------------------------------
+template <int D, int HALVES>
+__global__ void __launch_bounds__(4 * D / HALVES, HALVES)
+hql_backwy_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__ Vp, size_t vcap,
+                  const double *__restrict__ Timg, cplx *__restrict__ U) {
+  using G = BackWyGeom<D>;
+  constexpr int NB = G::NB, TLD = G::TLD, NT = 4 * D / HALVES, NW = NB / HALVES;
+  static_assert(D % 32 == 0 && D <= 96 && NB % HALVES == 0, "D = 32, 64 or 96");
+  extern __shared__ __align__(16) unsigned char bw_smem[];
+  double *Vre = reinterpret_cast<double *>(bw_smem);  // blocks b = 0 .. NB-1, [8][ld(b)] each
+  double *Vim = Vre + G::VPLANE;
+  double *Tre = Vim + G::VPLANE;                       // [NB][8][TLD]
+  double *Tim = Tre + NB * 8 * TLD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fm = lane >> 2, fj = lane & 3;
+  const size_t mat = blockIdx.x / HALVES;
+  const int ctile = (blockIdx.x % HALVES) * NW + warp;  // this warp's column tile
   const size_t dd = (size_t)d * d;
   const cplx *myv = Vp + mat * vcap;
 
-  // ---- stage V (unit diagonal and zeros made explicit) and tau ----
-  for (int i = tid; i < D; i += NT) stau[i] = (i < d - 1) ? tau[mat * d + i] : make_c(0.0, 0.0);
-  for (int idx = tid; idx < D * D; idx += NT) {
-    const int i = idx / D, r = idx - i * D;  // reflector i, row r
-    cplx v = make_c(0.0, 0.0);
-    if (i < d - 1 && r < d) {
-      if (r > i + 1) {
-        const int mk = d - i - 2;
-        v = myv[(size_t)mk * (mk - 1) / 2 + (r - i - 2)];
-      } else if (r == i + 1) {
-        v = make_c(1.0, 0.0);
-      }
-    }
-    const int p = (0x53427160u >> (4 * (r & 7))) & 7;
-    Vre[i * LD + (r & ~7) + p] = v.x;
-    Vim[i * LD + (r & ~7) + p] = v.y;
-  }
-  __syncthreads();
-
-  // ---- T_b (warp b) ----
-  {
-    const int b = warp;
-    double gr[2] = {0.0, 0.0}, gi[2] = {0.0, 0.0}, gr2[2] = {0.0, 0.0}, gi2[2] = {0.0, 0.0};
-    const double *vrb = Vre + (8 * b + fm) * LD, *vib = Vim + (8 * b + fm) * LD;
-    for (int t = b; t < NB; ++t) {
-      {
-        const double vr = vrb[8 * t + fj], vi = vib[8 * t + fj];
-        dmma884(gr[0], gr[1], vr, vr);
-        dmma884(gi[0], gi[1], vr, vi);
-        dmma884(gr[0], gr[1], vi, vi);
-        dmma884(gi[0], gi[1], -vi, vr);
-      }
-      {
-        const double vr = vrb[8 * t + 4 + (fj ^ 2)], vi = vib[8 * t + 4 + (fj ^ 2)];
-        dmma884(gr2[0], gr2[1], vr, vr);
-        dmma884(gi2[0], gi2[1], vr, vi);
-        dmma884(gr2[0], gr2[1], vi, vi);
-        dmma884(gi2[0], gi2[1], -vi, vr);
-      }
-    }
-    cplx *gs = Gs + b * 64;
-    gs[fm * 8 + 2 * fj] = make_c(gr[0] + gr2[0], gi[0] + gi2[0]);
-    gs[fm * 8 + 2 * fj + 1] = make_c(gr[1] + gr2[1], gi[1] + gi2[1]);
-    __syncwarp();
-    if (lane < 8) {
-      const int l = lane;
-      cplx T[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const cplx ti = stau[8 * b + i];
-        cplx acc = make_c(0.0, 0.0);
-#pragma unroll
-        for (int q = 0; q < i; ++q)
-          if (q >= l) cfma(acc, T[q], gs[q * 8 + i]);
-        const cplx off = cmul(make_c(-ti.x, -ti.y), acc);
-        T[i] = (i == l) ? ti : ((i > l) ? off : make_c(0.0, 0.0));
-      }
-      // operand order of step 2: B[k = (j, e) <-> reflector 2j + e][n = u' <-> reflector 4 (u' % 2) + u' / 2] = T[refl(u')][2j + e]
-      const int up = 2 * (l & 3) + (l >> 2);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        Tre[(b * 8 + 4 * (c & 1) + (c >> 1)) * TLD + up] = T[c].x;
-        Tim[(b * 8 + 4 * (c & 1) + (c >> 1)) * TLD + up] = T[c].y;
-      }
-    }
-  }
-
-  // ---- C^T tiles of this warp's 8 columns ----
+  // ---- C^T tiles of this warp's 8 columns (loads in flight while V is staged) ----
   double cr[NB][2], ci[NB][2];
   {
-    const int n = 8 * warp + fm;
+    const int n = 8 * ctile + fm;
 #pragma unroll
     for (int t = 0; t < NB; ++t)
 #pragma unroll
@@ -144,15 +169,58 @@ hql_backwy_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__
         ci[t][e] = 0.0;
       }
   }
+  // ---- stage V (unit diagonal and zeros made explicit) and the T image ----
+  {
+    const double *tg = Timg + mat * G::TIMG;
+    for (int q = tid; q < G::TIMG / 2; q += NT) reinterpret_cast<double2 *>(Tre)[q] = reinterpret_cast<const double2 *>(tg)[q];
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int wb = D - 8 * b;          // rows 8b .. D-1
+    const int cnt = 8 * wb;            // elements of the block
+    const int ldb = G::ld(b), ob = G::voff(b);
+    constexpr int MAXB = (8 * D + NT - 1) / NT;
+    cplx v[MAXB];
+    int dst[MAXB];
+#pragma unroll
+    for (int u = 0; u < MAXB; ++u) {
+      const int idx = tid + u * NT;
+      dst[u] = -1;
+      v[u] = make_c(0.0, 0.0);
+      if (idx < cnt) {
+        const int il = idx / wb, c = idx - il * wb;  // reflector 8b + il, row 8b + c
+        const int i = 8 * b + il, r = 8 * b + c;
+        if (i < d - 1 && r < d) {
+          if (r > i + 1) {
+            const int mk = d - i - 2;
+            v[u] = myv[(size_t)mk * (mk - 1) / 2 + (r - i - 2)];
+          } else if (r == i + 1) {
+            v[u] = make_c(1.0, 0.0);
+          }
+        }
+        dst[u] = ob + il * ldb + (c & ~7) + (int)((0x53427160u >> (4 * (c & 7))) & 7);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXB; ++u)
+      if (dst[u] >= 0) {
+        Vre[dst[u]] = v[u].x;
+        Vim[dst[u]] = v[u].y;
+      }
+  }
   __syncthreads();
 
   const int p3 = (0x53427160u >> (4 * fm)) & 7;  // row position of step 3's N index
 #pragma unroll 1
   for (int b = NB - 1; b >= 0; --b) {
-    // 1. W^T = C^T conj(V_b): two accumulator sets (even / odd tiles) halve the dependent DMMA chain
+    const int ldb = G::ld(b);
+    const double *vr0 = Vre + G::voff(b), *vi0 = Vim + G::voff(b);
+    // 1. W^T = C^T conj(V_b): two accumulator sets (the two slots) halve the dependent DMMA chain
     double wr[2] = {0.0, 0.0}, wi[2] = {0.0, 0.0}, xr[2] = {0.0, 0.0}, xi[2] = {0.0, 0.0};
     {
-      const double *vrb = Vre + (8 * b + fm) * LD, *vib = Vim + (8 * b + fm) * LD;
+      const double *vrb = vr0 + fm * ldb - 8 * b, *vib = vi0 + fm * ldb - 8 * b;
 #pragma unroll
       for (int t = 0; t < NB; ++t) {
         if (t >= b) {
@@ -190,7 +258,7 @@ hql_backwy_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__
       if (t >= b) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const double vr = Vre[(8 * b + 4 * e + fj) * LD + 8 * t + p3], vi = Vim[(8 * b + 4 * e + fj) * LD + 8 * t + p3];
+          const double vr = vr0[(4 * e + fj) * ldb + 8 * (t - b) + p3], vi = vi0[(4 * e + fj) * ldb + 8 * (t - b) + p3];
           dmma884(cr[t][0], cr[t][1], nyr[e], vr);
           dmma884(ci[t][0], ci[t][1], nyr[e], vi);
           dmma884(cr[t][0], cr[t][1], yi[e], vi);
@@ -201,7 +269,7 @@ hql_backwy_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__
   }
 
   {
-    const int n = 8 * warp + fm;
+    const int n = 8 * ctile + fm;
 #pragma unroll
     for (int t = 0; t < NB; ++t)
 #pragma unroll

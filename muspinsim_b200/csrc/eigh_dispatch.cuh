@@ -4,7 +4,9 @@
 #include "eigh_jacobi.cuh"
 #include "eigh_backwy.cuh"
 #include "eigh_large.cuh"
+#include "eigh_tdc.cuh"
 #include "eigh_tridiag_rw.cuh"
+#include "eigh_tridiag_rw1.cuh"
 #include "eigh_tridiag_warp.cuh"
 #include "profiler.cuh"
 #include "rotate.cuh"
@@ -18,6 +20,7 @@ enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 // measured-fastest variants; the others stay as independent cross-checks covered by the parity tests.
 struct EighOpts {
   bool reflect = true;         // "reflect": K4 applies the reflectors to Zt (d <= 96); 0: Q formed in K1 + GEMM
+  bool tdc = true;             // "tdc": tridiagonal divide and conquer (32 < d <= 96) instead of QL + rotation replay
   bool back_wy = true;         // "back_wy": K4 in compact-WY blocks on the FP64 tensor pipe (32 < d <= 96); 0: level-2 reflector kernel
   bool tridiag_warp = true;    // "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
   bool small24 = true;         // "small24": D = 16 / 24 instantiations of the replay / reflector kernels for d <= 16 / 24 (else D = 32)
@@ -25,6 +28,7 @@ struct EighOpts {
   bool tridiag_phases = true;  // "tridiag_phases": K1 in up to three launches of decreasing size
   bool apply_warp = true;      // "apply_warp": rotation replay with one warp per CTA (d > 32)
   int tql_threads = 0;         // "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
+  bool tridiag_one = true;     // "tridiag_one": one-barrier-per-step register tridiagonalisation (eigh_tridiag_rw1.cuh); 0: two-barrier kernel
   bool tridiag_rw = true;      // "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96); 0: shared-memory kernel
   bool use_reflect(int d) const { return reflect && d >= 3 && d <= 96; }
 };
@@ -44,6 +48,8 @@ struct EighWs {
   cplx *Q[2] = {nullptr, nullptr};  // [2]: stage A (tridiagonalisation) of the next launch group overlaps stage B
   bool dbl = false;
   cplx *Vp[2] = {nullptr, nullptr}, *tauv[2] = {nullptr, nullptr};  // packed reflectors + tau (d <= 96 path)
+  double *tdc_rec = nullptr;  // leaf results of the tridiagonal divide and conquer (eigh_tdc.cuh), 32 < d <= 96
+  double *Timg = nullptr;  // compact-WY T factors in operand order (eigh_backwy.cuh), 32 < d <= 96
   size_t vcap = 0;
   double2 *rot = nullptr;
   SweepIdx *swp = nullptr;
@@ -77,6 +83,10 @@ struct EighWs {
       Vp[i] = tauv[i] = nullptr;
     }
     cudaFree(Zt);
+    cudaFree(Timg);
+    Timg = nullptr;
+    cudaFree(tdc_rec);
+    tdc_rec = nullptr;
     cudaFree(Awork);
     Awork = nullptr;
     cudaFree(rot);
@@ -114,6 +124,8 @@ struct EighWs {
         EW_ALLOC(tauv[i], (size_t)n * d);
       }
       EW_ALLOC(Zt, (size_t)n * dd);
+      if (d > 32 && d <= 96) EW_ALLOC(Timg, (size_t)n * BackWyGeom<96>::TIMG);
+      if (d > 32 && d <= 96) EW_ALLOC(tdc_rec, (size_t)n * TdcGeom<96>::LEAF_REC);
       if (d > HQL_MAX_D) EW_ALLOC(Awork, (size_t)n * d * (d | 1));
       EW_ALLOC(rot, (size_t)n * rot_cap);
       EW_ALLOC(swp, (size_t)n * swp_cap);
@@ -173,25 +185,48 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
       cplx *vp_ = ws.Vp[buf], *tt_ = ws.tauv[buf];
       // phase buffers for the trailing blocks (Q is not used on the reflector path)
       cplx *A64 = ws.Q[buf], *A32 = ws.Q[buf] + (size_t)n * 64 * 64;
+      if (o.tridiag_one) {
       const unsigned g = (unsigned)n;
-      if (d <= 32) {
-        hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-      } else if (!o.tridiag_phases) {
-        if (d <= 64)
-          hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-        else
-          hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-      } else if (d <= 64) {
-        const int k1 = d - 32;
-        hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A32);
-        hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(32, d, k1, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-        ++*launches;
+        if (d <= 32) {
+          hql_tridiag_rw1_kernel<32><<<g, 128, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        } else if (!o.tridiag_phases) {
+          if (d <= 64)
+            hql_tridiag_rw1_kernel<64><<<g, 256, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+          else
+            hql_tridiag_rw1_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        } else if (d <= 64) {
+          const int k1 = d - 32;
+          hql_tridiag_rw1_kernel<64><<<g, 256, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A32);
+          hql_tridiag_rw1_kernel<32><<<g, 128, 0, st>>>(32, d, k1, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+          ++*launches;
+        } else {
+          const int k1 = d - 64;
+          hql_tridiag_rw1_kernel<96><<<g, 384, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A64);
+          hql_tridiag_rw1_kernel<64><<<g, 256, 0, st>>>(64, d, k1, 32, nullptr, nullptr, nullptr, A64, dd_, ee_, vp_, ws.vcap, tt_, A32);
+          hql_tridiag_rw1_kernel<32><<<g, 128, 0, st>>>(32, d, k1 + 32, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+          *launches += 2;
+        }
       } else {
-        const int k1 = d - 64;
-        hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A64);
-        hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(64, d, k1, 32, nullptr, nullptr, nullptr, A64, dd_, ee_, vp_, ws.vcap, tt_, A32);
-        hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(32, d, k1 + 32, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-        *launches += 2;
+      const unsigned g = (unsigned)n;
+        if (d <= 32) {
+          hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        } else if (!o.tridiag_phases) {
+          if (d <= 64)
+            hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+          else
+            hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        } else if (d <= 64) {
+          const int k1 = d - 32;
+          hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A32);
+          hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(32, d, k1, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+          ++*launches;
+        } else {
+          const int k1 = d - 64;
+          hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A64);
+          hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(64, d, k1, 32, nullptr, nullptr, nullptr, A64, dd_, ee_, vp_, ws.vcap, tt_, A32);
+          hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(32, d, k1 + 32, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+          *launches += 2;
+        }
       }
     } else if (Ain) {
       e = cudaFuncSetAttribute(hql_tridiag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -237,7 +272,23 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
                               cudaStream_t st, int64_t *launches, Profiler *prof, bool sorted, const EighOpts &o) {
   if (method != EIGH_HQL) return 0;
   cudaError_t e;
-  {
+  const bool use_tdc = o.tdc && o.use_reflect(d) && d > 32 && d <= 96;
+  if (use_tdc) {
+    ProfScope ps(prof, st, PH_EIGH_TDC);
+    if (d <= 64) {
+      const size_t sm = TdcGeom<64>::smem_bytes;
+      cudaFuncSetAttribute(tdc_merge_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      tdc_leaf_kernel<64><<<(unsigned)n, 128, 0, st>>>(d, ws.dbuf[buf], ws.ebuf[buf], ws.tdc_rec, status);
+      tdc_merge_kernel<64><<<(unsigned)n, TdcGeom<64>::NT, sm, st>>>(d, ws.tdc_rec, lam, ws.Zt);
+    } else {
+      const size_t sm = TdcGeom<96>::smem_bytes;
+      cudaFuncSetAttribute(tdc_merge_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      tdc_leaf_kernel<96><<<(unsigned)n, 128, 0, st>>>(d, ws.dbuf[buf], ws.ebuf[buf], ws.tdc_rec, status);
+      tdc_merge_kernel<96><<<(unsigned)n, TdcGeom<96>::NT, sm, st>>>(d, ws.tdc_rec, lam, ws.Zt);
+    }
+    *launches += 2;
+  }
+  if (!use_tdc) {
     ProfScope ps(prof, st, PH_EIGH_TQL);
     int nt = o.tql_threads ? o.tql_threads : (d <= 32 ? 32 : 16);  // measured: C3 (d = 24) 12.0 -> 10.2 ms per 10^6 with 32
     while (nt > 8 && hql_tql_smem(d, nt) > 200 * 1024) nt >>= 1;  // (d, e) of nt matrices per CTA in shared memory
@@ -256,14 +307,16 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     if (nt == 8) TQL_LAUNCH(8) else if (nt == 16) TQL_LAUNCH(16) else TQL_LAUNCH(32)
 #undef TQL_LAUNCH
   }
-  ++*launches;
+  if (!use_tdc) ++*launches;
   const size_t zsmem = hql_apply_smem(d, ws.swp_cap);
-  if (d <= HQL_MAX_D) {
+  if (!use_tdc && d <= HQL_MAX_D) {
     e = cudaFuncSetAttribute(hql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem);
     if (e != cudaSuccess) return (int)e;
   }
   const int ath = std::min(128, (d + 31) & ~31);
-  if (!sorted && d <= 96) {
+  if (use_tdc) {
+    // eigenvectors of T already in ws.Zt
+  } else if (!sorted && d <= 96) {
     // register-resident rows (static column indices): D = d rounded up to 32 / 64 / 96
     const int D = d <= 16 && o.small24 ? 16 : (d <= 24 && o.small24 ? 24 : (d <= 32 ? 32 : (d <= 64 ? 64 : 96)));
     const int nth = D < 32 ? D : (o.apply_warp ? 32 : D);  // option "apply_warp": one warp (32 rows of Z) per CTA
@@ -295,19 +348,22 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
     ProfScope ps(prof, st, PH_EIGH_APPLY);
     hql_apply_kernel<<<(unsigned)n, ath, zsmem, st>>>(d, ws.rot, ws.rot_cap, ws.swp, ws.swp_cap, ws.nswp, ws.perm, ws.Zt);
   }
-  ++*launches;
+  if (!use_tdc) ++*launches;
   {
     ProfScope ps(prof, st, PH_EIGH_BACK);
     if (o.use_reflect(d) && o.back_wy && d > 32) {
       if (d <= 64) {
         const size_t sm = BackWyGeom<64>::smem_bytes;
-        cudaFuncSetAttribute(hql_backwy_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_backwy_kernel<64><<<(unsigned)n, 256, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        cudaFuncSetAttribute(hql_backwy_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_tfactor_kernel<64><<<(unsigned)n, 256, 0, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
+        hql_backwy_kernel<64, 2><<<(unsigned)(2 * n), 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.Timg, U);
       } else {
         const size_t sm = BackWyGeom<96>::smem_bytes;
-        cudaFuncSetAttribute(hql_backwy_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_backwy_kernel<96><<<(unsigned)n, 384, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.tauv[buf], U);
+        cudaFuncSetAttribute(hql_backwy_kernel<96, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_tfactor_kernel<96><<<(unsigned)n, 384, 0, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
+        hql_backwy_kernel<96, 2><<<(unsigned)(2 * n), 192, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.Timg, U);
       }
+      ++*launches;
     } else if (o.use_reflect(d)) {
       if (d <= 32) {
         const size_t sm = hql_reflect_smem(32);

@@ -1,0 +1,457 @@
+// eigh_tdc.cuh -- K2 + K3 replaced: eigenvalues AND eigenvectors of the tridiagonal matrix by
+// divide and conquer (LAPACK dstedc inside np.linalg.eigh, /root/reference/muspinsim/spinop.py:69),
+// 32 < d <= 96.
+//
+// What it replaces and why.  The QL pipeline ran (i) one THREAD per matrix through a serial chain
+// of ~1.2 d^2 plane rotations (hql_tql_kernel, 3.35 ms at C5 no matter how few matrices a GPU
+// holds: the chain, not the batch, sets the time -- it is what limits strong scaling at 2 500
+// matrices per GPU) and (ii) replayed the recorded rotations on d rows (hql_apply_reg_kernel,
+// 8.8 ms, ~7 d^3 vector flops, 9 GB of rotation-stream traffic).  Here the matrix is torn into four
+// leaves of <= 24 rows:
+//   tdc_leaf_kernel   one WARP per leaf (4 per matrix, ~10 small CTAs per SM): every lane repeats
+//                     the scalar QL chain (16 x shorter than the full one), lane r updates row r of
+//                     the leaf's eigenvectors in shared memory -- no rotation ever leaves the SM;
+//   tdc_merge_kernel  one CTA per matrix, two merge levels; all merges of a level run concurrently.
+//                     Secular roots, Gu/Eisenstat z and the column norms use FOUR adjacent lanes per
+//                     root (each sums a quarter of the poles; quad shuffles), the eigenvector update
+//                     Q <- Q [V 0; 0 I] is a DMMA GEMM whose B fragments (zhat_i / (d_i - lambda_j))
+//                     are formed on the fly.
+// The first version was ONE kernel with one thread per root and ran 31 ms at C5 (ncu: 49 % of the
+// CTA lifetime in the leaf phase with 8 of 12 warps parked at the barrier, 38 % in the secular phase
+// at one dependent instruction per 9 cycles); hence the split and the quads.
+//
+// Numerics are in tdc_core.cuh (shared with the host build that tests/test_tdc_host.py checks against
+// LAPACK); this file is the parallel orchestration.  Shared memory of the merge kernel: the
+// eigenvector matrix is kept TRANSPOSED, QsT[column][row] with leading dimension D + 4 (= 4 mod 16):
+// the GEMM's A fragments (row = lane/4, k = lane%4 -> 4 columns) are bank-conflict free for
+// consecutive columns.  Thread t < d owns global index t (an entry of z, a sorted position) of the
+// merge that contains t; quad g = tid / 4 owns root g; warp w owns output columns 8w .. 8w+7.
+// Output: eigenvalues in ASCENDING order, Zt row-major with eigenvectors in columns.
+#pragma once
+#include "common.cuh"
+#include "polar.cuh"  // dmma884
+#include "tdc_core.cuh"
+
+namespace musim {
+
+#define TDC_LEAF_MAX 24  // rows of a leaf (d <= 96 in four leaves cut at multiples of 8)
+
+template <int D>
+struct TdcGeom {
+  static constexpr int LD = D + 4;
+  static constexpr int NT = 4 * D;  // D / 8 warps
+  static constexpr size_t smem_bytes =
+      (size_t)D * LD * sizeof(double)      // QsT
+      + 13 * (size_t)D * sizeof(double)    // Dv zv sD sZ nd zk wgt mu dorg zh sn lamn fin
+      + 4 * (size_t)D * sizeof(int)        // sidx ncol orgi dest
+      + (size_t)D * sizeof(tdc::RotRec)    // rots
+      + (size_t)D                          // flag
+      + 64 * sizeof(double);               // per-merge scalars
+  // leaf kernel output per matrix: header (orgnrm, beta[1..3]) + D scaled leaf eigenvalues + 4 leaf blocks
+  static constexpr int LEAF_HDR = 8;
+  static constexpr int LEAF_REC = LEAF_HDR + D + 4 * TDC_LEAF_MAX * TDC_LEAF_MAX;  // doubles
+};
+
+struct TdcRows {  // one lane = one row of the leaf's eigenvector block (tdc::leaf_ql)
+  double *base;   // element (row, column j) at base[j * ld]
+  int ld;
+  bool active;
+  double f, cur, nxt;
+  __device__ __forceinline__ void begin(int m) {
+    if (active) {
+      f = base[m * ld];
+      cur = base[(m - 1) * ld];
+    }
+  }
+  __device__ __forceinline__ void load(int j) {
+    if (active) nxt = base[j * ld];
+  }
+  __device__ __forceinline__ void rot(int j, double cx, double cy) {
+    if (active) {
+      const double a = cur;
+      base[(j + 1) * ld] = cx * f - cy * a;
+      f = fma(cy, f, cx * a);
+      cur = nxt;
+    }
+  }
+  __device__ __forceinline__ void end(int l) {
+    if (active) base[l * ld] = f;
+  }
+};
+
+struct QuadGroup {  // four adjacent lanes share one root (tdc_core.cuh)
+  static constexpr int P = 4;
+  int p;
+  unsigned mask;
+  __device__ __forceinline__ int part() const { return p; }
+  __device__ __forceinline__ double sum(double v) const {
+    v += __shfl_xor_sync(mask, v, 1);
+    v += __shfl_xor_sync(mask, v, 2);
+    return v;
+  }
+  __device__ __forceinline__ double prod(double v) const {
+    v *= __shfl_xor_sync(mask, v, 1);
+    v *= __shfl_xor_sync(mask, v, 2);
+    return v;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Leaves.  One CTA (4 warps) per matrix: scale to unit max-norm (dstedc), tear, QL per leaf.
+// ---------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+tdc_leaf_kernel(int d, const double *__restrict__ din, const double *__restrict__ ein, double *__restrict__ rec,
+                int *__restrict__ status) {
+  using G = TdcGeom<D>;
+  constexpr int LM = TDC_LEAF_MAX;
+  __shared__ double Dv[D], E[D], Zl[4][LM * LM];  // leaf block q: element (row r, column j) at Zl[q][j * LM + r]
+  __shared__ double s_scale;
+  __shared__ int bnd[5];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t mat = blockIdx.x;
+  double *out = rec + mat * G::LEAF_REC;
+  for (int i = tid; i < D; i += 128) {
+    Dv[i] = i < d ? din[mat * d + i] : 0.0;
+    E[i] = i < d - 1 ? ein[mat * d + i] : 0.0;
+  }
+  for (int i = tid; i < 4 * LM * LM; i += 128) (&Zl[0][0])[i] = 0.0;
+  if (tid == 0) tdc::leaf_bounds(d, bnd);
+  __syncthreads();
+  if (warp == 0) {
+    double mx = 0.0;
+    for (int i = lane; i < d; i += 32) mx = fmax(mx, fmax(fabs(Dv[i]), fabs(E[i])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_scale = mx;
+  }
+  __syncthreads();
+  const double orgnrm = s_scale;
+  {
+    const double scl = orgnrm > 0.0 ? 1.0 / orgnrm : 1.0;
+    for (int i = tid; i < D; i += 128) {
+      Dv[i] *= scl;
+      E[i] *= scl;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    out[0] = orgnrm;
+    for (int q = 1; q <= 3; ++q) {
+      const int m = bnd[q];
+      double beta = 0.0;
+      if (m > 0 && m < d && bnd[q] > bnd[q - 1]) {
+        beta = E[m - 1];
+        Dv[m - 1] -= fabs(beta);
+        Dv[m] -= fabs(beta);
+        E[m - 1] = 0.0;
+      }
+      out[q] = beta;
+    }
+  }
+  __syncthreads();
+  {
+    const int o = bnd[warp], n = bnd[warp + 1] - bnd[warp];
+    if (n > 0) {
+      if (lane < n) Zl[warp][lane * LM + lane] = 1.0;
+      __syncwarp();
+      TdcRows rows;
+      rows.base = &Zl[warp][lane];
+      rows.ld = LM;
+      rows.active = lane < n;
+      rows.f = rows.cur = rows.nxt = 0.0;
+      const bool ok = tdc::leaf_ql(n, Dv + o, E + o, rows);
+      if (!ok && lane == 0) atomicMax(status, 1);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += 128) out[G::LEAF_HDR + i] = Dv[i];
+  for (int i = tid; i < 4 * LM * LM; i += 128) out[G::LEAF_HDR + D + i] = (&Zl[0][0])[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Merges.
+// ---------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(4 * D, 2)
+tdc_merge_kernel(int d, const double *__restrict__ rec, double *__restrict__ lam, double *__restrict__ Zt) {
+  using G = TdcGeom<D>;
+  constexpr int LD = G::LD, NT = G::NT, NB = D / 8, LM = TDC_LEAF_MAX;
+  extern __shared__ __align__(16) unsigned char tdc_smem[];
+  double *QsT = reinterpret_cast<double *>(tdc_smem);
+  double *Dv = QsT + D * LD, *zv = Dv + D, *sD = zv + D, *sZ = sD + D, *nd = sZ + D, *zk = nd + D, *wgt = zk + D, *mu = wgt + D,
+         *dorg = mu + D, *zh = dorg + D, *sn = zh + D, *lamn = sn + D, *fin = lamn + D;
+  double *scal = fin + D;
+  int *sidx = reinterpret_cast<int *>(scal + 64), *ncol = sidx + D, *orgi = ncol + D, *dest = orgi + D;
+  tdc::RotRec *rots = reinterpret_cast<tdc::RotRec *>(dest + D);
+  unsigned char *flag = reinterpret_cast<unsigned char *>(rots + D);
+  // per-merge scalars (slot m = 0, 1): rho, tol; beta[1..3]; ints: k, skip, anyclose, nrot
+  double *m_rho = scal, *m_tol = scal + 2, *m_beta = scal + 4;
+  int *m_k = reinterpret_cast<int *>(scal + 16), *m_skip = m_k + 2, *m_close = m_k + 4, *m_nrot = m_k + 6;
+  int *bnd = m_k + 8;  // [5]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fm = lane >> 2, fj = lane & 3;
+  const size_t mat = blockIdx.x;
+  const double *in = rec + mat * G::LEAF_REC;
+
+  // ---- load the leaves: eigenvalues, eigenvector blocks on the diagonal of QsT ----
+  for (int i = tid; i < D * LD; i += NT) QsT[i] = 0.0;
+  if (tid == 0) tdc::leaf_bounds(d, bnd);
+  if (tid < 4) m_beta[tid] = in[tid];  // [0] = orgnrm, [1..3] = beta of the tears
+  if (tid < D) Dv[tid] = in[G::LEAF_HDR + tid];
+  __syncthreads();
+  const double orgnrm = m_beta[0];
+  for (int i = tid; i < 4 * LM * LM; i += NT) {
+    const int q = i / (LM * LM), rem = i - q * LM * LM;
+    const int j = rem / LM, r = rem - j * LM;
+    const int o = bnd[q], n = bnd[q + 1] - bnd[q];
+    if (j < n && r < n) QsT[(o + j) * LD + o + r] = in[G::LEAF_HDR + D + i];
+  }
+
+  QuadGroup grp;
+  grp.p = tid & 3;
+  grp.mask = 0xFu << (lane & ~3);
+  const int g = tid >> 2;  // root / z entry handled by this quad (phases P6 - P8)
+
+  for (int level = 1; level <= 2; ++level) {
+    __syncthreads();
+    auto describe = [&](int idx, int &ms, int &l, int &m, int &h) {
+      if (level == 2) {
+        ms = 0;
+        l = bnd[0];
+        m = bnd[2];
+        h = bnd[4];
+      } else if (idx < bnd[2]) {
+        ms = 0;
+        l = bnd[0];
+        m = bnd[1];
+        h = bnd[2];
+      } else {
+        ms = 1;
+        l = bnd[2];
+        m = bnd[3];
+        h = bnd[4];
+      }
+    };
+    int mslot, lo, mid, hi;
+    describe(tid, mslot, lo, mid, hi);
+    const bool mine = tid < d;
+    const int n = hi - lo;
+    // P1: z, rho
+    if (mine) {
+      const double beta = (level == 2) ? m_beta[2] : (mslot == 0 ? m_beta[1] : m_beta[3]);
+      const double sg = beta < 0.0 ? -1.0 : 1.0;
+      zv[tid] = (tid < mid ? QsT[tid * LD + mid - 1] : sg * QsT[tid * LD + mid]) * 0.70710678118654752440;
+      if (tid == lo) {
+        m_rho[mslot] = 2.0 * fabs(beta);
+        m_close[mslot] = 0;
+        m_nrot[mslot] = 0;
+      }
+    }
+    __syncthreads();
+    // P2: tolerance, first deflation test, sort by rank
+    if (mine) {
+      const double rho = m_rho[mslot];
+      double dmax = 0.0, zmax = 0.0;
+      for (int i = lo; i < hi; ++i) {
+        dmax = fmax(dmax, fabs(Dv[i]));
+        zmax = fmax(zmax, fabs(zv[i]));
+      }
+      const double tol = 8.0 * tdc::EPS * fmax(dmax, zmax);
+      const bool skip = (rho == 0.0) || (rho * zmax <= tol);
+      const double my = Dv[tid];
+      int rank = 0;
+      for (int i = lo; i < hi; ++i) {
+        const double di = Dv[i];
+        rank += (di < my) || (di == my && i < tid);
+      }
+      sD[lo + rank] = my;
+      sZ[lo + rank] = zv[tid];
+      sidx[lo + rank] = tid;
+      flag[lo + rank] = (rho * fabs(zv[tid]) <= tol) ? 1 : 0;
+      if (tid == lo) {
+        m_tol[mslot] = tol;
+        m_skip[mslot] = skip ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    const bool skip = mine ? (m_skip[mslot] != 0) : true;
+    // P3: would the sequential deflation scan rotate anything?
+    if (mine && !skip) {
+      const int p = tid;  // sorted position (global)
+      if (!flag[p]) {
+        int q = p - 1;
+        while (q >= lo && flag[q]) --q;
+        if (q >= lo && tdc::close_pair(sD[q], sZ[q], sD[p], sZ[p], m_tol[mslot])) m_close[mslot] = 1;
+      }
+    }
+    __syncthreads();
+    // P4: the scan itself (one thread per merge; rare), then the rotations on the columns of Q
+    if (mine && !skip && tid == lo && m_close[mslot]) {
+      m_nrot[mslot] = tdc::deflate_scan(n, sD + lo, sZ + lo, flag + lo, m_tol[mslot], rots + lo);
+    }
+    __syncthreads();
+    if (mine && !skip) {
+      const int nr = m_nrot[mslot];
+      for (int r = 0; r < nr; ++r) {
+        const tdc::RotRec rr = rots[lo + r];
+        double *cp = QsT + sidx[lo + rr.p] * LD, *cq = QsT + sidx[lo + rr.q] * LD;
+        const double x = cp[tid], y = cq[tid];
+        cp[tid] = rr.c * x + rr.s * y;
+        cq[tid] = rr.c * y - rr.s * x;
+      }
+    }
+    // P5: compaction into the new order [survivors (ascending), deflated]
+    if (mine && !skip) {
+      int k = 0, before = 0;
+      for (int q = lo; q < hi; ++q) {
+        const int sv = flag[q] ? 0 : 1;
+        k += sv;
+        before += (q < tid) ? sv : 0;
+      }
+      const bool surv = !flag[tid];
+      const int i = surv ? before : k + ((tid - lo) - before);
+      nd[lo + i] = sD[tid];
+      zk[lo + i] = sZ[tid];
+      wgt[lo + i] = m_rho[mslot] * sZ[tid] * sZ[tid];
+      ncol[lo + i] = sidx[tid];
+      if (tid == lo) m_k[mslot] = k;
+    }
+    __syncthreads();
+    // quad g owns root / entry g of the merge that contains g
+    int gslot, glo, gmid, ghi;
+    describe(g, gslot, glo, gmid, ghi);
+    const bool gact = (g < d) && (m_skip[gslot] == 0);
+    const int gk = gact ? m_k[gslot] : 0;
+    const int gj = g - glo;
+    // P6: secular roots
+    if (gact && gj < gk) {
+      double m_;
+      const int og = tdc::secular_root(gk, nd + glo, zk + glo, wgt + glo, m_rho[gslot], gj, &m_, grp);
+      if (grp.p == 0) {
+        mu[g] = m_;
+        orgi[g] = og;
+        dorg[g] = nd[glo + og];
+        lamn[g] = nd[glo + og] + m_;
+      }
+    }
+    __syncthreads();
+    // P7: Gu / Eisenstat z
+    if (gact && gj < gk) {
+      const double v = tdc::zhat(gk, nd + glo, mu + glo, orgi + glo, m_rho[gslot], gj, zk[g], grp);
+      if (grp.p == 0) zh[g] = v;
+    }
+    __syncthreads();
+    // P8: column norms
+    if (gact && gj < gk) {
+      const double v = tdc::inv_colnorm(gk, nd + glo, zh + glo, mu[g], dorg[g], grp);
+      if (grp.p == 0) sn[g] = v;
+    }
+    __syncthreads();
+
+    // P9: Q_new = Q [V 0; 0 I] (new column order): warp w owns output columns 8w .. 8w+7
+    int wslot, wlo, wmid, whi;
+    describe(8 * warp, wslot, wlo, wmid, whi);
+    const bool wactive = 8 * warp < d;
+    const bool wskip = wactive ? (m_skip[wslot] != 0) : true;
+    double acc[NB][2];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) acc[t][0] = acc[t][1] = 0.0;
+    if (wactive && !wskip) {
+      const int wk = m_k[wslot];
+      const int jb = 8 * warp + fm;  // B operand's output column
+      const bool jv = (jb - wlo) < wk && jb < whi;
+      const double s_j = jv ? sn[jb] : 0.0, mu_j = jv ? mu[jb] : 0.0, do_j = jv ? dorg[jb] : 0.0;
+      const int tlo = wlo >> 3, thi = (whi + 7) >> 3;
+      const int nchunk = (wk + 3) >> 2;
+      for (int q = 0; q < nchunk; ++q) {
+        const int i = 4 * q + fj;
+        double bval = 0.0;
+        int acol = wlo;
+        if (i < wk) {
+          acol = ncol[wlo + i];
+          if (jv) bval = zh[wlo + i] * s_j * TDC_RCP((nd[wlo + i] - do_j) - mu_j);
+        }
+        const double *ap = QsT + acol * LD + fm;
+#pragma unroll
+        for (int t = 0; t < NB; ++t)
+          if (t >= tlo && t < thi) dmma884(acc[t][0], acc[t][1], ap[8 * t], bval);
+      }
+      // deflated columns are copied
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int jj = 8 * warp + 2 * fj + e;
+        if (jj < whi && (jj - wlo) >= wk) {
+          const double *cp = QsT + ncol[jj] * LD + fm;
+#pragma unroll
+          for (int t = 0; t < NB; ++t)
+            if (t >= tlo && t < thi) acc[t][e] = cp[8 * t];
+        }
+      }
+    }
+    __syncthreads();  // every read of the old Q is done
+    if (level == 1) {
+      if (wactive && !wskip) {
+        const int wk = m_k[wslot];
+        const int tlo = wlo >> 3, thi = (whi + 7) >> 3;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jj = 8 * warp + 2 * fj + e;
+          if (jj < whi) {
+#pragma unroll
+            for (int t = 0; t < NB; ++t)
+              if (t >= tlo && t < thi) QsT[jj * LD + 8 * t + fm] = acc[t][e];
+            if (fm == 0) Dv[jj] = (jj - wlo) < wk ? lamn[jj] : nd[jj];
+          }
+        }
+      }
+    } else {
+      // ---- top level: final eigenvalues, ascending order, output ----
+      const int k = (mine && !skip) ? m_k[mslot] : 0;
+      if (mine) fin[tid] = skip ? Dv[tid] : ((tid - lo) < k ? lamn[tid] : nd[tid]);
+      __syncthreads();
+      if (mine) {
+        const double my = fin[tid];
+        int rank = 0;
+        for (int i = 0; i < d; ++i) {
+          const double fi = fin[i];
+          rank += (fi < my) || (fi == my && i < tid);
+        }
+        dest[tid] = rank;
+        lam[mat * d + rank] = my * (orgnrm > 0.0 ? orgnrm : 1.0);
+      }
+      if (wactive && wskip) {  // nothing was merged at the top: Q is unchanged, column jj stays column jj
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jj = 8 * warp + 2 * fj + e;
+          if (jj < d) {
+#pragma unroll
+            for (int t = 0; t < NB; ++t) acc[t][e] = QsT[jj * LD + 8 * t + fm];
+          }
+        }
+      }
+      __syncthreads();
+      // stage row-major in shared memory (the old Q is dead), then write coalesced
+      if (wactive) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jj = 8 * warp + 2 * fj + e;
+          if (jj < d) {
+            const int dj = dest[jj];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) QsT[(8 * t + fm) * LD + dj] = acc[t][e];  // now [row][column]
+          }
+        }
+      }
+      __syncthreads();
+      const size_t dd = (size_t)d * d;
+      for (int idx = tid; idx < d * d; idx += NT) {
+        const int r = idx / d, c = idx - r * d;
+        Zt[mat * dd + idx] = QsT[r * LD + c];
+      }
+    }
+  }
+}
+
+}  // namespace musim

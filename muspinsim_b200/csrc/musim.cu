@@ -184,10 +184,14 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->eo.tridiag_fused = value != 0;
   else if (!strcmp(key, "small24"))
     h->eo.small24 = value != 0;
+  else if (!strcmp(key, "tridiag_one"))  // 0: two-barrier register tridiagonalisation (eigh_tridiag_rw.cuh)
+    h->eo.tridiag_one = value != 0;
   else if (!strcmp(key, "tridiag_rw"))  // 0: shared-memory tridiagonalisation kernel
     h->eo.tridiag_rw = value != 0;
   else if (!strcmp(key, "reflect"))  // 0: form Q in the tridiagonalisation kernel + GEMM back-transformation
     h->eo.reflect = value != 0;
+  else if (!strcmp(key, "tdc"))  // 0: QL iteration + rotation replay instead of the tridiagonal divide and conquer (32 < d <= 96)
+    h->eo.tdc = value != 0;
   else if (!strcmp(key, "back_wy"))  // 0: level-2 reflector kernel instead of the compact-WY DMMA kernel (32 < d <= 96)
     h->eo.back_wy = value != 0;
   else if (!strcmp(key, "defaults")) {  // reset every kernel-selection option (a cached handle starts a new runner clean)

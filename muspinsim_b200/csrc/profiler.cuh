@@ -20,11 +20,12 @@ enum Phase {
   PH_POLAR,
   PH_INTEGRAL,
   PH_LINDBLAD,
+  PH_EIGH_TDC,
   PH_COUNT
 };
 static const char *const kPhaseNames[PH_COUNT] = {"eigh_tridiag", "eigh_tql", "eigh_apply", "eigh_back",
                                                   "eigh_jacobi",  "rotate",   "rho0",       "polar",
-                                                  "integral",     "lindblad"};
+                                                  "integral",     "lindblad", "eigh_tdc"};
 
 struct Profiler {
   bool on = false;

@@ -1,0 +1,411 @@
+// tdc_core.cuh -- numerical core of the tridiagonal DIVIDE AND CONQUER eigensolver (host + device).
+//
+// Second stage of np.linalg.eigh (LAPACK zheevd -> dstedc, /root/reference/muspinsim/spinop.py:69):
+// eigenvalues and eigenvectors of the real symmetric tridiagonal matrix the Householder reduction
+// leaves.  T is torn into NLEAF diagonal blocks (Cuppen),
+//     T = blockdiag(T_0', .., T_{NLEAF-1}') + sum_tears |beta| u u^T,  u = e_last + sign(beta) e_first,
+// the leaves are solved by implicit QL (short serial chains that run concurrently), and pairs of
+// blocks are merged level by level: each merge is the eigenproblem of D + rho z z^T,
+//   * deflation (dlaed2): components with rho |z_i| <= tol, and close eigenvalue pairs (one plane
+//     rotation each), drop out;
+//   * the remaining k roots of the secular equation 1 + rho sum z_i^2 / (d_i - lambda) = 0 are
+//     found INDEPENDENTLY (one thread each), each in the frame of its nearest pole so that the
+//     differences d_i - lambda keep full relative accuracy;
+//   * z is recomputed from the computed roots (Gu / Eisenstat, dlaed3), which makes the eigenvectors
+//     v_j = (zhat_i / (d_i - lambda_j))_i orthogonal to working precision;
+//   * Q <- Q [V 0; 0 I] is a GEMM (DMMA on the device).
+// Everything in this header is plain scalar code shared by the CUDA kernel (eigh_tdc.cuh) and by a
+// host build (tdc_host.cpp -> tests/test_tdc_host.py compares it with LAPACK without a GPU).  The
+// restated algorithms follow the published LAPACK routines named above (netlib LAPACK 3.x: dsteqr /
+// dlaev2 for the leaves, dlaed2 / dlaed4 / dlaed3 for a merge); the root finder is our own
+// (two-pole + linear-remainder model with a safeguarded bracket) instead of dlaed4's rational
+// interpolation cases.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TDC_HD __host__ __device__ __forceinline__
+#else
+#define TDC_HD inline
+#endif
+
+namespace musim {
+namespace tdc {
+
+constexpr double EPS = 1.1102230246251565e-16;  // dlamch('Epsilon'): relative machine precision 2^-53
+
+#if defined(__CUDA_ARCH__)
+// 1 / x to ~1 ulp without the special-case path of the IEEE division (ncu: the full sequence and its
+// branch were 40 % of the instructions of the secular loop): MUFU.RCP64H seed (>= 20 bits) + 2 Newton
+// steps.  Only for arguments that are neither subnormal nor huge (pole distances of a unit-norm problem).
+__device__ __forceinline__ double tdc_fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+#define TDC_RCP(x) ::musim::tdc::tdc_fast_rcp(x)
+#define TDC_RSQRT(x) rsqrt(x)
+#else
+#define TDC_RCP(x) (1.0 / (x))
+#define TDC_RSQRT(x) (1.0 / sqrt(x))
+#endif
+
+// A group of P threads (P = 1 on the host, 4 adjacent lanes on the device) shares one root / one
+// entry of z: thread `part` takes the poles i = part, part + P, ... and the partial results are
+// combined by the reducer (sum / product over the group, result in every member).
+struct SerialGroup {
+  static constexpr int P = 1;
+  TDC_HD int part() const { return 0; }
+  TDC_HD double sum(double v) const { return v; }
+  TDC_HD double prod(double v) const { return v; }
+};
+
+#if defined(TDC_STATS) && !defined(__CUDA_ARCH__)
+static long g_sec_outer = 0, g_sec_inner = 0, g_sec_roots = 0;  // host-only iteration counters (tests)
+#define TDC_COUNT(x) (++(x))
+#else
+#define TDC_COUNT(x) ((void)0)
+#endif
+
+// 2 x 2 symmetric eigenproblem [[a, b], [b, c]] (LAPACK dlaev2): rt1 >= rt2 in absolute value,
+// (cs1, sn1) the unit eigenvector of rt1.
+TDC_HD void laev2(double a, double b, double c, double &rt1, double &rt2, double &cs1, double &sn1) {
+  const double sm = a + c, df = a - c, adf = fabs(df), tb = b + b, ab = fabs(tb);
+  double acmx, acmn;
+  if (fabs(a) > fabs(c)) {
+    acmx = a;
+    acmn = c;
+  } else {
+    acmx = c;
+    acmn = a;
+  }
+  double rt;
+  if (adf > ab) {
+    const double q = ab / adf;
+    rt = adf * sqrt(1.0 + q * q);
+  } else if (adf < ab) {
+    const double q = adf / ab;
+    rt = ab * sqrt(1.0 + q * q);
+  } else {
+    rt = ab * 1.4142135623730951;
+  }
+  int sgn1, sgn2;
+  if (sm < 0.0) {
+    rt1 = 0.5 * (sm - rt);
+    sgn1 = -1;
+    rt2 = (acmx / rt1) * acmn - (b / rt1) * b;
+  } else if (sm > 0.0) {
+    rt1 = 0.5 * (sm + rt);
+    sgn1 = 1;
+    rt2 = (acmx / rt1) * acmn - (b / rt1) * b;
+  } else {
+    rt1 = 0.5 * rt;
+    rt2 = -0.5 * rt;
+    sgn1 = 1;
+  }
+  double cs;
+  if (df >= 0.0) {
+    cs = df + rt;
+    sgn2 = 1;
+  } else {
+    cs = df - rt;
+    sgn2 = -1;
+  }
+  if (fabs(cs) > ab) {
+    const double ct = -tb / cs;
+    sn1 = 1.0 / sqrt(1.0 + ct * ct);
+    cs1 = ct * sn1;
+  } else if (ab == 0.0) {
+    cs1 = 1.0;
+    sn1 = 0.0;
+  } else {
+    const double tn = -cs / tb;
+    cs1 = 1.0 / sqrt(1.0 + tn * tn);
+    sn1 = tn * cs1;
+  }
+  if (sgn1 == sgn2) {
+    const double tn = cs1;
+    cs1 = -sn1;
+    sn1 = tn;
+  }
+}
+
+// Implicit QL on the leaf (D[0..n), E[0..n), E[n-1] ignored) with the eigenvector rows updated through
+// `rows` (EISPACK tql2 / LAPACK dsteqr, same arithmetic as hql_tql_kernel):
+//   rows.begin(m)       f = Z[.][m];  cur = Z[.][m-1]
+//   rows.load(j)        nxt = Z[.][j]                      (issued BEFORE the scalar chain of the rotation)
+//   rows.rot(j, cx, cy) a = cur;  Z[.][j+1] = cx f - cy a;  f = cy f + cx a;  cur = nxt
+//   rows.end(l)         Z[.][l] = f
+// On the device every lane of a warp runs the scalar chain redundantly (no communication) and owns
+// one row.  The values the NEXT rotation needs (e, d, the row entry) are fetched at the top of the
+// current one and carried in registers, so that no shared-memory latency sits on the serial chain
+// (first device version without this: 1 300 cycles per rotation, ncu).  Returns false if the
+// iteration limit is hit.
+template <class Rows>
+TDC_HD bool leaf_ql(int n, double *D, double *E, Rows &rows) {
+  const double eps2 = 4.930380657631324e-32;  // (2^-52)^2
+  const double safmin = 2.2250738585072014e-308;
+  if (n > 0) E[n - 1] = 0.0;
+  int l = 0, nit = 0;
+  const int maxit = 60 * n;
+  while (l < n) {
+    int m = l;
+    while (m < n - 1) {
+      const double em = E[m];
+      if (em * em <= (eps2 * fabs(D[m])) * fabs(D[m + 1]) + safmin) break;
+      ++m;
+    }
+    if (m < n - 1) E[m] = 0.0;
+    if (m == l) {
+      ++l;
+      continue;
+    }
+    if (nit >= maxit) return false;
+    if (m == l + 1) {
+      double rt1, rt2, c, s;
+      laev2(D[l], E[l], D[l + 1], rt1, rt2, c, s);
+      rows.begin(l + 1);
+      rows.rot(l, c, s);
+      rows.end(l);
+      D[l] = rt1;
+      D[l + 1] = rt2;
+      E[l] = 0.0;
+      l += 2;
+      continue;
+    }
+    ++nit;
+    double p = D[l];
+    const double el_l = E[l];
+    double g = (D[l + 1] - p) / (2.0 * el_l);
+    double r = sqrt(fma(g, g, 1.0));
+    g = D[m] - p + el_l / (g + copysign(r, g));
+    double s = 1.0, c = 1.0;
+    p = 0.0;
+    // carried / prefetched values: d_ip1 = D[i+1] (untouched so far in this sweep), e_i, d_i
+    double d_ip1 = D[m];
+    double e_i = E[m - 1], d_i = D[m - 1];
+    rows.begin(m);
+    for (int i = m - 1; i >= l; --i) {
+      double e_nx = 0.0, d_nx = 0.0;
+      if (i > l) {
+        e_nx = E[i - 1];
+        d_nx = D[i - 1];
+        rows.load(i - 1);
+      }
+      const double f = s * e_i;
+      const double b = c * e_i;
+      const double q = fma(g, g, f * f);
+      if (q == 0.0) {
+        c = 1.0;
+        s = 0.0;
+        r = 0.0;
+      } else {
+        const double ri = TDC_RSQRT(q);
+        r = q * ri;
+        c = g * ri;
+        s = f * ri;
+      }
+      if (i != m - 1) E[i + 1] = r;
+      g = d_ip1 - p;
+      r = fma(d_i - g, s, 2.0 * c * b);
+      p = s * r;
+      D[i + 1] = g + p;
+      g = fma(c, r, -b);
+      rows.rot(i, c, -s);
+      d_ip1 = d_i;
+      e_i = e_nx;
+      d_i = d_nx;
+    }
+    rows.end(l);
+    D[l] = D[l] - p;
+    E[l] = g;
+  }
+  return true;
+}
+
+// Root j (0-based, ascending) of 1 + rho sum_i z_i^2 / (dk_i - lambda) = 0 for strictly increasing
+// dk[0..k), non-zero zk, rho > 0.  Returns the index `org` of the pole nearest to the root and
+// *mu = lambda - dk[org]; dk_i - lambda must then be formed as (dk_i - dk_org) - mu.
+template <class Group>
+TDC_HD int secular_root(int k, const double *dk, const double *zk, const double *wk, double rho, int j,
+                        double *mu_out, const Group &grp) {
+  // wk[i] = rho zk[i]^2 (precomputed once per merge)
+  if (k == 1) {
+    *mu_out = wk[0];
+    return 0;
+  }
+  const bool last = (j == k - 1);
+  const int L = j, R = last ? j : j + 1;
+  const double a = wk[L], b = last ? 0.0 : wk[R];
+  const double half = last ? 0.0 : 0.5 * (dk[R] - dk[L]);
+  int org = L;
+  double lo = 0.0, hi, mu;
+  if (!last) {
+    hi = half;
+    mu = half;  // first evaluation at the midpoint, in the frame of the left pole; it also picks the frame
+  } else {
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s += zk[i] * zk[i];
+    hi = rho * s;  // lambda_max <= dk[k-1] + rho |z|^2
+    mu = 0.5 * hi;
+  }
+  double dorg = dk[L];
+  double dL = 0.0, dR = dk[R] - dk[L];
+  TDC_COUNT(g_sec_roots);
+  for (int it = 0; it < 80; ++it) {
+    TDC_COUNT(g_sec_outer);
+    double c0 = 0.0, c1 = 0.0, asum = 0.0;
+#pragma unroll 4
+    for (int i = grp.part(); i < k; i += Group::P) {
+      // straight-line body: the two neighbouring poles (treated exactly below) get weight 0; their
+      // distances (dk_i - dorg) - mu are never 0 inside the bracket, so the reciprocal is finite
+      const double wi = (i == L || i == R) ? 0.0 : wk[i];
+      const double rdel = TDC_RCP((dk[i] - dorg) - mu);
+      const double t = wi * rdel;
+      c0 += t;
+      c1 = fma(t, rdel, c1);
+      asum += fabs(t);
+    }
+    c0 = grp.sum(c0);
+    c1 = grp.sum(c1);
+    asum = grp.sum(asum);
+    const double pL = a / (dL - mu), pR = last ? 0.0 : b / (dR - mu);
+    const double g = 1.0 + c0 + pL + pR;
+    if (it == 0 && !last && g < 0.0) {
+      // root in the right half: continue in the frame of the right pole, mu in [-half, 0).  The
+      // quantities just evaluated are frame independent (dk_i - lambda is the same point).
+      org = R;
+      dorg = dk[R];
+      dL = dk[L] - dk[R];
+      dR = 0.0;
+      mu = -half;
+      lo = -half;
+      hi = 0.0;
+    }
+    const double err = 8.0 * EPS * (1.0 + asum + fabs(pL) + fabs(pR));
+    if (fabs(g) <= err) break;
+    if (g < 0.0)
+      lo = mu;
+    else
+      hi = mu;
+    if (hi - lo <= 2.0 * EPS * fmax(fabs(lo), fabs(hi))) break;
+    // model h(x) = C0 + c1 (x - mu) + a / (dL - x) + b / (dR - x): exact in the two neighbouring poles,
+    // first order in the rest; increasing on the interval -> safeguarded Newton inside (lo, hi)
+    const double C0 = 1.0 + c0;
+    double x = mu;
+    for (int in = 0; in < 12; ++in) {
+      TDC_COUNT(g_sec_inner);
+      const double eL = dL - x, eR = dR - x;
+      const double rL = 1.0 / eL, rR = last ? 0.0 : 1.0 / eR;
+      const double h = C0 + c1 * (x - mu) + a * rL + b * rR;
+      const double hp = c1 + a * rL * rL + b * rR * rR;
+      double xn = x - h / hp;
+      if (!(xn > lo)) xn = 0.5 * (x + lo);
+      if (!(xn < hi)) xn = 0.5 * (x + hi);
+      const bool done = fabs(xn - x) <= 4.0 * EPS * fabs(xn);
+      x = xn;
+      if (done) break;
+    }
+    if (x == mu) break;
+    mu = x;
+  }
+  *mu_out = mu;
+  return org;
+}
+
+// Gu / Eisenstat: the z that makes the COMPUTED roots exact (dlaed3).  diff(i, j) = dk_i - lambda_j
+// = (dk_i - dk[org_j]) - mu_j.  `sgn` supplies the sign (the original z_i).
+template <class Group>
+TDC_HD double zhat(int k, const double *dk, const double *mu, const int *org, double rho, int i, double sgn,
+                   const Group &grp) {
+  double prod = (grp.part() == 0) ? -((dk[i] - dk[org[i]]) - mu[i]) / rho : 1.0;  // (lambda_i - dk_i) / rho > 0
+#pragma unroll 4
+  for (int j = grp.part(); j < k; j += Group::P) {
+    const double num = (dk[i] - dk[org[j]]) - mu[j], den = dk[i] - dk[j];
+    prod *= (j == i) ? 1.0 : num * TDC_RCP(den);
+  }
+  prod = grp.prod(prod);
+  return copysign(sqrt(fabs(prod)), sgn);
+}
+
+// 1 / || (zh_i / diff(i, j))_i ||
+template <class Group>
+TDC_HD double inv_colnorm(int k, const double *dk, const double *zh, double mu_j, double dorg_j, const Group &grp) {
+  double s = 0.0;
+#pragma unroll 4
+  for (int i = grp.part(); i < k; i += Group::P) {
+    const double v = zh[i] * TDC_RCP((dk[i] - dorg_j) - mu_j);
+    s = fma(v, v, s);
+  }
+  s = grp.sum(s);
+  return 1.0 / sqrt(s);
+}
+
+struct RotRec {
+  int p, q;  // sorted positions: column p is deflated, q survives (LAPACK dlaed2: PJ, NJ)
+  double c, s;
+};
+
+// Sequential deflation scan of dlaed2 over the merge's entries in ascending order of sD.
+// flag[p]: 0 candidate, 1 deflated because rho |z| <= tol (set by the caller); the scan sets 2 for
+// entries deflated by a rotation.  Returns the number of rotations recorded: columns (p, q) of Q are
+// then to be rotated as  col_p' = c col_p + s col_q,  col_q' = c col_q - s col_p  (drot).
+TDC_HD int deflate_scan(int n, double *sD, double *sZ, unsigned char *flag, double tol, RotRec *rots) {
+  int pj = -1, nr = 0;
+  for (int p = 0; p < n; ++p) {
+    if (flag[p]) continue;
+    if (pj < 0) {
+      pj = p;
+      continue;
+    }
+    double s = sZ[pj], c = sZ[p];
+    const double tau = sqrt(c * c + s * s);
+    const double t = sD[p] - sD[pj];
+    c /= tau;
+    s = -s / tau;
+    if (fabs(t * c * s) <= tol) {
+      sZ[p] = tau;
+      sZ[pj] = 0.0;
+      rots[nr].p = pj;
+      rots[nr].q = p;
+      rots[nr].c = c;
+      rots[nr].s = s;
+      ++nr;
+      const double tt = sD[pj] * c * c + sD[p] * s * s;
+      sD[p] = sD[pj] * s * s + sD[p] * c * c;
+      sD[pj] = tt;
+      flag[pj] = 2;
+    }
+    pj = p;
+  }
+  return nr;
+}
+
+// The closeness test of the scan for one adjacent pair of candidates with their ORIGINAL values: if
+// it fails for every pair, the scan would not rotate anything and can be skipped.
+TDC_HD bool close_pair(double d_prev, double z_prev, double d_cur, double z_cur, double tol) {
+  const double tau = sqrt(z_cur * z_cur + z_prev * z_prev);
+  const double c = z_cur / tau, s = -z_prev / tau;
+  return fabs((d_cur - d_prev) * c * s) <= tol;
+}
+
+// Leaf boundaries: the d rows are cut at multiples of 8 (row tiles of the DMMA GEMMs) into 4 leaves
+// of at most 24 rows (d <= 96), sizes as even as the tiles allow.  bnd[0..4].
+TDC_HD void leaf_bounds(int d, int *bnd) {
+  const int tiles = (d + 7) / 8;
+  int t0 = 0;
+  bnd[0] = 0;
+  for (int q = 0; q < 4; ++q) {
+    const int cnt = tiles / 4 + (q < tiles % 4 ? 1 : 0);
+    t0 += cnt;
+    bnd[q + 1] = (8 * t0 < d) ? 8 * t0 : d;
+  }
+  bnd[4] = d;
+}
+
+}  // namespace tdc
+}  // namespace musim

@@ -110,3 +110,17 @@ def test_large_dimension_degenerate_and_physical():
     mats.append(s.hamiltonian + 0.3 * s.zeeman_operators()[2])
     A = np.array([0.5 * (m + m.conj().T) for m in mats])
     _check(A, 2, tol=2e-12)
+
+
+@pytest.mark.parametrize("d", [33, 34, 40, 41, 47, 49, 56, 57, 63, 65, 72, 73, 80, 88, 90, 95])
+def test_divide_and_conquer_range(d):
+    """32 < d <= 96: tridiagonal divide and conquer (eigh_tdc.cuh) + compact-WY back-transformation
+    (eigh_backwy.cuh); ragged dimensions (leaves cut at multiples of 8), degenerate and torn spectra."""
+    rng = np.random.default_rng(1000 + d)
+    _check(_rand_herm(rng, 8, d), 2)
+    q, _ = np.linalg.qr(_rand_herm(rng, 1, d)[0])
+    mats = [(q * (np.arange(d) // 3).astype(float)) @ q.conj().T, np.zeros((d, d), dtype=complex),
+            np.eye(d, dtype=complex) * -2.0, np.diag(rng.normal(size=d)).astype(complex),
+            np.diag(np.abs(np.arange(d) - (d - 1) / 2)).astype(complex) + np.diag(np.ones(d - 1), 1) + np.diag(np.ones(d - 1), -1),
+            _rand_herm(rng, 1, d)[0] * 1e-7, _rand_herm(rng, 1, d)[0] * 7e4]
+    _check(np.array([0.5 * (m + m.conj().T) for m in mats]), 2)

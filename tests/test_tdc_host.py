@@ -1,0 +1,97 @@
+"""The numerical core of the tridiagonal divide-and-conquer eigensolver (csrc/tdc_core.cuh: leaf QL,
+deflation, secular roots, Gu/Eisenstat vectors) is plain host/device code: here it is built for the
+HOST (csrc/tdc_host.cpp, g++) and compared with LAPACK -- eigenvalues, orthogonality and residual
+-- on random, degenerate, clustered, graded and torn matrices and on the tridiagonal forms of the
+benchmark spin Hamiltonians (zero field included).  No GPU needed; the CUDA kernel (eigh_tdc.cuh)
+runs the same functions per thread and is checked against the same bar in test_gpu_eigh.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "muspinsim_b200", "csrc", "tdc_host.cpp")
+OUT = os.path.join(ROOT, "oracle", "_build", "libtdc_host.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    deps = [SRC, os.path.join(os.path.dirname(SRC), "tdc_core.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(p) > os.path.getmtime(OUT) for p in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", OUT, SRC])
+    return ctypes.CDLL(OUT)
+
+
+def _solve(lib, d, e):
+    n = len(d)
+    d, e = np.ascontiguousarray(d, float), np.ascontiguousarray(e, float)
+    lam, Z, st = np.zeros(n), np.zeros((n, n)), (ctypes.c_int * 3)()
+    rc = lib.tdc_host_eigh(n, d.ctypes.data, e.ctypes.data, lam.ctypes.data, Z.ctypes.data, st)
+    return rc, lam, Z, list(st)
+
+
+def _check(lib, d, e, tol=2e-14):
+    n = len(d)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    rc, lam, Z, st = _solve(lib, d, e)
+    assert rc == 0
+    w = np.linalg.eigvalsh(T)
+    sc = max(np.max(np.abs(w)), 1e-300)
+    assert np.max(np.abs(np.sort(lam) - w)) <= tol * sc
+    assert np.max(np.abs(Z.T @ Z - np.eye(n))) <= tol
+    assert np.max(np.abs(T @ Z - Z * lam)) <= tol * sc
+    return st
+
+
+@pytest.mark.parametrize("n", [33, 34, 40, 41, 48, 57, 64, 65, 72, 80, 90, 95, 96])
+def test_random_matrices(lib, n):
+    rng = np.random.default_rng(n)
+    for _ in range(5):
+        _check(lib, rng.normal(size=n), rng.normal(size=n - 1))
+
+
+def test_structured_and_degenerate_matrices(lib):
+    rng = np.random.default_rng(7)
+    n = 96
+    st = _check(lib, np.zeros(n), np.ones(n - 1))
+    assert st[1] > 0  # the mirror-symmetric halves share every eigenvalue: rotation deflation is exercised
+    _check(lib, 2 * np.ones(n), -np.ones(n - 1))
+    _check(lib, np.arange(n, dtype=float), 1e-3 * np.ones(n - 1))
+    _check(lib, np.abs(np.arange(n) - 47.5), np.ones(n - 1))  # Wilkinson: pairs agreeing to working precision
+    _check(lib, np.ones(n), np.zeros(n - 1))
+    _check(lib, rng.normal(size=n), 1e-9 * rng.normal(size=n - 1))
+    e = rng.normal(size=n - 1)
+    e[[23, 47, 71]] = 0.0  # zero coupling exactly at the tears (rho = 0)
+    _check(lib, rng.normal(size=n), e)
+    e = rng.normal(size=n - 1)
+    e[[10, 30, 60]] = 0.0
+    _check(lib, rng.normal(size=n), e)
+    _check(lib, np.repeat(rng.normal(size=12), 8), 1e-12 * rng.normal(size=n - 1))
+    _check(lib, 1e8 * rng.normal(size=n), 1e8 * rng.normal(size=n - 1))
+    _check(lib, 1e-8 * rng.normal(size=n), 1e-8 * rng.normal(size=n - 1))
+    d = rng.normal(size=n)
+    e = rng.normal(size=n - 1) * 10.0 ** rng.uniform(-14, 0, size=n - 1)
+    _check(lib, d, e)
+
+
+@pytest.mark.parametrize("which", ["c5", "c2_d64"])
+def test_spin_hamiltonians_including_zero_field(lib, which):
+    import scipy.linalg as sl
+
+    from muspinsim_b200 import workloads
+    from muspinsim_b200.spinsys import system_from_spec
+
+    spec = workloads.c5_large(n_orient=2, nt=4) if which == "c5" else workloads.c2_hfine_powder(n_orient=2, nt=4, n_h=4)
+    s, _ = system_from_spec(spec)
+    H0, Z3 = s.hamiltonian, s.zeeman_operators()
+    rng = np.random.default_rng(3)
+    fields = [np.zeros(3), np.array([0, 0, 0.01]), np.array([0, 0, 1e-7]), np.array([0.3, -0.2, 0.5])]
+    fields += [0.01 * v / np.linalg.norm(v) for v in rng.normal(size=(4, 3))]
+    for B in fields:
+        H = H0 + sum(B[a] * Z3[a] for a in range(3))
+        Hh = sl.hessenberg(H)
+        # a diagonal unitary scaling makes the sub-diagonal real and non-negative
+        _check(lib, np.real(np.diag(Hh)).copy(), np.abs(np.diag(Hh, -1)).copy())
