@@ -36,7 +36,8 @@
 // and writes T in the operand order of step 2.
 #pragma once
 #include "common.cuh"
-#include "polar.cuh"  // dmma884
+#include "eigh_hql.cuh"  // cp_async16
+#include "polar.cuh"    // dmma884
 
 namespace musim {
 
@@ -53,26 +54,40 @@ struct BackWyGeom {
   }
   static constexpr int VPLANE = voff(NB);
   static constexpr size_t smem_bytes = (size_t)(2 * VPLANE + TIMG) * sizeof(double);
+  static constexpr size_t tf_smem_bytes = (size_t)((D - 1) * (D - 2) / 2 + 8) * sizeof(cplx);  // >= NB * 64 Gram entries
 };
 
 // ---------------------------------------------------------------------------------------
-// T factors of all blocks of one matrix: one CTA (NB warps) per matrix.
+// T factors of all blocks of one matrix: one CTA (NB warps) per matrix.  The packed reflectors
+// (71 KB at d = 96, contiguous) are staged into shared memory with 16-byte cp.async first: the
+// version that gathered them straight from global memory (8 x 64-byte segments per load
+// instruction, each warp waiting on its own dependent chain) ran 1.13 ms at C5, long_scoreboard
+// 15 warps per issue (profiles/r2_ncu_k4.md).
 // ---------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(4 * D)
 hql_tfactor_kernel(int d, const cplx *__restrict__ Vp, size_t vcap, const cplx *__restrict__ tau,
                    double *__restrict__ Timg) {
   using G = BackWyGeom<D>;
-  constexpr int NB = G::NB, TLD = G::TLD;
-  __shared__ __align__(16) cplx Gs[NB][64];
+  constexpr int NB = G::NB, TLD = G::TLD, NT = 4 * D;
+  extern __shared__ __align__(16) unsigned char tf_smem[];
+  cplx *sV = reinterpret_cast<cplx *>(tf_smem);  // packed reflectors; the Gram matrices re-use the front afterwards
   const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
   const int fm = lane >> 2, fj = lane & 3;
   const size_t mat = blockIdx.x;
+  {
+    const int total = (d - 1) * (d - 2) / 2;
+    const cplx *src = Vp + mat * vcap;
+    for (int e = tid; e < total; e += NT) cp_async16(&sV[e], &src[e]);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+  }
   const int i = 8 * b + fm;  // this lane's reflector
   const bool valid = i < d - 1;
   const int mk = d - i - 2;
   // v_i[r] for r > i + 1 sits at base[r]
-  const cplx *base = Vp + mat * vcap + (valid ? (size_t)mk * (mk - 1) / 2 : 0) - (i + 2);
+  const cplx *base = sV + (valid ? mk * (mk - 1) / 2 : 0) - (i + 2);
   double gr[2][2][2] = {}, gi[2][2][2] = {}, hr[2][2][2] = {}, hi[2][2][2] = {};  // [t parity][e][slot]: short dependent chains
 #define TF_TILE(T_, TP_)                                                     \
   _Pragma("unroll") for (int e = 0; e < 2; ++e) {                            \
@@ -96,7 +111,8 @@ hql_tfactor_kernel(int d, const cplx *__restrict__ Vp, size_t vcap, const cplx *
     }
   }
 #undef TF_TILE
-  cplx *gs = Gs[b];
+  __syncthreads();  // every warp is done with the staged reflectors
+  cplx *gs = sV + b * 64;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const double re = (gr[0][0][s] + gr[0][1][s]) + (gr[1][0][s] + gr[1][1][s]) + (hr[0][0][s] + hr[0][1][s]) + (hr[1][0][s] + hr[1][1][s]);

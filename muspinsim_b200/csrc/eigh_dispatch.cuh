@@ -6,7 +6,6 @@
 #include "eigh_large.cuh"
 #include "eigh_tdc.cuh"
 #include "eigh_tridiag_rw.cuh"
-#include "eigh_tridiag_rw1.cuh"
 #include "eigh_tridiag_warp.cuh"
 #include "profiler.cuh"
 #include "rotate.cuh"
@@ -28,7 +27,6 @@ struct EighOpts {
   bool tridiag_phases = true;  // "tridiag_phases": K1 in up to three launches of decreasing size
   bool apply_warp = true;      // "apply_warp": rotation replay with one warp per CTA (d > 32)
   int tql_threads = 0;         // "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
-  bool tridiag_one = true;     // "tridiag_one": one-barrier-per-step register tridiagonalisation (eigh_tridiag_rw1.cuh); 0: two-barrier kernel
   bool tridiag_rw = true;      // "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96); 0: shared-memory kernel
   bool use_reflect(int d) const { return reflect && d >= 3 && d <= 96; }
 };
@@ -48,7 +46,15 @@ struct EighWs {
   cplx *Q[2] = {nullptr, nullptr};  // [2]: stage A (tridiagonalisation) of the next launch group overlaps stage B
   bool dbl = false;
   cplx *Vp[2] = {nullptr, nullptr}, *tauv[2] = {nullptr, nullptr};  // packed reflectors + tau (d <= 96 path)
-  double *tdc_rec = nullptr;  // leaf results of the tridiagonal divide and conquer (eigh_tdc.cuh), 32 < d <= 96
+  // tridiagonal divide and conquer (eigh_tdc.cuh), 32 < d <= 96: the four leaves of every matrix as a batch
+  // of 4 n independent 24 x 24 problems for the batched QL kernels
+  double *l_hdr = nullptr, *l_d = nullptr, *l_e = nullptr, *l_lam = nullptr, *l_Z = nullptr;
+  double2 *l_rot = nullptr;
+  SweepIdx *l_swp = nullptr;
+  int *l_nswp = nullptr;
+  unsigned short *l_perm = nullptr;
+  static constexpr size_t L_ROT_CAP = 2 * 24 * 24 + 64 + 14 * (6 * 24 + 16);
+  static constexpr int L_SWP_CAP = 6 * 24 + 16;
   double *Timg = nullptr;  // compact-WY T factors in operand order (eigh_backwy.cuh), 32 < d <= 96
   size_t vcap = 0;
   double2 *rot = nullptr;
@@ -85,8 +91,20 @@ struct EighWs {
     cudaFree(Zt);
     cudaFree(Timg);
     Timg = nullptr;
-    cudaFree(tdc_rec);
-    tdc_rec = nullptr;
+    cudaFree(l_hdr);
+    cudaFree(l_d);
+    cudaFree(l_e);
+    cudaFree(l_lam);
+    cudaFree(l_Z);
+    cudaFree(l_rot);
+    cudaFree(l_swp);
+    cudaFree(l_nswp);
+    cudaFree(l_perm);
+    l_hdr = l_d = l_e = l_lam = l_Z = nullptr;
+    l_rot = nullptr;
+    l_swp = nullptr;
+    l_nswp = nullptr;
+    l_perm = nullptr;
     cudaFree(Awork);
     Awork = nullptr;
     cudaFree(rot);
@@ -125,7 +143,17 @@ struct EighWs {
       }
       EW_ALLOC(Zt, (size_t)n * dd);
       if (d > 32 && d <= 96) EW_ALLOC(Timg, (size_t)n * BackWyGeom<96>::TIMG);
-      if (d > 32 && d <= 96) EW_ALLOC(tdc_rec, (size_t)n * TdcGeom<96>::LEAF_REC);
+      if (d > 32 && d <= 96) {
+        EW_ALLOC(l_hdr, (size_t)n * 4);
+        EW_ALLOC(l_d, (size_t)n * 4 * 24);
+        EW_ALLOC(l_e, (size_t)n * 4 * 24);
+        EW_ALLOC(l_lam, (size_t)n * 4 * 24);
+        EW_ALLOC(l_Z, (size_t)n * 4 * 24 * 24);
+        EW_ALLOC(l_rot, (size_t)n * 4 * L_ROT_CAP);
+        EW_ALLOC(l_swp, (size_t)n * 4 * L_SWP_CAP);
+        EW_ALLOC(l_nswp, (size_t)n * 4);
+        EW_ALLOC(l_perm, (size_t)n * 4 * 24);
+      }
       if (d > HQL_MAX_D) EW_ALLOC(Awork, (size_t)n * d * (d | 1));
       EW_ALLOC(rot, (size_t)n * rot_cap);
       EW_ALLOC(swp, (size_t)n * swp_cap);
@@ -185,28 +213,7 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
       cplx *vp_ = ws.Vp[buf], *tt_ = ws.tauv[buf];
       // phase buffers for the trailing blocks (Q is not used on the reflector path)
       cplx *A64 = ws.Q[buf], *A32 = ws.Q[buf] + (size_t)n * 64 * 64;
-      if (o.tridiag_one) {
-      const unsigned g = (unsigned)n;
-        if (d <= 32) {
-          hql_tridiag_rw1_kernel<32><<<g, 128, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-        } else if (!o.tridiag_phases) {
-          if (d <= 64)
-            hql_tridiag_rw1_kernel<64><<<g, 256, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-          else
-            hql_tridiag_rw1_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-        } else if (d <= 64) {
-          const int k1 = d - 32;
-          hql_tridiag_rw1_kernel<64><<<g, 256, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A32);
-          hql_tridiag_rw1_kernel<32><<<g, 128, 0, st>>>(32, d, k1, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-          ++*launches;
-        } else {
-          const int k1 = d - 64;
-          hql_tridiag_rw1_kernel<96><<<g, 384, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A64);
-          hql_tridiag_rw1_kernel<64><<<g, 256, 0, st>>>(64, d, k1, 32, nullptr, nullptr, nullptr, A64, dd_, ee_, vp_, ws.vcap, tt_, A32);
-          hql_tridiag_rw1_kernel<32><<<g, 128, 0, st>>>(32, d, k1 + 32, 32, nullptr, nullptr, nullptr, A32, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
-          *launches += 2;
-        }
-      } else {
+      {
       const unsigned g = (unsigned)n;
         if (d <= 32) {
           hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
@@ -275,17 +282,30 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   const bool use_tdc = o.tdc && o.use_reflect(d) && d > 32 && d <= 96;
   if (use_tdc) {
     ProfScope ps(prof, st, PH_EIGH_TDC);
+    // leaves: prepare (scale, tear, pad to 24) -> batched QL (thread per leaf) -> rotation replay (thread per row)
+    const int64_t nl = 4 * n;
+    tdc_prep_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(d, n, ws.dbuf[buf], ws.ebuf[buf], ws.l_hdr, ws.l_d, ws.l_e);
+    {
+      const size_t sm = hql_tql_smem(24, 32);
+      cudaFuncSetAttribute(hql_tql_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      hql_tql_kernel<32><<<(unsigned)((nl + 31) / 32), 32, sm, st>>>(24, nl, ws.l_d, ws.l_e, ws.l_lam, ws.l_perm, ws.l_rot,
+                                                                       EighWs::L_ROT_CAP, ws.l_swp, EighWs::L_SWP_CAP, ws.l_nswp,
+                                                                       status, 0, 24);
+      const size_t rsmem = hql_apply_reg_smem(24, 24, EighWs::L_SWP_CAP);
+      cudaFuncSetAttribute(hql_apply_reg_kernel<24, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      hql_apply_reg_kernel<24, 24><<<dim3((unsigned)nl, 1), 24, rsmem, st>>>(24, ws.l_rot, EighWs::L_ROT_CAP, ws.l_swp,
+                                                                              EighWs::L_SWP_CAP, ws.l_nswp, ws.l_Z);
+    }
     if (d <= 64) {
       const size_t sm = TdcGeom<64>::smem_bytes;
       cudaFuncSetAttribute(tdc_merge_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      tdc_leaf_kernel<64><<<(unsigned)n, 128, 0, st>>>(d, ws.dbuf[buf], ws.ebuf[buf], ws.tdc_rec, status);
-      tdc_merge_kernel<64><<<(unsigned)n, TdcGeom<64>::NT, sm, st>>>(d, ws.tdc_rec, lam, ws.Zt);
+      tdc_merge_kernel<64><<<(unsigned)n, TdcGeom<64>::NT, sm, st>>>(d, ws.l_hdr, ws.l_lam, ws.l_Z, lam, ws.Zt);
     } else {
       const size_t sm = TdcGeom<96>::smem_bytes;
       cudaFuncSetAttribute(tdc_merge_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      tdc_leaf_kernel<96><<<(unsigned)n, 128, 0, st>>>(d, ws.dbuf[buf], ws.ebuf[buf], ws.tdc_rec, status);
-      tdc_merge_kernel<96><<<(unsigned)n, TdcGeom<96>::NT, sm, st>>>(d, ws.tdc_rec, lam, ws.Zt);
+      tdc_merge_kernel<96><<<(unsigned)n, TdcGeom<96>::NT, sm, st>>>(d, ws.l_hdr, ws.l_lam, ws.l_Z, lam, ws.Zt);
     }
+    *launches += 2;
     *launches += 2;
   }
   if (!use_tdc) {
@@ -355,12 +375,14 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
       if (d <= 64) {
         const size_t sm = BackWyGeom<64>::smem_bytes;
         cudaFuncSetAttribute(hql_backwy_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_tfactor_kernel<64><<<(unsigned)n, 256, 0, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
+        cudaFuncSetAttribute(hql_tfactor_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BackWyGeom<64>::tf_smem_bytes);
+        hql_tfactor_kernel<64><<<(unsigned)n, 256, BackWyGeom<64>::tf_smem_bytes, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
         hql_backwy_kernel<64, 2><<<(unsigned)(2 * n), 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.Timg, U);
       } else {
         const size_t sm = BackWyGeom<96>::smem_bytes;
         cudaFuncSetAttribute(hql_backwy_kernel<96, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hql_tfactor_kernel<96><<<(unsigned)n, 384, 0, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
+        cudaFuncSetAttribute(hql_tfactor_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BackWyGeom<96>::tf_smem_bytes);
+        hql_tfactor_kernel<96><<<(unsigned)n, 384, BackWyGeom<96>::tf_smem_bytes, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
         hql_backwy_kernel<96, 2><<<(unsigned)(2 * n), 192, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.Timg, U);
       }
       ++*launches;

@@ -47,36 +47,6 @@ struct TdcGeom {
       + (size_t)D * sizeof(tdc::RotRec)    // rots
       + (size_t)D                          // flag
       + 64 * sizeof(double);               // per-merge scalars
-  // leaf kernel output per matrix: header (orgnrm, beta[1..3]) + D scaled leaf eigenvalues + 4 leaf blocks
-  static constexpr int LEAF_HDR = 8;
-  static constexpr int LEAF_REC = LEAF_HDR + D + 4 * TDC_LEAF_MAX * TDC_LEAF_MAX;  // doubles
-};
-
-struct TdcRows {  // one lane = one row of the leaf's eigenvector block (tdc::leaf_ql)
-  double *base;   // element (row, column j) at base[j * ld]
-  int ld;
-  bool active;
-  double f, cur, nxt;
-  __device__ __forceinline__ void begin(int m) {
-    if (active) {
-      f = base[m * ld];
-      cur = base[(m - 1) * ld];
-    }
-  }
-  __device__ __forceinline__ void load(int j) {
-    if (active) nxt = base[j * ld];
-  }
-  __device__ __forceinline__ void rot(int j, double cx, double cy) {
-    if (active) {
-      const double a = cur;
-      base[(j + 1) * ld] = cx * f - cy * a;
-      f = fma(cy, f, cx * a);
-      cur = nxt;
-    }
-  }
-  __device__ __forceinline__ void end(int l) {
-    if (active) base[l * ld] = f;
-  }
 };
 
 struct QuadGroup {  // four adjacent lanes share one root (tdc_core.cuh)
@@ -97,76 +67,56 @@ struct QuadGroup {  // four adjacent lanes share one root (tdc_core.cuh)
 };
 
 // ---------------------------------------------------------------------------------------
-// Leaves.  One CTA (4 warps) per matrix: scale to unit max-norm (dstedc), tear, QL per leaf.
+// Leaves.  tdc_prep_kernel scales the matrix to unit max-norm (dstedc), tears it and writes the four
+// leaves as a batch of 4 n independent 24 x 24 tridiagonal problems (smaller leaves are padded with
+// decoupled zero rows), which the batched QL kernels solve: hql_tql_kernel (one THREAD per leaf: 32
+// scalar chains per warp instruction, rotations recorded) + hql_apply_reg_kernel<24> (one thread
+// per eigenvector row, rows in registers).  A first version ran the QL chain redundantly in every
+// lane of one warp per leaf and updated the rows in shared memory: 126 instructions per rotation per
+// WARP, 257 k warp instructions per matrix, 5.7 ms at C5 (FP64 pipe 53 %, issue bound).
 // ---------------------------------------------------------------------------------------
-template <int D>
 __global__ void __launch_bounds__(128)
-tdc_leaf_kernel(int d, const double *__restrict__ din, const double *__restrict__ ein, double *__restrict__ rec,
-                int *__restrict__ status) {
-  using G = TdcGeom<D>;
+tdc_prep_kernel(int d, int64_t n, const double *__restrict__ din, const double *__restrict__ ein,
+                double *__restrict__ hdr, double *__restrict__ dleaf, double *__restrict__ eleaf) {
   constexpr int LM = TDC_LEAF_MAX;
-  __shared__ double Dv[D], E[D], Zl[4][LM * LM];  // leaf block q: element (row r, column j) at Zl[q][j * LM + r]
-  __shared__ double s_scale;
-  __shared__ int bnd[5];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t mat = blockIdx.x;
-  double *out = rec + mat * G::LEAF_REC;
-  for (int i = tid; i < D; i += 128) {
-    Dv[i] = i < d ? din[mat * d + i] : 0.0;
-    E[i] = i < d - 1 ? ein[mat * d + i] : 0.0;
-  }
-  for (int i = tid; i < 4 * LM * LM; i += 128) (&Zl[0][0])[i] = 0.0;
-  if (tid == 0) tdc::leaf_bounds(d, bnd);
-  __syncthreads();
-  if (warp == 0) {
-    double mx = 0.0;
-    for (int i = lane; i < d; i += 32) mx = fmax(mx, fmax(fabs(Dv[i]), fabs(E[i])));
+  const int lane = threadIdx.x & 31;
+  const int64_t mat = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);  // one warp per matrix
+  if (mat >= n) return;
+  const double *dd = din + mat * d, *ee = ein + mat * d;
+  double mx = 0.0;
+  for (int i = lane; i < d; i += 32) mx = fmax(mx, fmax(fabs(dd[i]), i < d - 1 ? fabs(ee[i]) : 0.0));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) s_scale = mx;
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const double scl = mx > 0.0 ? 1.0 / mx : 1.0;
+  int bnd[5];
+  tdc::leaf_bounds(d, bnd);
+  double beta[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int q = 1; q <= 3; ++q) {
+    const int m = bnd[q];
+    if (m > 0 && m < d && bnd[q] > bnd[q - 1]) beta[q] = ee[m - 1] * scl;
   }
-  __syncthreads();
-  const double orgnrm = s_scale;
-  {
-    const double scl = orgnrm > 0.0 ? 1.0 / orgnrm : 1.0;
-    for (int i = tid; i < D; i += 128) {
-      Dv[i] *= scl;
-      E[i] *= scl;
-    }
+  if (lane == 0) {
+    hdr[mat * 4 + 0] = mx;
+    hdr[mat * 4 + 1] = beta[1];
+    hdr[mat * 4 + 2] = beta[2];
+    hdr[mat * 4 + 3] = beta[3];
   }
-  __syncthreads();
-  if (tid == 0) {
-    out[0] = orgnrm;
-    for (int q = 1; q <= 3; ++q) {
-      const int m = bnd[q];
-      double beta = 0.0;
-      if (m > 0 && m < d && bnd[q] > bnd[q - 1]) {
-        beta = E[m - 1];
-        Dv[m - 1] -= fabs(beta);
-        Dv[m] -= fabs(beta);
-        E[m - 1] = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int o = bnd[q], nq = bnd[q + 1] - bnd[q];
+    if (lane < LM) {
+      double dv = 0.0, ev = 0.0;
+      if (lane < nq) {
+        dv = dd[o + lane] * scl;
+        if (lane == 0 && q > 0) dv -= fabs(beta[q]);           // first row of the leaf: tear above
+        if (lane == nq - 1 && q < 3) dv -= fabs(beta[q + 1]);  // last row: tear below
+        if (lane < nq - 1) ev = ee[o + lane] * scl;
       }
-      out[q] = beta;
+      dleaf[(mat * 4 + q) * LM + lane] = dv;
+      eleaf[(mat * 4 + q) * LM + lane] = ev;
     }
   }
-  __syncthreads();
-  {
-    const int o = bnd[warp], n = bnd[warp + 1] - bnd[warp];
-    if (n > 0) {
-      if (lane < n) Zl[warp][lane * LM + lane] = 1.0;
-      __syncwarp();
-      TdcRows rows;
-      rows.base = &Zl[warp][lane];
-      rows.ld = LM;
-      rows.active = lane < n;
-      rows.f = rows.cur = rows.nxt = 0.0;
-      const bool ok = tdc::leaf_ql(n, Dv + o, E + o, rows);
-      if (!ok && lane == 0) atomicMax(status, 1);
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < D; i += 128) out[G::LEAF_HDR + i] = Dv[i];
-  for (int i = tid; i < 4 * LM * LM; i += 128) out[G::LEAF_HDR + D + i] = (&Zl[0][0])[i];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -174,7 +124,8 @@ tdc_leaf_kernel(int d, const double *__restrict__ din, const double *__restrict_
 // ---------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(4 * D, 2)
-tdc_merge_kernel(int d, const double *__restrict__ rec, double *__restrict__ lam, double *__restrict__ Zt) {
+tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict__ lamleaf,
+                 const double *__restrict__ Zleaf, double *__restrict__ lam, double *__restrict__ Zt) {
   using G = TdcGeom<D>;
   constexpr int LD = G::LD, NT = G::NT, NB = D / 8, LM = TDC_LEAF_MAX;
   extern __shared__ __align__(16) unsigned char tdc_smem[];
@@ -193,20 +144,23 @@ tdc_merge_kernel(int d, const double *__restrict__ rec, double *__restrict__ lam
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fm = lane >> 2, fj = lane & 3;
   const size_t mat = blockIdx.x;
-  const double *in = rec + mat * G::LEAF_REC;
 
-  // ---- load the leaves: eigenvalues, eigenvector blocks on the diagonal of QsT ----
+  // ---- load the leaves: eigenvalues, eigenvector blocks (row-major [r][c]) onto the diagonal of QsT ----
   for (int i = tid; i < D * LD; i += NT) QsT[i] = 0.0;
   if (tid == 0) tdc::leaf_bounds(d, bnd);
-  if (tid < 4) m_beta[tid] = in[tid];  // [0] = orgnrm, [1..3] = beta of the tears
-  if (tid < D) Dv[tid] = in[G::LEAF_HDR + tid];
+  if (tid < 4) m_beta[tid] = hdr[mat * 4 + tid];  // [0] = orgnrm, [1..3] = beta of the tears
   __syncthreads();
   const double orgnrm = m_beta[0];
+  if (tid < d) {
+    int q = 0;
+    while (q < 3 && tid >= bnd[q + 1]) ++q;
+    Dv[tid] = lamleaf[(mat * 4 + q) * LM + (tid - bnd[q])];
+  }
   for (int i = tid; i < 4 * LM * LM; i += NT) {
     const int q = i / (LM * LM), rem = i - q * LM * LM;
-    const int j = rem / LM, r = rem - j * LM;
-    const int o = bnd[q], n = bnd[q + 1] - bnd[q];
-    if (j < n && r < n) QsT[(o + j) * LD + o + r] = in[G::LEAF_HDR + D + i];
+    const int r = rem / LM, c = rem - r * LM;
+    const int o = bnd[q], nq = bnd[q + 1] - bnd[q];
+    if (r < nq && c < nq) QsT[(o + c) * LD + o + r] = Zleaf[(mat * 4 + q) * LM * LM + rem];
   }
 
   QuadGroup grp;

@@ -184,8 +184,6 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->eo.tridiag_fused = value != 0;
   else if (!strcmp(key, "small24"))
     h->eo.small24 = value != 0;
-  else if (!strcmp(key, "tridiag_one"))  // 0: two-barrier register tridiagonalisation (eigh_tridiag_rw.cuh)
-    h->eo.tridiag_one = value != 0;
   else if (!strcmp(key, "tridiag_rw"))  // 0: shared-memory tridiagonalisation kernel
     h->eo.tridiag_rw = value != 0;
   else if (!strcmp(key, "reflect"))  // 0: form Q in the tridiagonalisation kernel + GEMM back-transformation
