@@ -390,3 +390,56 @@ class ConfigTable:
             raise ValueError("times must be an array of values in microseconds")
         full = out.reshape(self._slot_shape + (out.shape[1],))
         return np.moveaxis(full, -1, self._t_pos).reshape(self.results_shape)
+
+    # ---- output side (simconfig.py:370-429) ----------------------------------------------
+    def _print_value(self, key, idx):
+        """Header text of one file-range value (the reference's _print_B / _print_orient, simconfig.py:638-647)."""
+        v = self._vals[key][idx]
+        if key == "B":
+            return "{0} T".format(np.asarray(v))
+        if key == "orient":
+            a, b, c = quat_to_zyz(v)
+            return "[ZYZ] a = {0:.1f} deg, b = {1:.1f} deg, c = {2:.1f} deg, weight = {3}".format(
+                np.degrees(a), np.degrees(b), np.degrees(c), self._ow[idx])
+        return np.asarray(v) if np.ndim(v) else float(v)
+
+    def save_output(self, results, name=None, path=".", extension=".dat"):
+        """Write one two-column file per file-range index tuple, `<name>[_i[_j...]].dat`, with the
+        reference's header; the x column is |B| when the x axis is a field.  Returns the file names."""
+        import datetime
+        import os
+        from itertools import product
+
+        from .constants import REFERENCE_VERSION
+
+        results = np.asarray(results)
+        if results.shape != self.results_shape:
+            raise ValueError("results do not have the shape of this configuration")
+        if name is None:
+            name = (self.spec or {}).get("name", "muspinsim")
+        header = "MUSPINSIM v.{0}\nOutput file written on {1}\nParameters used:\n".format(
+            REFERENCE_VERSION, datetime.datetime.now().ctime())
+        x = np.asarray(self.x_axis_values)
+        if self.x_name in ("B", "intrinsic_B"):
+            x = np.linalg.norm(x, axis=-1)
+        written = []
+        keys = list(self.file_ranges.keys())
+        for inds in product(*[range(n) for n in self.file_ranges.values()]):
+            fname = os.path.join(path, "{0}{1}{2}".format(name, "".join("_%d" % i for i in inds), extension))
+            hdr = header + "".join("\t{0:<20} = {1}\n".format(k, self._print_value(k, i)) for k, i in zip(keys, inds))
+            data = np.zeros((len(x), 2))
+            data[:, 0] = x
+            data[:, 1] = results[inds]
+            np.savetxt(fname, data, header=hdr)
+            written.append(fname)
+        return written
+
+
+def quat_to_zyz(q):
+    """Euler angles (a, b, c) with q = q_z(c) q_y(b) q_z(a) (ase Quaternion.euler_angles('zyz'))."""
+    R = quat_rotation_matrices(np.asarray(q, dtype=float)[None])[0]
+    b = np.arccos(np.clip(R[2, 2], -1.0, 1.0))
+    if abs(np.sin(b)) > 1e-12:
+        return np.arctan2(R[2, 1], -R[2, 0]), b, np.arctan2(R[1, 2], R[0, 2])
+    a = np.arctan2(R[1, 0], R[0, 0]) if R[2, 2] > 0 else np.arctan2(-R[1, 0], -R[0, 0])
+    return a, b, 0.0

@@ -76,3 +76,6 @@ def spin(elem="mu", iso=None):
             raise ValueError(f"Invalid multiplicity {iso} for electron")
         return 0.5 * int(iso)
     return _iso(elem, iso)[2]
+
+# version string the reference writes into its .dat headers (muspinsim/version.py:5)
+REFERENCE_VERSION = "2.3.1"

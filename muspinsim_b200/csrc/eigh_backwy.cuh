@@ -65,7 +65,7 @@ struct BackWyGeom {
 // 15 warps per issue (profiles/r2_ncu_k4.md).
 // ---------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(4 * D)
+__global__ void __launch_bounds__(4 * D, 2)
 hql_tfactor_kernel(int d, const cplx *__restrict__ Vp, size_t vcap, const cplx *__restrict__ tau,
                    double *__restrict__ Timg) {
   using G = BackWyGeom<D>;

@@ -44,8 +44,9 @@ struct TdcGeom {
       (size_t)D * LD * sizeof(double)      // QsT
       + 13 * (size_t)D * sizeof(double)    // Dv zv sD sZ nd zk wgt mu dorg zh sn lamn fin
       + 4 * (size_t)D * sizeof(int)        // sidx ncol orgi dest
+      + 2 * (size_t)(D + 16) * sizeof(int) // red: one region per concurrent merge (group padding: up to 9 extra entries)
       + (size_t)D * sizeof(tdc::RotRec)    // rots
-      + (size_t)D                          // flag
+      + 2 * (size_t)D                      // flag kind
       + 64 * sizeof(double);               // per-merge scalars
 };
 
@@ -133,13 +134,16 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
   double *Dv = QsT + D * LD, *zv = Dv + D, *sD = zv + D, *sZ = sD + D, *nd = sZ + D, *zk = nd + D, *wgt = zk + D, *mu = wgt + D,
          *dorg = mu + D, *zh = dorg + D, *sn = zh + D, *lamn = sn + D, *fin = lamn + D;
   double *scal = fin + D;
-  int *sidx = reinterpret_cast<int *>(scal + 64), *ncol = sidx + D, *orgi = ncol + D, *dest = orgi + D;
-  tdc::RotRec *rots = reinterpret_cast<tdc::RotRec *>(dest + D);
+  int *sidx = reinterpret_cast<int *>(scal + 64), *ncol = sidx + D, *orgi = ncol + D, *dest = orgi + D, *red = dest + D;
+  constexpr int RED = D + 16;  // stride of a merge slot's reduction list
+  tdc::RotRec *rots = reinterpret_cast<tdc::RotRec *>(red + 2 * RED);
   unsigned char *flag = reinterpret_cast<unsigned char *>(rots + D);
+  unsigned char *kind = flag + D;  // support of a column of Q: 0 top block only, 1 bottom block only, 2 both (after a deflation rotation)
   // per-merge scalars (slot m = 0, 1): rho, tol; beta[1..3]; ints: k, skip, anyclose, nrot
   double *m_rho = scal, *m_tol = scal + 2, *m_beta = scal + 4;
   int *m_k = reinterpret_cast<int *>(scal + 16), *m_skip = m_k + 2, *m_close = m_k + 4, *m_nrot = m_k + 6;
   int *bnd = m_k + 8;  // [5]
+  int *m_k0 = m_k + 16, *m_k1 = m_k + 18;  // survivors supported on the top / bottom block only
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fm = lane >> 2, fj = lane & 3;
@@ -197,6 +201,7 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
       const double beta = (level == 2) ? m_beta[2] : (mslot == 0 ? m_beta[1] : m_beta[3]);
       const double sg = beta < 0.0 ? -1.0 : 1.0;
       zv[tid] = (tid < mid ? QsT[tid * LD + mid - 1] : sg * QsT[tid * LD + mid]) * 0.70710678118654752440;
+      kind[tid] = tid < mid ? 0 : 1;
       if (tid == lo) {
         m_rho[mslot] = 2.0 * fabs(beta);
         m_close[mslot] = 0;
@@ -243,7 +248,12 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
     __syncthreads();
     // P4: the scan itself (one thread per merge; rare), then the rotations on the columns of Q
     if (mine && !skip && tid == lo && m_close[mslot]) {
-      m_nrot[mslot] = tdc::deflate_scan(n, sD + lo, sZ + lo, flag + lo, m_tol[mslot], rots + lo);
+      const int nr = tdc::deflate_scan(n, sD + lo, sZ + lo, flag + lo, m_tol[mslot], rots + lo);
+      m_nrot[mslot] = nr;
+      for (int r = 0; r < nr; ++r) {  // a rotation between the blocks makes both columns dense
+        const int cp = sidx[lo + rots[lo + r].p], cq = sidx[lo + rots[lo + r].q];
+        if (kind[cp] != kind[cq]) kind[cp] = kind[cq] = 2;
+      }
     }
     __syncthreads();
     if (mine && !skip) {
@@ -270,7 +280,37 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
       zk[lo + i] = sZ[tid];
       wgt[lo + i] = m_rho[mslot] * sZ[tid] * sZ[tid];
       ncol[lo + i] = sidx[tid];
-      if (tid == lo) m_k[mslot] = k;
+      // reduction order of the GEMM: survivors grouped by support [top | bottom | both], every group
+      // padded to whole k-chunks of 4 (entry -1): a chunk then touches only the row tiles of its block
+      int k0 = 0, k1 = 0, b0 = 0, b1 = 0, b2 = 0;
+      for (int q = lo; q < hi; ++q) {
+        if (flag[q]) continue;
+        const int kd = kind[sidx[q]];
+        k0 += kd == 0;
+        k1 += kd == 1;
+        if (q < tid) {
+          b0 += kd == 0;
+          b1 += kd == 1;
+          b2 += kd == 2;
+        }
+      }
+      const int p0 = (k0 + 3) & ~3, p1 = (k1 + 3) & ~3, p2 = (k - k0 - k1 + 3) & ~3;
+      if (surv) {
+        const int kd = kind[sidx[tid]];
+        red[mslot * RED + (kd == 0 ? b0 : (kd == 1 ? p0 + b1 : p0 + p1 + b2))] = i;
+      }
+      // padding entries (at most 3 per group), written by the first threads of the merge
+      {
+        const int t3 = tid - lo;
+        if (t3 < p0 - k0) red[mslot * RED + k0 + t3] = -1;
+        if (t3 < p1 - k1) red[mslot * RED + p0 + k1 + t3] = -1;
+        if (t3 < p2 - (k - k0 - k1)) red[mslot * RED + p0 + p1 + (k - k0 - k1) + t3] = -1;
+      }
+      if (tid == lo) {
+        m_k[mslot] = k;
+        m_k0[mslot] = k0;
+        m_k1[mslot] = k1;
+      }
     }
     __syncthreads();
     // quad g owns root / entry g of the merge that contains g
@@ -282,7 +322,7 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
     // P6: secular roots
     if (gact && gj < gk) {
       double m_;
-      const int og = tdc::secular_root(gk, nd + glo, zk + glo, wgt + glo, m_rho[gslot], gj, &m_, grp);
+      const int og = tdc::secular_root(gk, nd + glo, wgt + glo, gj, &m_, grp);
       if (grp.p == 0) {
         mu[g] = m_;
         orgi[g] = og;
@@ -317,20 +357,23 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
       const int jb = 8 * warp + fm;  // B operand's output column
       const bool jv = (jb - wlo) < wk && jb < whi;
       const double s_j = jv ? sn[jb] : 0.0, mu_j = jv ? mu[jb] : 0.0, do_j = jv ? dorg[jb] : 0.0;
-      const int tlo = wlo >> 3, thi = (whi + 7) >> 3;
-      const int nchunk = (wk + 3) >> 2;
-      for (int q = 0; q < nchunk; ++q) {
-        const int i = 4 * q + fj;
+      const int tlo = wlo >> 3, tmid = wmid >> 3, thi = (whi + 7) >> 3;
+      const int c0 = (m_k0[wslot] + 3) >> 2, c1 = (m_k1[wslot] + 3) >> 2;
+      const int c2 = (wk - m_k0[wslot] - m_k1[wslot] + 3) >> 2;
+      for (int q = 0; q < c0 + c1 + c2; ++q) {
+        // chunk of the top group: row tiles [tlo, tmid); bottom group: [tmid, thi); dense columns: all
+        const int ta = (q >= c0 && q < c0 + c1) ? tmid : tlo, tb = (q < c0) ? tmid : thi;
+        const int i = red[wslot * RED + 4 * q + fj];
         double bval = 0.0;
         int acol = wlo;
-        if (i < wk) {
+        if (i >= 0) {
           acol = ncol[wlo + i];
           if (jv) bval = zh[wlo + i] * s_j * TDC_RCP((nd[wlo + i] - do_j) - mu_j);
         }
         const double *ap = QsT + acol * LD + fm;
 #pragma unroll
         for (int t = 0; t < NB; ++t)
-          if (t >= tlo && t < thi) dmma884(acc[t][0], acc[t][1], ap[8 * t], bval);
+          if (t >= ta && t < tb) dmma884(acc[t][0], acc[t][1], ap[8 * t], bval);
       }
       // deflated columns are copied
 #pragma unroll

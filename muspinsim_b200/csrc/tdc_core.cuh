@@ -65,7 +65,7 @@ struct SerialGroup {
 };
 
 #if defined(TDC_STATS) && !defined(__CUDA_ARCH__)
-static long g_sec_outer = 0, g_sec_inner = 0, g_sec_roots = 0;  // host-only iteration counters (tests)
+static long g_sec_outer = 0, g_sec_inner = 0, g_sec_roots = 0, g_sec_hist[32] = {0};  // host-only iteration counters (tests)
 #define TDC_COUNT(x) (++(x))
 #else
 #define TDC_COUNT(x) ((void)0)
@@ -227,92 +227,138 @@ TDC_HD bool leaf_ql(int n, double *D, double *E, Rows &rows) {
   return true;
 }
 
-// Root j (0-based, ascending) of 1 + rho sum_i z_i^2 / (dk_i - lambda) = 0 for strictly increasing
-// dk[0..k), non-zero zk, rho > 0.  Returns the index `org` of the pole nearest to the root and
-// *mu = lambda - dk[org]; dk_i - lambda must then be formed as (dk_i - dk_org) - mu.
+// Root j (0-based, ascending) of g(lambda) = 1 + sum_i w_i / (dk_i - lambda) = 0, w_i = rho z_i^2, for
+// strictly increasing dk[0..k), non-zero z, rho > 0.  Returns the index `org` of the pole nearest to
+// the root and *mu = lambda - dk[org]; dk_i - lambda must then be formed as (dk_i - dk_org) - mu.
+//
+// Iteration ("middle way", Li 1994 / LAPACK dlaed4): with L, R the poles that bracket the root,
+// psi = sum_{i <= L}, phi = sum_{i >= R} are each replaced by a one-pole model that matches value
+// and slope at the current point,
+//     psi(x) ~ r_L + s / (d_L - x),  s = (d_L - mu)^2 psi'(mu),      phi(x) ~ r_R + S / (d_R - x),
+// and the resulting quadratic is solved in closed form for the step eta -- no inner iteration: every
+// pass is ONE sweep over the poles (4 interleaved reciprocal chains per lane on the device) plus a
+// fixed ~60-instruction tail.  A first version refined a two-pole + linear model by Newton steps:
+// 4.4 serial inner steps of ~80 dependent instructions per pass were half of the merge kernel.
+// Safeguards: a sign bracket [lo, hi] on g (bisection if the model step leaves it), stop when
+// |g| is within its rounding error bound, when the bracket collapses, or when the step is below
+// 2e-9 |mu| (quadratic convergence: the next error is below an ulp).
 template <class Group>
-TDC_HD int secular_root(int k, const double *dk, const double *zk, const double *wk, double rho, int j,
-                        double *mu_out, const Group &grp) {
-  // wk[i] = rho zk[i]^2 (precomputed once per merge)
+TDC_HD int secular_root(int k, const double *dk, const double *wk, int j, double *mu_out, const Group &grp) {
   if (k == 1) {
     *mu_out = wk[0];
     return 0;
   }
   const bool last = (j == k - 1);
-  const int L = j, R = last ? j : j + 1;
-  const double a = wk[L], b = last ? 0.0 : wk[R];
-  const double half = last ? 0.0 : 0.5 * (dk[R] - dk[L]);
-  int org = L;
-  double lo = 0.0, hi, mu;
+  const int L = last ? k - 2 : j, R = L + 1;  // the last root lies to the right of both of its poles
+  const double gap = dk[R] - dk[L];
+  int org;
+  double dL, dR, lo, hi, mu;
   if (!last) {
-    hi = half;
-    mu = half;  // first evaluation at the midpoint, in the frame of the left pole; it also picks the frame
+    org = L;  // first evaluation at the midpoint, in the frame of the left pole; it also picks the frame
+    dL = 0.0;
+    dR = gap;
+    lo = 0.0;
+    hi = 0.5 * gap;
+    mu = hi;
   } else {
+    org = R;
+    dL = -gap;
+    dR = 0.0;
     double s = 0.0;
-    for (int i = 0; i < k; ++i) s += zk[i] * zk[i];
-    hi = rho * s;  // lambda_max <= dk[k-1] + rho |z|^2
+    for (int i = 0; i < k; ++i) s += wk[i];
+    lo = 0.0;
+    hi = s;  // lambda_max <= dk[k-1] + rho |z|^2
     mu = 0.5 * hi;
   }
-  double dorg = dk[L];
-  double dL = 0.0, dR = dk[R] - dk[L];
+  double dorg = dk[org];
   TDC_COUNT(g_sec_roots);
-  for (int it = 0; it < 80; ++it) {
+  for (int it = 0; it < 60; ++it) {
     TDC_COUNT(g_sec_outer);
-    double c0 = 0.0, c1 = 0.0, asum = 0.0;
-#pragma unroll 4
-    for (int i = grp.part(); i < k; i += Group::P) {
-      // straight-line body: the two neighbouring poles (treated exactly below) get weight 0; their
-      // distances (dk_i - dorg) - mu are never 0 inside the bracket, so the reciprocal is finite
-      const double wi = (i == L || i == R) ? 0.0 : wk[i];
-      const double rdel = TDC_RCP((dk[i] - dorg) - mu);
-      const double t = wi * rdel;
-      c0 += t;
-      c1 = fma(t, rdel, c1);
-      asum += fabs(t);
+    // one sweep over the poles, left part (i <= L: psi) and right part (i >= R: phi) separately
+    double t0 = 0.0, dpsi = 0.0, dphi = 0.0, asum = 0.0;
+    {
+      const int p = grp.part();
+      // first index >= R with the residue of this lane
+      const int iR = R + ((p - R) % Group::P + Group::P) % Group::P;
+#pragma unroll 8
+      for (int i = p; i <= L; i += Group::P) {
+        const double rdel = TDC_RCP((dk[i] - dorg) - mu);
+        const double t = wk[i] * rdel;
+        t0 += t;
+        dpsi = fma(t, rdel, dpsi);
+        asum += fabs(t);
+      }
+#pragma unroll 8
+      for (int i = iR; i < k; i += Group::P) {
+        const double rdel = TDC_RCP((dk[i] - dorg) - mu);
+        const double t = wk[i] * rdel;
+        t0 += t;
+        dphi = fma(t, rdel, dphi);
+        asum += fabs(t);
+      }
     }
-    c0 = grp.sum(c0);
-    c1 = grp.sum(c1);
+    t0 = grp.sum(t0);
+    dpsi = grp.sum(dpsi);
+    dphi = grp.sum(dphi);
     asum = grp.sum(asum);
-    const double pL = a / (dL - mu), pR = last ? 0.0 : b / (dR - mu);
-    const double g = 1.0 + c0 + pL + pR;
+    const double g = 1.0 + t0;
     if (it == 0 && !last && g < 0.0) {
-      // root in the right half: continue in the frame of the right pole, mu in [-half, 0).  The
+      // root in the right half: continue in the frame of the right pole, mu in [-gap/2, 0).  The
       // quantities just evaluated are frame independent (dk_i - lambda is the same point).
       org = R;
       dorg = dk[R];
-      dL = dk[L] - dk[R];
+      dL = -gap;
       dR = 0.0;
-      mu = -half;
-      lo = -half;
+      mu = -0.5 * gap;
+      lo = mu;
       hi = 0.0;
     }
-    const double err = 8.0 * EPS * (1.0 + asum + fabs(pL) + fabs(pR));
+    const double err = 8.0 * EPS * (1.0 + asum);
     if (fabs(g) <= err) break;
     if (g < 0.0)
       lo = mu;
     else
       hi = mu;
     if (hi - lo <= 2.0 * EPS * fmax(fabs(lo), fabs(hi))) break;
-    // model h(x) = C0 + c1 (x - mu) + a / (dL - x) + b / (dR - x): exact in the two neighbouring poles,
-    // first order in the rest; increasing on the interval -> safeguarded Newton inside (lo, hi)
-    const double C0 = 1.0 + c0;
-    double x = mu;
-    for (int in = 0; in < 12; ++in) {
-      TDC_COUNT(g_sec_inner);
-      const double eL = dL - x, eR = dR - x;
-      const double rL = 1.0 / eL, rR = last ? 0.0 : 1.0 / eR;
-      const double h = C0 + c1 * (x - mu) + a * rL + b * rR;
-      const double hp = c1 + a * rL * rL + b * rR * rR;
-      double xn = x - h / hp;
-      if (!(xn > lo)) xn = 0.5 * (x + lo);
-      if (!(xn < hi)) xn = 0.5 * (x + hi);
-      const bool done = fabs(xn - x) <= 4.0 * EPS * fabs(xn);
-      x = xn;
-      if (done) break;
+    // quadratic for the step eta:  c eta^2 - (c (DL + DR) + s + S) eta + DL DR g = 0
+    const double DL = dL - mu, DR = dR - mu;
+    double sL = DL * DL * dpsi, sR = DR * DR * dphi;
+    double c = g - DL * dpsi - DR * dphi;
+    if (it == 0) {
+      // initial guess (dlaed4): the two neighbouring poles with their TRUE weights, the rest constant
+      sL = wk[L];
+      sR = wk[R];
+      c = g - sL / DL - sR / DR;
     }
-    if (x == mu) break;
+    const double Bq = -(c * (DL + DR) + sL + sR), Cq = DL * DR * g;
+    double disc = Bq * Bq - 4.0 * c * Cq;
+    disc = disc > 0.0 ? sqrt(disc) : 0.0;
+    const double q = -0.5 * (Bq + (Bq >= 0.0 ? disc : -disc));
+    // the two roots q / c and Cq / q; the wanted one keeps x strictly inside the bracket
+    const double e1 = (c != 0.0) ? q / c : 0.0, e2 = (q != 0.0) ? Cq / q : 0.0;
+    const double x1 = mu + e1, x2 = mu + e2;
+    const bool ok1 = (c != 0.0) && x1 > lo && x1 < hi, ok2 = (q != 0.0) && x2 > lo && x2 < hi;
+    double x;
+    if (ok1 && ok2)
+      x = fabs(e1) < fabs(e2) ? x1 : x2;
+    else if (ok1)
+      x = x1;
+    else if (ok2)
+      x = x2;
+    else
+      x = 0.5 * (lo + hi);
+    const bool small_step = fabs(x - mu) <= 2.0e-9 * fabs(x);
     mu = x;
+    if (small_step) break;
   }
+#if defined(TDC_STATS) && !defined(__CUDA_ARCH__)
+  {
+    static thread_local long last_outer = 0;
+    long n_it = g_sec_outer - last_outer;
+    last_outer = g_sec_outer;
+    ++g_sec_hist[n_it < 31 ? n_it : 31];
+  }
+#endif
   *mu_out = mu;
   return org;
 }

@@ -116,7 +116,7 @@ void merge(int lo, int mid, int hi, double beta, double *D, double *QT, int ld, 
   for (int i = 0; i < k; ++i) wk[i] = rho * zk[i] * zk[i];
   std::vector<int> org(k);
   for (int j = 0; j < k; ++j) {
-    org[j] = secular_root(k, dk.data(), zk.data(), wk.data(), rho, j, &mu[j], SerialGroup());
+    org[j] = secular_root(k, dk.data(), wk.data(), j, &mu[j], SerialGroup());
     lamn[j] = dk[org[j]] + mu[j];
   }
   for (int i = 0; i < k; ++i) zh[i] = zhat(k, dk.data(), mu.data(), org.data(), rho, i, zk[i], SerialGroup());
@@ -199,5 +199,6 @@ extern "C" void tdc_host_counters(long *out) {
   out[0] = g_sec_roots;
   out[1] = g_sec_outer;
   out[2] = g_sec_inner;
+  for (int i = 0; i < 32; ++i) out[3 + i] = g_sec_hist[i];
 }
 #endif

@@ -51,6 +51,7 @@ class ExperimentRunner:
         self._handle = None
         self._handle_cache = handle_cache
         self.results = None
+        self._results_function = (spec or {}).get("results_function") if spec is not None else None
         self.options = {}
         self.device_expand = True  # expand the configuration table on the device when all configurations share a mode
 
@@ -187,5 +188,31 @@ class ExperimentRunner:
         out = self.run_partial(rank, size)
         if comm is not None:
             out = comm.sum_data(out)  # mpi.py:104-112
-        self.results = self._table.finish(out)
+        results = self._table.finish(out)
+        if self._results_function is not None:
+            results = self.apply_results_function(results)
+        self.results = results
         return self.results
+
+    # ---- output side (experiment.py:347-356, simconfig.py:370-429) -----------------------
+    def apply_results_function(self, results, variables=None):
+        """The reference evaluates the `results_function` expression of the input file with the
+        variables x (x-axis values) and y (results); here it is a callable f(x, y, **variables) or an
+        expression string evaluated with numpy's functions in scope."""
+        f = self._results_function
+        x = self._table.x_axis_values
+        if callable(f):
+            y = f(x, results, **(variables or {}))
+        else:
+            scope = {k: getattr(np, k) for k in ("exp", "sin", "cos", "tan", "sqrt", "log", "abs", "pi", "arcsin",
+                                                 "arccos", "arctan", "sinh", "cosh", "tanh")}
+            scope.update(variables or {})
+            scope.update(x=x, y=results)
+            y = eval(compile(str(f), "<results_function>", "eval"), {"__builtins__": {}}, scope)  # noqa: S307
+        return np.array(y, dtype=float).reshape(results.shape)
+
+    def save_output(self, name=None, path=".", extension=".dat"):
+        """Write the `.dat` files of the last run (MuSpinConfig.save_output, simconfig.py:370-429)."""
+        if self.results is None:
+            raise RuntimeError("run() has not been called")
+        return self._table.save_output(self.results, name=name, path=path, extension=extension)

@@ -265,3 +265,52 @@ def test_run_host_validates_array_lengths_and_slots():
         _lib.Handle.run_host(h, 1, B, B, np.zeros(3), np.ones(4), np.zeros(4, int), t, 1.0, out)  # len(T) != n
     with pytest.raises(ValueError):
         _lib.Handle.run_host(h, 1, B, B, np.zeros(4), np.ones(4), np.array([0, 1, 2, 0]), t, 1.0, out)  # slot >= n_slots
+
+
+@pytest.mark.parametrize("name", ["alc_T_filerange", "polarization_filerange", "time_averaged_vs_field", "c2_fast_d16"])
+def test_output_side_matches_the_reference_dat_files(name, tmp_path):
+    """ExperimentRunner.save_output writes the reference's files -- same names, same
+    two columns (|B| as x for field axes), same header apart from the date line (simconfig.py:370-429)."""
+    import os
+
+    from oracle import ref_driver
+
+    spec, want = load_golden(name)
+    r = ExperimentRunner(spec)
+    r._handle = OracleHandle(spec)
+    r.run()
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    files = r.save_output(name="out", path=str(ours))
+    assert len(files) == int(np.prod(r.config.results_shape[:-1])) and all(os.path.exists(f) for f in files)
+    for f in files:
+        data = np.loadtxt(f)
+        assert data.shape == (r.config.results_shape[-1], 2)
+    if not ref_driver.available():
+        return
+    theirs = tmp_path / "theirs"
+    theirs.mkdir()
+    rr = ref_driver.make_runner(spec)
+    rr.run()
+    rr.config.save_output(name="out", path=str(theirs))
+    assert sorted(os.listdir(ours)) == sorted(os.listdir(theirs))
+    for f in sorted(os.listdir(ours)):
+        a, b = np.loadtxt(ours / f), np.loadtxt(theirs / f)
+        assert a.shape == b.shape and np.max(np.abs(a - b)) < 1e-10
+        ha = [ln for ln in open(ours / f) if ln.startswith("#")]
+        hb = [ln for ln in open(theirs / f) if ln.startswith("#")]
+        assert len(ha) == len(hb)
+        for la, lb in zip(ha, hb):
+            if "written on" not in la:
+                assert la == lb
+
+
+def test_results_function_callable_and_expression():
+    """experiment.py:347-356: the results function sees x (x-axis values) and y (results)."""
+    spec, want = load_golden("c1_hfine")
+    for f in (lambda x, y: 2.0 * y * np.exp(-0.1 * x), "2*y*exp(-0.1*x)"):
+        r = ExperimentRunner(dict(spec, results_function=f))
+        r._handle = OracleHandle(spec)
+        got = r.run()
+        t = np.asarray(r.config.x_axis_values)
+        assert np.max(np.abs(got - 2.0 * want * np.exp(-0.1 * t))) < 1e-10
