@@ -160,6 +160,26 @@ int musim_fp64_peak(int device, int kind, double *tflops);
 
 const char *musim_last_error(musim_handle *h);
 int musim_destroy(musim_handle *h);
+/* Celio's method (Phys. Rev. Lett. 56, 2720): Trotter-split evolution of `n_states` state vectors and
+ * the muon polarisation <psi| sigma_mu (x) 1 |psi> at every time step, summed over the states into
+ * results[num_times] (+=).  Replaces the reference's C++ extension call
+ *     muspinsim.cpp.celio_evolve(num_times, psi, sigma_mu, half_dim, k, evol_contribs, results)
+ * (cpp/celio.cpp:23-69; gate application parallel.cpp:236-266, measurement parallel.cpp:130-168),
+ * which CelioHamiltonian._fast_evolve_cpp (celio.py:433-476) calls once per random initial state;
+ * here all states go in one call.  All pointers are HOST pointers.
+ *   psi        [n_states][dim] complex128, row-major
+ *   sigma_mu   [2][2] complex128 (Hermitian)
+ *   contribution c: matrix [mat_dim[c]][mat_dim[c]] complex128 (concatenated in `matrices`),
+ *                   other_dim[c] = dim / mat_dim[c], indices[c][dim] (Celio_EvolveContrib.indices)
+ *   flags      bit 0: force the streamed (global-memory) path also for small systems (cross-check)
+ * Returns 0, MUSIM_EINVAL, MUSIM_ECUDA or MUSIM_EUNSUP (a gate larger than 64 x 64). */
+int musim_celio_evolve(int device, int64_t dim, int n_states, const double *psi, const double *sigma_mu,
+                       int64_t half_dim, int k, int n_contrib, const int32_t *mat_dim, const int64_t *other_dim,
+                       const double *matrices, const int64_t *indices, int num_times, double *results, int flags);
+
+/* Kernel launches issued by musim_celio_evolve so far (process-wide). */
+int64_t musim_celio_launch_count(void);
+
 int musim_version(void);
 
 /* Number of CUDA devices visible to the process (0 if there is none): lets the reference-side

@@ -33,6 +33,8 @@ EXPORTS = [
     "musim_launch_count",
     "musim_phase_ms",
     "musim_fp64_peak",
+    "musim_celio_evolve",
+    "musim_celio_launch_count",
     "musim_device_count",
     "musim_last_error",
     "musim_destroy",
@@ -87,6 +89,10 @@ def load():
     lib.musim_phase_ms.restype = dbl
     lib.musim_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(dbl)]
     lib.musim_fp64_peak.restype = i32
+    lib.musim_celio_evolve.argtypes = [i32, i64, i32, vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp, i32]
+    lib.musim_celio_evolve.restype = i32
+    lib.musim_celio_launch_count.argtypes = []
+    lib.musim_celio_launch_count.restype = i64
     lib.musim_device_count.argtypes = []
     lib.musim_device_count.restype = i32
     lib.musim_last_error.argtypes = [vp]
@@ -256,6 +262,34 @@ def nufft_tables(nt):
     dec = np.zeros(int(nt))
     lib.musim_nufft_tables(int(nt), None, None, None, coef.ctypes.data, dec.ctypes.data)
     return M.value, w.value, deg.value, coef, dec
+
+
+def celio_evolve(device, psi, sigma_mu, k, contribs, num_times, results, streamed=False):
+    """Celio's method on the GPU for a batch of state vectors (include/musim.h: musim_celio_evolve).
+    psi [n_states, dim] complex; contribs = [(matrix [md, md] complex, other_dim, indices [dim])];
+    results [num_times] float64 is accumulated into (summed over the states)."""
+    lib = load()
+    psi = _c128(np.atleast_2d(psi))
+    n_states, dim = psi.shape
+    sig = _c128(sigma_mu)
+    if sig.shape != (2, 2) or dim % 2:
+        raise ValueError("sigma_mu must be 2x2 and the state dimension even")
+    md = np.ascontiguousarray([np.asarray(m).shape[0] for m, _, _ in contribs], dtype=np.int32)
+    od = np.ascontiguousarray([int(o) for _, o, _ in contribs], dtype=np.int64)
+    mats = _c128(np.concatenate([np.asarray(m, dtype=complex).reshape(-1) for m, _, _ in contribs])) if contribs else None
+    idx = np.ascontiguousarray(np.concatenate([np.asarray(i, dtype=np.int64).reshape(-1) for _, _, i in contribs])) if contribs else None
+    if contribs and idx.size != len(contribs) * dim:
+        raise ValueError("every contribution needs `dim` indices")
+    if not (results.flags.c_contiguous and results.dtype == np.float64 and results.shape == (num_times,)):
+        raise ValueError("results must be a C-contiguous float64 [num_times] array")
+    rc = lib.musim_celio_evolve(int(device), dim, n_states, _ptr(psi), _ptr(sig), dim // 2, int(k), len(contribs),
+                                _ptr(md) if len(contribs) else None, _ptr(od) if len(contribs) else None,
+                                _ptr(mats), _ptr(idx), int(num_times), _ptr(results), 1 if streamed else 0)
+    if rc == -1:
+        raise ValueError("musim_celio_evolve: invalid arguments")
+    if rc:
+        raise MusimError("musim_celio_evolve failed: %s (%d)" % (_ERRORS.get(rc, "?"), rc))
+    return results
 
 
 def device_count():

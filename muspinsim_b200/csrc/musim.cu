@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "profiler.cuh"
 #include "eigh_dispatch.cuh"
+#include "celio.cuh"
 #include "lindblad.cuh"
 #include "peak.cuh"
 #include "polar.cuh"
@@ -925,6 +926,24 @@ extern "C" int musim_run_axes_host(musim_handle *h, int mode, int64_t n_cfg, int
   if (hstat[0] != 0) return set_err(h, MUSIM_ENOTCONV, "eigensolver did not converge");
   return MUSIM_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Celio's method (state-vector Trotter evolution), batched over initial states
+// ---------------------------------------------------------------------------------------
+static int64_t g_celio_launches = 0;
+
+extern "C" int musim_celio_evolve(int device, int64_t dim, int n_states, const double *psi, const double *sigma_mu,
+                                  int64_t half_dim, int k, int n_contrib, const int32_t *mat_dim,
+                                  const int64_t *other_dim, const double *matrices, const int64_t *indices,
+                                  int num_times, double *results, int flags) {
+  static_assert(sizeof(long long) == sizeof(int64_t), "index width");
+  return celio_evolve_host(device, (long long)dim, n_states, psi, sigma_mu, (long long)half_dim, k, n_contrib,
+                           reinterpret_cast<const int *>(mat_dim), reinterpret_cast<const long long *>(other_dim), matrices,
+                           reinterpret_cast<const long long *>(indices), num_times, results, &g_celio_launches,
+                           flags & 1);
+}
+
+extern "C" int64_t musim_celio_launch_count(void) { return g_celio_launches; }
 
 // ---------------------------------------------------------------------------------------
 // FP64 peak micro-benchmarks
