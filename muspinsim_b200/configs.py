@@ -42,6 +42,8 @@ def default_spec():
         "x_axis": "time",
         "y_axis": "asymmetry",
         "average_axes": ["orientation"],
+        "celio": [0],  # [k] or [k, averages] (keyword.py `celio`; 0 = do not use Celio's method)
+        "results_function": None,
     }
 
 

@@ -52,6 +52,12 @@ class ExperimentRunner:
         self._handle_cache = handle_cache
         self.results = None
         self._results_function = (spec or {}).get("results_function") if spec is not None else None
+        # `celio k [averages]` keyword (simconfig.py:537-565): k = 0 means Celio's method is not used
+        cel = list(np.atleast_1d((spec or {}).get("celio", [0])))
+        self._celio_k = int(cel[0])
+        self._celio_averages = int(cel[1]) if len(cel) > 1 else 0
+        if self._celio_k < 0 or self._celio_averages < 0:
+            raise ValueError("Value of k / averages for Celio's method must a postive integer or 0")
         self.options = {}
         self.device_expand = True  # expand the configuration table on the device when all configurations share a mode
 
@@ -150,6 +156,8 @@ class ExperimentRunner:
             raise ValueError("times must be an array of values in microseconds")
         nt = 1 if tab.y == "integral" else len(tab.times)
         out = np.zeros((tab.n_slots, nt))
+        if self._celio_k:
+            return self._run_partial_celio(rank, size, out)
         if self._handle_cache is not None and hasattr(self.handle, "update_system"):
             # a shared (cached) handle may hold another runner's couplings: re-upload H0 / Z
             self.handle.update_system(self._system.hamiltonian, self._system.zeeman_operators())
@@ -179,6 +187,36 @@ class ExperimentRunner:
                 MU_TAU,
                 out,
             )
+        return out
+
+    def _run_partial_celio(self, rank, size, out):
+        """Celio's method (experiment.py:454-470): every configuration is one call of the batched
+        GPU state-vector evolution, all random initial states at once.  Hsys + Hz as lists of terms
+        (spinsys.py:613-626, experiment.py:251-267): the system's interaction terms, then one Zeeman
+        term per spin when the field is not zero."""
+        from .celio import CelioHamiltonian, term_matrix, terms_from_system
+
+        tab = self._table
+        if self._dissip:
+            raise NotImplementedError("Dissipation is not supported when using Celio's method")
+        if tab.y != "asymmetry":
+            raise NotImplementedError("Celio's method evaluates the time-domain signal only")
+        if self._celio_averages <= 0:
+            raise NotImplementedError("Celio's method without random initial states (density-matrix Trotter "
+                                      "evolution, celio.py:207-287) stays with the reference")
+        base = terms_from_system(self._system)
+        for c in range(rank, tab.n_cfg, size):
+            if tab.T[c] != np.inf:
+                raise ValueError("The fast version of Celio's method requires T -> inf. Either remove the number "
+                                 "of averages or don't use celio.")
+            terms = list(base)
+            B = tab.B[c]
+            if not np.array_equal(B, [0, 0, 0]):
+                for i in range(len(self._system)):
+                    terms.append(((i,), term_matrix(self._system, (i,), B * self._system.gammas[i])))
+            H = CelioHamiltonian(terms, self._celio_k, self._system, device=self._device)
+            data = H.fast_evolve(self._system.sigma_mu(tab.p[c]), tab.times, self._celio_averages)
+            out[tab.slot[c], :] += tab.w[c] * data
         return out
 
     def run(self):
