@@ -6,6 +6,7 @@
 #include "eigh_large.cuh"
 #include "eigh_tdc.cuh"
 #include "eigh_tridiag_rw.cuh"
+#include "eigh_tridiag_hs.cuh"
 #include "eigh_tridiag_warp.cuh"
 #include "profiler.cuh"
 #include "rotate.cuh"
@@ -28,6 +29,7 @@ struct EighOpts {
   bool apply_warp = true;      // "apply_warp": rotation replay with one warp per CTA (d > 32)
   int tql_threads = 0;         // "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
   bool tridiag_rw = true;      // "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96); 0: shared-memory kernel
+  bool tridiag_hs = true;      // "tridiag_hs": half-storage DMMA tridiagonalisation for the phases with a live block > 48 (48 < d <= 96)
   bool use_reflect(int d) const { return reflect && d >= 3 && d <= 96; }
 };
 
@@ -70,7 +72,7 @@ struct EighWs {
     const size_t dd = (size_t)d * d;
     if (method == EIGH_HQL)
       return (d > HQL_MAX_D ? (size_t)d * (d | 1) * sizeof(cplx) : 0) +
-             2 * (2 * d * sizeof(double) + dd * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
+             2 * (2 * d * sizeof(double) + std::max<size_t>(dd, 72 * 72 + 48 * 48) * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
              (2 * dd + 64 + 14 * (6 * d + 16)) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
              d * sizeof(unsigned short);
     return jacobi_vglobal(d) ? (size_t)d * (d | 1) * sizeof(cplx) : 0;
@@ -137,7 +139,7 @@ struct EighWs {
       for (int i = 0; i < (dbl ? 2 : 1); ++i) {
         EW_ALLOC(dbuf[i], (size_t)n * d);
         EW_ALLOC(ebuf[i], (size_t)n * d);
-        EW_ALLOC(Q[i], (size_t)n * std::max<size_t>(dd, 64 * 64 + 32 * 32));
+        EW_ALLOC(Q[i], (size_t)n * std::max<size_t>(dd, 72 * 72 + 48 * 48));
         EW_ALLOC(Vp[i], (size_t)n * vcap);
         EW_ALLOC(tauv[i], (size_t)n * d);
       }
@@ -222,6 +224,35 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
             hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
           else
             hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
+        } else if (o.tridiag_hs && d > 48) {
+          // live block d -> 72 -> 48 (half-storage DMMA kernel, 2 / 3 matrices per SM) -> 24 -> done (rows-per-warp kernel)
+          cplx *bufs[2] = {ws.Q[buf], ws.Q[buf] + (size_t)n * 72 * 72};
+          int cur = d, koff = 0, ib = 0, nl = 0;
+          const cplx *in = Ain;
+          bool first = true;
+          for (;;) {
+            const int nxt = cur > 72 ? 72 : (cur > 48 ? 48 : (cur > 24 ? 24 : 0));
+            const int steps = nxt ? cur - nxt : cur;
+            cplx *out = nxt ? bufs[ib] : nullptr;
+            const cplx *h0 = first ? H0 : nullptr, *zz = first ? Z : nullptr;
+            const double *bb = first ? B : nullptr;
+            if (cur > 72)
+              hql_tridiag_hs_kernel<12><<<g, 32 * HsGeom<12>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+            else if (cur > 48)
+              hql_tridiag_hs_kernel<9><<<g, 32 * HsGeom<9>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+            else if (cur > 32)
+              hql_tridiag_rw_kernel<48><<<g, 192, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+            else
+              hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+            ++nl;
+            if (!nxt) break;
+            koff += steps;
+            cur = nxt;
+            in = out;
+            ib ^= 1;
+            first = false;
+          }
+          *launches += nl - 1;
         } else if (d <= 64) {
           const int k1 = d - 32;
           hql_tridiag_rw_kernel<64><<<g, 256, 0, st>>>(d, d, 0, k1, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, A32);

@@ -1,0 +1,397 @@
+// eigh_tridiag_hs.cuh -- K1 for the large phases (live block 96 -> 72 -> 48): Householder
+// tridiagonalisation with the matrix in registers in HERMITIAN HALF STORAGE, laid out as FP64
+// tensor-core accumulator fragments.
+//
+// Why (profiles/r2_ncu_full_summary.md): with the full matrix in registers
+// (eigh_tridiag_rw.cuh) one 96 x 96 matrix fills an SM, so a Householder step is one dependency
+// chain per SM: 2 400 cycles of FP64 pipe and 2 400 shared-memory wavefronts run back to back
+// (FP64 43 %, LSU 48 %).  Here
+//   * only the lower triangle is kept, as 24 x 24 "superblocks" of 3 x 3 tiles of 8 x 8; a tile is a
+//     pair (re, im) of mma.m8n8k4 accumulator fragments: lane (g, q) = (lane >> 2, lane & 3) holds the
+//     elements (row g, columns 2q, 2q + 1).  A warp owns one off-diagonal superblock (9 tiles) and, warps
+//     0 .. S-1, the lower 6 tiles of a diagonal one: 120 registers of matrix per thread, 168 in all, i.e.
+//     three warps per scheduler: TWO 96 x 96 matrices per SM (four at 72 x 72), whose phases overlap;
+//   * the rank-2 update A -= v w^H + w v^H is exactly one k = 4 DMMA per tile and per part:
+//     Re -= [v_r.x v_r.y w_r.x w_r.y] . [w_c.x w_c.y v_c.x v_c.y]^T, Im likewise with the row operand
+//     permuted -- 2 DMMAs per tile instead of 128 DFMAs per warp, and the operands are ONE 16-byte
+//     load per row tile and ONE 8-byte load per column tile (the full-storage kernel loads v and p for
+//     every row and column of the thread's tile: 4 x the shared-memory wavefronts);
+//   * the symmetric product y = A x' uses every stored off-diagonal superblock twice (row direction:
+//     reduce over the 4 lanes of a row; column direction: reduce over the 8 lanes of a column), the
+//     partial sums of the superblocks meet in shared memory, and ONE warp combines them into p, v, the
+//     dot product p^H v and w = p + a2 v (no block-wide reduction tree).
+// Three barriers per step; arithmetic identical to tools/hql_prototype.py::tridiag_lower (zhetd2,
+// lower).  The kernel stops after `nsteps` steps and hands the trailing block to the next phase like
+// hql_tridiag_rw_kernel (same outputs: d, e, tau, packed reflectors).
+#pragma once
+#include "common.cuh"
+#include "polar.cuh"  // dmma884
+
+namespace musim {
+
+struct HsTile {
+  double re[2], im[2];
+};
+
+template <int NT>
+struct HsGeom {
+  static constexpr int S = NT / 3;              // superblock rows
+  static constexpr int NW = S * (S - 1) / 2;    // warps = off-diagonal superblocks (6 or 3)
+  static constexpr int D = 8 * NT;
+  static constexpr int CTAS = 12 / NW;          // 12 warps per SM at 168 registers
+};
+
+__device__ __forceinline__ cplx hs_shfl(cplx v, int m) {
+  return make_c(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ cplx hs_sel(bool c, cplx a, cplx b) { return make_c(c ? a.x : b.x, c ? a.y : b.y); }
+
+// Reduce three per-row-tile values over the 4 lanes of a row: lane q ends up with row tile q (q = 3
+// duplicates tile 2) and stores it.
+__device__ __forceinline__ void hs_reduce_rows(const cplx (&yr)[3], int lane, cplx *dst) {
+  const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
+  const cplx rcv = hs_shfl(hs_sel(b0, yr[0], yr[1]), 1);
+  const cplx t = cadd(hs_sel(b0, yr[1], yr[0]), rcv);
+  const cplx t2 = cadd(yr[2], hs_shfl(yr[2], 1));
+  const cplx rcv2 = hs_shfl(hs_sel(b1, t, t2), 2);
+  const cplx f = cadd(hs_sel(b1, t2, t), rcv2);
+  const int g = lane >> 2, q = lane & 3;
+  if (q < 3) dst[8 * q + g] = f;
+}
+// Stage 1 of the reduction over the 8 lanes of a column: two columns -> one (column 2q + g0).
+__device__ __forceinline__ cplx hs_reduce_cols1(cplx yc0, cplx yc1, int lane) {
+  const bool g0 = (lane & 4) != 0;
+  const cplx rcv = hs_shfl(hs_sel(g0, yc0, yc1), 4);
+  return cadd(hs_sel(g0, yc1, yc0), rcv);
+}
+
+// y += A x' over an OFF-DIAGONAL superblock (SI > SJ): row direction y_I += A x_J (partial sums to
+// yrow_dst[24 SI + ...]) and column direction y_J += A^H x_I (partial sums to ycol_dst[24 SJ + ...]).
+__device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[3][3], int SI, int SJ, int k, const cplx *x, cplx xp0,
+                                              int lane, cplx *yrow_dst, cplx *ycol_dst) {
+  const int g = lane >> 2, q = lane & 3;
+  const int r0 = 24 * SI + g, c0 = 24 * SJ + 2 * q;
+  cplx xr[3], yr[3], u[3];
+#pragma unroll
+  for (int ti = 0; ti < 3; ++ti) {
+    yr[ti] = make_c(0.0, 0.0);
+    xr[ti] = x[r0 + 8 * ti];
+    if (r0 + 8 * ti == k + 1) xr[ti] = xp0;
+  }
+#pragma unroll
+  for (int tj = 0; tj < 3; ++tj) {
+    cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
+    if (24 * SJ + 8 * tj + 7 > k) {  // tile column has live columns (uniform)
+      cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];  // zero for columns <= k (publish_col)
+      if (c0 + 8 * tj == k + 1) xc0 = xp0;
+      if (c0 + 8 * tj + 1 == k + 1) xc1 = xp0;
+#pragma unroll
+      for (int ti = 0; ti < 3; ++ti) {
+        const cplx A0 = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
+        const cplx A1 = make_c(a[ti][tj].re[1], a[ti][tj].im[1]);
+        cfma(yr[ti], A0, xc0);
+        cfma(yr[ti], A1, xc1);
+        ccfma(yc0, A0, xr[ti]);
+        ccfma(yc1, A1, xr[ti]);
+      }
+    }
+    u[tj] = hs_reduce_cols1(yc0, yc1, lane);
+  }
+  hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
+  {
+    const bool g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
+    const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
+    const cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
+    const cplx z2 = cadd(u[2], hs_shfl(u[2], 8));
+    const cplx rcv2 = hs_shfl(hs_sel(g2, z, z2), 16);
+    const cplx f = cadd(hs_sel(g2, z2, z), rcv2);  // g2 = 0: tile g1, g2 = 1: tile 2
+    if (!(g1 && g2)) ycol_dst[24 * SJ + 8 * (g2 ? 2 : (g1 ? 1 : 0)) + 2 * q + ((lane >> 2) & 1)] = f;
+  }
+}
+
+// The same over the lower tiles (tj <= ti) of the DIAGONAL superblock SI: the diagonal tiles are full
+// Hermitian 8 x 8 blocks (row direction only), the three tiles below them work in both directions.
+__device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[3][3], int SI, int k, const cplx *x, cplx xp0,
+                                               int lane, cplx *yrow_dst, cplx *ycol_dst) {
+  const int g = lane >> 2, q = lane & 3;
+  const int r0 = 24 * SI + g, c0 = 24 * SI + 2 * q;
+  cplx xr[3], yr[3], u[2];
+#pragma unroll
+  for (int ti = 0; ti < 3; ++ti) {
+    yr[ti] = make_c(0.0, 0.0);
+    xr[ti] = x[r0 + 8 * ti];
+    if (r0 + 8 * ti == k + 1) xr[ti] = xp0;
+  }
+#pragma unroll
+  for (int tj = 0; tj < 3; ++tj) {
+    cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
+    if (24 * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
+      cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
+      if (c0 + 8 * tj == k + 1) xc0 = xp0;
+      if (c0 + 8 * tj + 1 == k + 1) xc1 = xp0;
+#pragma unroll
+      for (int ti = tj; ti < 3; ++ti) {
+        const cplx A0 = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
+        const cplx A1 = make_c(a[ti][tj].re[1], a[ti][tj].im[1]);
+        cfma(yr[ti], A0, xc0);
+        cfma(yr[ti], A1, xc1);
+        if (ti > tj) {
+          ccfma(yc0, A0, xr[ti]);
+          ccfma(yc1, A1, xr[ti]);
+        }
+      }
+    }
+    if (tj < 2) u[tj] = hs_reduce_cols1(yc0, yc1, lane);
+  }
+  hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
+  {
+    const bool g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
+    const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
+    cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
+    z = cadd(z, hs_shfl(z, 16));
+    if (!g2) ycol_dst[24 * SI + 8 * (g1 ? 1 : 0) + 2 * q + ((lane >> 2) & 1)] = z;
+  }
+}
+
+// A -= v w^H + w v^H on one superblock: two DMMAs per live tile.  DIAG: lower tiles only.
+template <bool DIAG>
+__device__ __forceinline__ void hs_update(HsTile (&a)[3][3], int SI, int SJ, int k, const cplx *sv, const cplx *sw,
+                                          int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const cplx *arow = (q < 2) ? sv : sw;
+  const double *bcol = reinterpret_cast<const double *>((q < 2) ? sw : sv) + (q & 1);
+  double are[3], aim[3], bb[3];
+#pragma unroll
+  for (int ti = 0; ti < 3; ++ti) {
+    const cplx z = arow[24 * SI + 8 * ti + g];
+    are[ti] = (q & 1) ? -z.y : -z.x;
+    aim[ti] = (q & 1) ? z.x : -z.y;
+  }
+#pragma unroll
+  for (int tj = 0; tj < 3; ++tj) bb[tj] = bcol[2 * (24 * SJ + 8 * tj + g)];
+#pragma unroll
+  for (int tj = 0; tj < 3; ++tj) {
+    if (24 * SJ + 8 * tj + 7 > k) {
+#pragma unroll
+      for (int ti = (DIAG ? tj : 0); ti < 3; ++ti) {
+        dmma884(a[ti][tj].re[0], a[ti][tj].re[1], are[ti], bb[tj]);
+        dmma884(a[ti][tj].im[0], a[ti][tj].im[1], aim[ti], bb[tj]);
+      }
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(32 * HsGeom<NT>::NW, HsGeom<NT>::CTAS)
+hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__restrict__ H0,
+                      const cplx *__restrict__ Z, const double *__restrict__ Bf, const cplx *__restrict__ Ain,
+                      double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Vp, size_t vcap,
+                      cplx *__restrict__ tauout, cplx *__restrict__ Aout) {
+  using G = HsGeom<NT>;
+  constexpr int S = G::S, NW = G::NW, D = G::D;
+  constexpr int RPL = (D + 31) / 32;  // rows per lane of the combining warp
+  constexpr int WC = (NT == 12) ? 5 : 0;  // combining warp: the one with the least work
+  __shared__ __align__(16) cplx sx[2][D];        // column k of the trailing matrix, by parity of k
+  __shared__ __align__(16) double sxn[2][8];     // per-warp partial ||x[2:]||^2, by parity of k
+  __shared__ __align__(16) cplx sv[D];           // v of the current step
+  __shared__ __align__(16) cplx sw[D];           // w = p + a2 v
+  // partial products: slot c < S of super-row R comes from superblock (R, c) (row direction) or (c, R)
+  // (column direction), slot S from the column direction inside the diagonal superblock (R, R)
+  __shared__ __align__(16) cplx ypart[S + 1][D];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const size_t cfg = blockIdx.x;
+  const size_t dd = (size_t)d * d;
+
+  // superblocks of this warp: the diagonal block (w, w) for w < S, and one off-diagonal block
+  const bool has0 = w < S;
+  const int SI0 = has0 ? w : 0;
+  int SI1, SJ1;
+  if (NT == 12) {
+    // w = 0: (3,2)  1: (3,1)  2: (2,1)  3: (3,0)  4: (1,0)  5: (2,0)
+    SI1 = (w == 2 || w == 5) ? 2 : ((w == 4) ? 1 : 3);
+    SJ1 = (w == 0) ? 2 : ((w == 1 || w == 2) ? 1 : 0);
+  } else {
+    SI1 = (w == 2) ? 1 : 2;  // w = 0: (2,1)  1: (2,0)  2: (1,0)
+    SJ1 = (w == 0) ? 1 : 0;
+  }
+
+  HsTile a0[3][3], a1[3][3];  // a0: only tj <= ti is used
+  {
+    double bx = 0, by = 0, bz = 0;
+    if (!Ain) {
+      bx = Bf[cfg * 3 + 0];
+      by = Bf[cfg * 3 + 1];
+      bz = Bf[cfg * 3 + 2];
+    }
+    auto load_elem = [&](int r, int c) {
+      cplx v = make_c(0.0, 0.0);
+      if (r < d && c < d) {
+        const size_t idx = (size_t)r * d + c;
+        if (Ain) {
+          v = Ain[cfg * dd + idx];
+        } else {
+          v = H0[idx];
+          const cplx z0 = Z[idx], z1 = Z[dd + idx], z2 = Z[2 * dd + idx];
+          v.x += bx * z0.x + by * z1.x + bz * z2.x;
+          v.y += bx * z0.y + by * z1.y + bz * z2.y;
+        }
+        if (r == c) v.y = 0.0;
+      }
+      return v;
+    };
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 3; ++tj)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (tj <= ti) {
+            cplx v = make_c(0.0, 0.0);
+            if (has0) v = load_elem(24 * SI0 + 8 * ti + g, 24 * SI0 + 8 * tj + 2 * q + s);
+            a0[ti][tj].re[s] = v.x;
+            a0[ti][tj].im[s] = v.y;
+          }
+          const cplx v1 = load_elem(24 * SI1 + 8 * ti + g, 24 * SJ1 + 8 * tj + 2 * q + s);
+          a1[ti][tj].re[s] = v1.x;
+          a1[ti][tj].im[s] = v1.y;
+        }
+  }
+  for (int i = tid; i < D; i += 32 * NW) ypart[S][i] = make_c(0.0, 0.0);
+
+  // Publish column kc of the (updated) matrix for rows > kc, the partial norms of rows > kc + 1 and
+  // the diagonal element.  In half storage column kc lives in the superblocks (., kc / 24).
+  auto publish_sb = [&](const HsTile (&a)[3][3], int SI, int kc, int tjk, bool diag, double &xn) {
+    const int par = kc & 1;
+    const bool s1 = (kc & 1) != 0;
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti) {
+      cplx v = make_c(0.0, 0.0);
+#pragma unroll
+      for (int tj = 0; tj < 3; ++tj)
+        if (tj == tjk && (!diag || tj <= ti))
+          v = make_c(s1 ? a[ti][tj].re[1] : a[ti][tj].re[0], s1 ? a[ti][tj].im[1] : a[ti][tj].im[0]);
+      const int r = 24 * SI + 8 * ti + g;
+      if (r > kc) sx[par][r] = v;  // (diagonal superblock: tiles above the diagonal only hold rows < kc)
+      if (r > kc + 1) xn = fma(v.y, v.y, fma(v.x, v.x, xn));  // rows >= d hold zeros
+      if (r == kc) {
+        dout[cfg * dstride + koff + kc] = v.x;
+        sx[par][kc] = make_c(0.0, 0.0);
+        if (kc > 0) sx[par][kc - 1] = make_c(0.0, 0.0);
+      }
+    }
+  };
+  auto publish_col = [&](int kc) {
+    const int J = kc >> 3, SJk = J / 3, tjk = J - 3 * SJk, qk = (kc & 7) >> 1;
+    double xn = 0.0;
+    if (has0 && SI0 == SJk && q == qk) publish_sb(a0, SI0, kc, tjk, true, xn);
+    if (SJ1 == SJk && q == qk) publish_sb(a1, SI1, kc, tjk, false, xn);
+    xn += __shfl_xor_sync(0xffffffffu, xn, 4);
+    xn += __shfl_xor_sync(0xffffffffu, xn, 8);
+    xn += __shfl_xor_sync(0xffffffffu, xn, 16);
+    if (lane == qk) sxn[kc & 1][w] = xn;
+  };
+
+  publish_col(0);
+  const int kend = (nsteps < d - 1) ? nsteps : d - 1;
+  for (int k = 0; k < kend; ++k) {
+    __syncthreads();  // #1: column k and its partial norms are visible
+    const cplx *x = sx[k & 1];
+    double xn = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) xn += sxn[k & 1][i];
+    const cplx alpha = x[k + 1];
+    const int mk = d - k - 2;
+    const size_t voff = (size_t)mk * (mk - 1) / 2;
+    if (xn == 0.0 && alpha.y == 0.0) {  // identity reflector (uniform: every thread sees the same values)
+      if (tid == 0) {
+        eout[cfg * dstride + koff + k] = alpha.x;
+        tauout[cfg * dstride + koff + k] = make_c(0.0, 0.0);
+      }
+      for (int i = tid; i < mk; i += 32 * NW) Vp[cfg * vcap + voff + i] = make_c(0.0, 0.0);
+      publish_col(k + 1);
+      continue;
+    }
+    // Householder scalars, redundantly per thread (rsqrt / rcp, no IEEE division)
+    const double s2 = alpha.x * alpha.x + alpha.y * alpha.y + xn;
+    const double ri = rsqrt(s2);
+    const double sg = (alpha.x >= 0.0) ? -1.0 : 1.0;  // sign of beta
+    const double beta = sg * (s2 * ri);
+    const double ib = sg * ri;
+    const cplx tau = make_c((beta - alpha.x) * ib, -alpha.y * ib);
+    const cplx xp0 = make_c(alpha.x - beta, alpha.y);  // x'_{k+1} = alpha - beta = 1/scale
+
+    // ---- partial products y = A22 x' ----
+    if (has0) hs_matvec_diag(a0, SI0, k, x, xp0, lane, ypart[SI0], ypart[S]);
+    hs_matvec_off(a1, SI1, SJ1, k, x, xp0, lane, ypart[SJ1], ypart[SI1]);
+    __syncthreads();  // #2: the partial products are visible
+
+    if (w == WC) {  // combine: p = tau A v, v, a2 = -1/2 tau p^H v, w = p + a2 v
+      const double den = __drcp_rn(xp0.x * xp0.x + xp0.y * xp0.y);
+      const cplx scale = make_c(xp0.x * den, -xp0.y * den);
+      const cplx ts = cmul(tau, scale);
+      cplx vv[RPL], pp[RPL];
+      cplx dt = make_c(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int r = lane + 32 * i;
+        vv[i] = make_c(0.0, 0.0);
+        pp[i] = make_c(0.0, 0.0);
+        if (r < D) {
+          cplx y = ypart[0][r];
+#pragma unroll
+          for (int c = 1; c <= S; ++c) y = cadd(y, ypart[c][r]);
+          vv[i] = (r == k + 1) ? make_c(1.0, 0.0) : cmul(scale, x[r]);  // x[r] = 0 for r <= k
+          pp[i] = cmul(ts, y);
+          dt = cadd(dt, ccmul(pp[i], vv[i]));  // conj(p) v
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dt = cadd(dt, hs_shfl(dt, o));
+      // a2 is real for Hermitian A (its imaginary part is rounding noise)
+      const double a2 = -0.5 * (tau.x * dt.x - tau.y * dt.y);
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int r = lane + 32 * i;
+        if (r < D) {
+          sv[r] = vv[i];
+          sw[r] = make_c(fma(a2, vv[i].x, pp[i].x), fma(a2, vv[i].y, pp[i].y));
+          if (r >= k + 2 && r < d) Vp[cfg * vcap + voff + (r - k - 2)] = vv[i];  // reflector k for the back-transformation
+        }
+      }
+      if (lane == 0) {
+        eout[cfg * dstride + koff + k] = beta;
+        tauout[cfg * dstride + koff + k] = tau;
+      }
+    }
+    __syncthreads();  // #3: v and w are visible
+
+    if (has0) hs_update<true>(a0, SI0, SI0, k, sv, sw, lane);
+    hs_update<false>(a1, SI1, SJ1, k, sv, sw, lane);
+    publish_col(k + 1);
+  }
+  if (kend == d - 1) {
+    if (tid == 0) eout[cfg * dstride + koff + d - 1] = 0.0;
+  } else {  // hand the trailing block (both triangles) to the next phase
+    const int ds = d - kend;
+    cplx *Ao = Aout + cfg * (size_t)ds * ds;
+    auto store_elem = [&](int r, int c, cplx v, bool mirror) {
+      if (r >= kend && c >= kend && r < d && c < d) {
+        Ao[(size_t)(r - kend) * ds + (c - kend)] = v;
+        if (mirror) Ao[(size_t)(c - kend) * ds + (r - kend)] = cconj(v);
+      }
+    };
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 3; ++tj)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (tj <= ti && has0)
+            store_elem(24 * SI0 + 8 * ti + g, 24 * SI0 + 8 * tj + 2 * q + s, make_c(a0[ti][tj].re[s], a0[ti][tj].im[s]), tj < ti);
+          store_elem(24 * SI1 + 8 * ti + g, 24 * SJ1 + 8 * tj + 2 * q + s, make_c(a1[ti][tj].re[s], a1[ti][tj].im[s]), true);
+        }
+  }
+}
+
+}  // namespace musim

@@ -38,7 +38,7 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int m) {
 // SM) continues on that block -- the trailing problem is self-similar, the packed reflectors
 // keep their offsets, and d / e / tau are written at offset `koff` of rows of length `dstride`.
 template <int D>
-__global__ void __launch_bounds__(4 * D, (D <= 32 ? 4 : (D <= 64 ? 2 : 1)))
+__global__ void __launch_bounds__(4 * D, (D <= 32 ? 4 : (D <= 48 ? 3 : (D <= 64 ? 2 : 1))))
 hql_tridiag_rw_kernel(int d, int dstride, int koff, int nsteps, const cplx *__restrict__ H0,
                       const cplx *__restrict__ Z, const double *__restrict__ Bf,
                       const cplx *__restrict__ Ain, double *__restrict__ dout,
