@@ -204,7 +204,7 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
       const size_t sm = hql_tridiag_warpf_smem(d);
       cudaFuncSetAttribute(hql_tridiag_warpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       hql_tridiag_warpf_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
-          d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf]);
+          d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf], d, 0);
     } else if (o.use_reflect(d) && o.tridiag_warp && d <= 32) {
       const size_t sm = hql_tridiag_warp_smem(d);
       cudaFuncSetAttribute(hql_tridiag_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -242,7 +242,12 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
               hql_tridiag_hs_kernel<9><<<g, 32 * HsGeom<9>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
             else if (cur > 32)
               hql_tridiag_rw_kernel<48><<<g, 192, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
-            else
+            else if (!first && o.tridiag_warp && o.tridiag_fused) {  // last phase: warp per matrix, no block barriers
+              const size_t sm = hql_tridiag_warpf_smem(cur);
+              cudaFuncSetAttribute(hql_tridiag_warpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+              hql_tridiag_warpf_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
+                  cur, n, nullptr, nullptr, nullptr, in, dd_, ee_, vp_, ws.vcap, tt_, d, koff);
+            } else
               hql_tridiag_rw_kernel<32><<<g, 128, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
             ++nl;
             if (!nxt) break;

@@ -18,12 +18,16 @@
 //     every row and column of the thread's tile: 4 x the shared-memory wavefronts);
 //   * the symmetric product y = A x' uses every stored off-diagonal superblock twice (row direction:
 //     reduce over the 4 lanes of a row; column direction: reduce over the 8 lanes of a column), the
-//     partial sums of the superblocks meet in shared memory, and ONE warp combines them into p, v, the
-//     dot product p^H v and w = p + a2 v (no block-wide reduction tree).
+//     partial sums of the superblocks meet in shared memory; the scalar a2 = -1/2 tau p^H v needs no
+//     second pass: p^H v is a multiple of the Hermitian form x'^H A x', which every superblock
+//     accumulates from its own partial products during the mat-vec (one warp sum + NW partials), so
+//     after the barrier every warp finishes p, v and w = p + a2 v for its share of the rows and writes
+//     them already in DMMA operand order (no selects or negations in the update).
 // Three barriers per step; arithmetic identical to tools/hql_prototype.py::tridiag_lower (zhetd2,
 // lower).  The kernel stops after `nsteps` steps and hands the trailing block to the next phase like
 // hql_tridiag_rw_kernel (same outputs: d, e, tau, packed reflectors).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "polar.cuh"  // dmma884
 
@@ -67,38 +71,56 @@ __device__ __forceinline__ cplx hs_reduce_cols1(cplx yc0, cplx yc1, int lane) {
 
 // y += A x' over an OFF-DIAGONAL superblock (SI > SJ): row direction y_I += A x_J (partial sums to
 // yrow_dst[24 SI + ...]) and column direction y_J += A^H x_I (partial sums to ycol_dst[24 SJ + ...]).
-__device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[3][3], int SI, int SJ, int k, const cplx *x, cplx xp0,
-                                              int lane, cplx *yrow_dst, cplx *ycol_dst) {
+// x' = x except x'_{k+1} = alpha - beta: only the real part differs (xp0x).  qacc += 2 Re(x_I^H A x_J).
+__device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[3][3], int SI, int SJ, int k, const cplx *x, double xp0x,
+                                              int lane, cplx *yrow_dst, cplx *ycol_dst, double &qacc) {
   const int g = lane >> 2, q = lane & 3;
   const int r0 = 24 * SI + g, c0 = 24 * SJ + 2 * q;
-  cplx xr[3], yr[3], u[3];
+  cplx xr[3];
 #pragma unroll
   for (int ti = 0; ti < 3; ++ti) {
-    yr[ti] = make_c(0.0, 0.0);
     xr[ti] = x[r0 + 8 * ti];
-    if (r0 + 8 * ti == k + 1) xr[ti] = xp0;
+    if (r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
   }
+  // two passes over the register tiles (rows, then columns) keep the live set small: 168 registers
+  // hold 120 of matrix, and the one-pass version spilled
+  {
+    cplx yr[3];
 #pragma unroll
-  for (int tj = 0; tj < 3; ++tj) {
-    cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
-    if (24 * SJ + 8 * tj + 7 > k) {  // tile column has live columns (uniform)
-      cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];  // zero for columns <= k (publish_col)
-      if (c0 + 8 * tj == k + 1) xc0 = xp0;
-      if (c0 + 8 * tj + 1 == k + 1) xc1 = xp0;
+    for (int ti = 0; ti < 3; ++ti) yr[ti] = make_c(0.0, 0.0);
 #pragma unroll
-      for (int ti = 0; ti < 3; ++ti) {
-        const cplx A0 = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
-        const cplx A1 = make_c(a[ti][tj].re[1], a[ti][tj].im[1]);
-        cfma(yr[ti], A0, xc0);
-        cfma(yr[ti], A1, xc1);
-        ccfma(yc0, A0, xr[ti]);
-        ccfma(yc1, A1, xr[ti]);
+    for (int tj = 0; tj < 3; ++tj) {
+      if (24 * SJ + 8 * tj + 7 > k) {  // tile column has live columns (uniform)
+        cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];  // zero for columns <= k (publish_col)
+        if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
+        if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti) {
+          cfma(yr[ti], make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xc0);
+          cfma(yr[ti], make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xc1);
+        }
       }
     }
-    u[tj] = hs_reduce_cols1(yc0, yc1, lane);
+    double t = 0.0;
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti) t = fma(xr[ti].x, yr[ti].x, fma(xr[ti].y, yr[ti].y, t));
+    qacc = fma(2.0, t, qacc);
+    hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
   }
-  hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
   {
+    cplx u[3];
+#pragma unroll
+    for (int tj = 0; tj < 3; ++tj) {
+      cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
+      if (24 * SJ + 8 * tj + 7 > k) {
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti) {
+          ccfma(yc0, make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xr[ti]);
+          ccfma(yc1, make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xr[ti]);
+        }
+      }
+      u[tj] = hs_reduce_cols1(yc0, yc1, lane);
+    }
     const bool g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
     const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
     const cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
@@ -111,40 +133,58 @@ __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[3][3], int SI, i
 
 // The same over the lower tiles (tj <= ti) of the DIAGONAL superblock SI: the diagonal tiles are full
 // Hermitian 8 x 8 blocks (row direction only), the three tiles below them work in both directions.
-__device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[3][3], int SI, int k, const cplx *x, cplx xp0,
-                                               int lane, cplx *yrow_dst, cplx *ycol_dst) {
+// qacc += x_I^H A_II x_I (row- and column-direction partial products together cover the whole block).
+__device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[3][3], int SI, int k, const cplx *x, double xp0x,
+                                               int lane, cplx *yrow_dst, cplx *ycol_dst, double &qacc) {
   const int g = lane >> 2, q = lane & 3;
   const int r0 = 24 * SI + g, c0 = 24 * SI + 2 * q;
-  cplx xr[3], yr[3], u[2];
+  cplx xr[3];
+  double t = 0.0;
 #pragma unroll
   for (int ti = 0; ti < 3; ++ti) {
-    yr[ti] = make_c(0.0, 0.0);
     xr[ti] = x[r0 + 8 * ti];
-    if (r0 + 8 * ti == k + 1) xr[ti] = xp0;
+    if (r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
   }
+  {  // row direction (pass 1)
+    cplx yr[3];
 #pragma unroll
-  for (int tj = 0; tj < 3; ++tj) {
-    cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
-    if (24 * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
-      cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
-      if (c0 + 8 * tj == k + 1) xc0 = xp0;
-      if (c0 + 8 * tj + 1 == k + 1) xc1 = xp0;
+    for (int ti = 0; ti < 3; ++ti) yr[ti] = make_c(0.0, 0.0);
 #pragma unroll
-      for (int ti = tj; ti < 3; ++ti) {
-        const cplx A0 = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
-        const cplx A1 = make_c(a[ti][tj].re[1], a[ti][tj].im[1]);
-        cfma(yr[ti], A0, xc0);
-        cfma(yr[ti], A1, xc1);
-        if (ti > tj) {
-          ccfma(yc0, A0, xr[ti]);
-          ccfma(yc1, A1, xr[ti]);
+    for (int tj = 0; tj < 3; ++tj) {
+      if (24 * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
+        cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
+        if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
+        if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
+#pragma unroll
+        for (int ti = tj; ti < 3; ++ti) {
+          cfma(yr[ti], make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xc0);
+          cfma(yr[ti], make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xc1);
         }
       }
     }
-    if (tj < 2) u[tj] = hs_reduce_cols1(yc0, yc1, lane);
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti) t = fma(xr[ti].x, yr[ti].x, fma(xr[ti].y, yr[ti].y, t));
+    hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
   }
-  hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
-  {
+  {  // column direction of the tiles below the diagonal (pass 2)
+    cplx u[2];
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) {
+      cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
+      if (24 * SI + 8 * tj + 7 > k) {
+#pragma unroll
+        for (int ti = tj + 1; ti < 3; ++ti) {
+          ccfma(yc0, make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xr[ti]);
+          ccfma(yc1, make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xr[ti]);
+        }
+        cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
+        if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
+        if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
+        t = fma(xc0.x, yc0.x, fma(xc0.y, yc0.y, fma(xc1.x, yc1.x, fma(xc1.y, yc1.y, t))));
+      }
+      u[tj] = hs_reduce_cols1(yc0, yc1, lane);
+    }
+    qacc += t;
     const bool g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
     const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
     cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
@@ -154,21 +194,19 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[3][3], int SI, 
 }
 
 // A -= v w^H + w v^H on one superblock: two DMMAs per live tile.  DIAG: lower tiles only.
+// Operands in shared memory, already in fragment order (written by the combine step):
+//   sAr[r] = -(v.x, v.y, w.x, w.y), sAi[r] = (-v.y, v.x, -w.y, w.x), sB[c] = (w.x, w.y, v.x, v.y).
 template <bool DIAG>
-__device__ __forceinline__ void hs_update(HsTile (&a)[3][3], int SI, int SJ, int k, const cplx *sv, const cplx *sw,
-                                          int lane) {
-  const int g = lane >> 2, q = lane & 3;
-  const cplx *arow = (q < 2) ? sv : sw;
-  const double *bcol = reinterpret_cast<const double *>((q < 2) ? sw : sv) + (q & 1);
+__device__ __forceinline__ void hs_update(HsTile (&a)[3][3], int SI, int SJ, int k, const double *sAr, const double *sAi,
+                                          const double *sB, int lane) {
   double are[3], aim[3], bb[3];
 #pragma unroll
   for (int ti = 0; ti < 3; ++ti) {
-    const cplx z = arow[24 * SI + 8 * ti + g];
-    are[ti] = (q & 1) ? -z.y : -z.x;
-    aim[ti] = (q & 1) ? z.x : -z.y;
+    are[ti] = sAr[4 * (24 * SI + 8 * ti) + lane];  // [row 8 I + g][q]
+    aim[ti] = sAi[4 * (24 * SI + 8 * ti) + lane];
   }
 #pragma unroll
-  for (int tj = 0; tj < 3; ++tj) bb[tj] = bcol[2 * (24 * SJ + 8 * tj + g)];
+  for (int tj = 0; tj < 3; ++tj) bb[tj] = sB[4 * (24 * SJ + 8 * tj) + lane];  // [column 8 J + g][q]
 #pragma unroll
   for (int tj = 0; tj < 3; ++tj) {
     if (24 * SJ + 8 * tj + 7 > k) {
@@ -189,12 +227,12 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
                       cplx *__restrict__ tauout, cplx *__restrict__ Aout) {
   using G = HsGeom<NT>;
   constexpr int S = G::S, NW = G::NW, D = G::D;
-  constexpr int RPL = (D + 31) / 32;  // rows per lane of the combining warp
-  constexpr int WC = (NT == 12) ? 5 : 0;  // combining warp: the one with the least work
+  constexpr int RPW = D / NW;  // rows per warp in the combine step (16 or 24)
   __shared__ __align__(16) cplx sx[2][D];        // column k of the trailing matrix, by parity of k
   __shared__ __align__(16) double sxn[2][8];     // per-warp partial ||x[2:]||^2, by parity of k
-  __shared__ __align__(16) cplx sv[D];           // v of the current step
-  __shared__ __align__(16) cplx sw[D];           // w = p + a2 v
+  __shared__ __align__(16) double sq[8];         // per-warp partial x'^H A x'
+  __shared__ __align__(16) cplx ssc[4];          // step scalars: ts = tau scale, scale, -1/2 |tau|^2 |scale|^2
+  __shared__ __align__(16) double sAr[4 * D], sAi[4 * D], sB[4 * D];  // update operands (see hs_update)
   // partial products: slot c < S of super-row R comes from superblock (R, c) (row direction) or (c, R)
   // (column direction), slot S from the column direction inside the diagonal superblock (R, R)
   __shared__ __align__(16) cplx ypart[S + 1][D];
@@ -260,22 +298,33 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
   for (int i = tid; i < D; i += 32 * NW) ypart[S][i] = make_c(0.0, 0.0);
 
   // Publish column kc of the (updated) matrix for rows > kc, the partial norms of rows > kc + 1 and
-  // the diagonal element.  In half storage column kc lives in the superblocks (., kc / 24).
+  // the diagonal element.  In half storage column kc lives in the superblocks (., kc / 24); the tile
+  // column and the fragment slot are uniform, so they are branches, not selects.
   auto publish_sb = [&](const HsTile (&a)[3][3], int SI, int kc, int tjk, bool diag, double &xn) {
     const int par = kc & 1;
-    const bool s1 = (kc & 1) != 0;
+    cplx v[3];
+#pragma unroll
+    for (int ti = 0; ti < 3; ++ti) v[ti] = make_c(0.0, 0.0);
+#pragma unroll
+    for (int tj = 0; tj < 3; ++tj)
+      if (tj == tjk) {
+        if (kc & 1) {
+#pragma unroll
+          for (int ti = 0; ti < 3; ++ti)
+            if (!diag || tj <= ti) v[ti] = make_c(a[ti][tj].re[1], a[ti][tj].im[1]);
+        } else {
+#pragma unroll
+          for (int ti = 0; ti < 3; ++ti)
+            if (!diag || tj <= ti) v[ti] = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
+        }
+      }
 #pragma unroll
     for (int ti = 0; ti < 3; ++ti) {
-      cplx v = make_c(0.0, 0.0);
-#pragma unroll
-      for (int tj = 0; tj < 3; ++tj)
-        if (tj == tjk && (!diag || tj <= ti))
-          v = make_c(s1 ? a[ti][tj].re[1] : a[ti][tj].re[0], s1 ? a[ti][tj].im[1] : a[ti][tj].im[0]);
       const int r = 24 * SI + 8 * ti + g;
-      if (r > kc) sx[par][r] = v;  // (diagonal superblock: tiles above the diagonal only hold rows < kc)
-      if (r > kc + 1) xn = fma(v.y, v.y, fma(v.x, v.x, xn));  // rows >= d hold zeros
+      if (r > kc) sx[par][r] = v[ti];  // (diagonal superblock: tiles above the diagonal only hold rows < kc)
+      if (r > kc + 1) xn = fma(v[ti].y, v[ti].y, fma(v[ti].x, v[ti].x, xn));  // rows >= d hold zeros
       if (r == kc) {
-        dout[cfg * dstride + koff + kc] = v.x;
+        dout[cfg * dstride + koff + kc] = v[ti].x;
         sx[par][kc] = make_c(0.0, 0.0);
         if (kc > 0) sx[par][kc - 1] = make_c(0.0, 0.0);
       }
@@ -284,16 +333,24 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
   auto publish_col = [&](int kc) {
     const int J = kc >> 3, SJk = J / 3, tjk = J - 3 * SJk, qk = (kc & 7) >> 1;
     double xn = 0.0;
-    if (has0 && SI0 == SJk && q == qk) publish_sb(a0, SI0, kc, tjk, true, xn);
-    if (SJ1 == SJk && q == qk) publish_sb(a1, SI1, kc, tjk, false, xn);
-    xn += __shfl_xor_sync(0xffffffffu, xn, 4);
-    xn += __shfl_xor_sync(0xffffffffu, xn, 8);
-    xn += __shfl_xor_sync(0xffffffffu, xn, 16);
+    const bool in0 = has0 && SI0 == SJk, in1 = SJ1 == SJk;
+    if (in0 || in1) {  // uniform
+      if (q == qk) {
+        if (in0) publish_sb(a0, SI0, kc, tjk, true, xn);
+        if (in1) publish_sb(a1, SI1, kc, tjk, false, xn);
+      }
+      xn += __shfl_xor_sync(0xffffffffu, xn, 4);
+      xn += __shfl_xor_sync(0xffffffffu, xn, 8);
+      xn += __shfl_xor_sync(0xffffffffu, xn, 16);
+    }
     if (lane == qk) sxn[kc & 1][w] = xn;
   };
 
   publish_col(0);
   const int kend = (nsteps < d - 1) ? nsteps : d - 1;
+  // the step loop exists twice: warps with / without a diagonal superblock (no per-step branches on it)
+  auto run = [&](auto has0_tag) {
+  constexpr bool HAS0 = decltype(has0_tag)::value;
   for (int k = 0; k < kend; ++k) {
     __syncthreads();  // #1: column k and its partial norms are visible
     const cplx *x = sx[k & 1];
@@ -301,9 +358,9 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
 #pragma unroll
     for (int i = 0; i < NW; ++i) xn += sxn[k & 1][i];
     const cplx alpha = x[k + 1];
-    const int mk = d - k - 2;
-    const size_t voff = (size_t)mk * (mk - 1) / 2;
-    if (xn == 0.0 && alpha.y == 0.0) {  // identity reflector (uniform: every thread sees the same values)
+    if (xn == 0.0 && alpha.y == 0.0) {
+      const int mk = d - k - 2;
+      const size_t voff = (size_t)mk * (mk - 1) / 2;  // identity reflector (uniform: every thread sees the same values)
       if (tid == 0) {
         eout[cfg * dstride + koff + k] = alpha.x;
         tauout[cfg * dstride + koff + k] = make_c(0.0, 0.0);
@@ -312,64 +369,73 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
       publish_col(k + 1);
       continue;
     }
-    // Householder scalars, redundantly per thread (rsqrt / rcp, no IEEE division)
+    // Householder scalars: beta (-> x'_{k+1}) redundantly per thread (rsqrt, no IEEE division); the rest by one
+    // thread, handed to the combine step through shared memory (keeps them out of the registers during the mat-vec)
     const double s2 = alpha.x * alpha.x + alpha.y * alpha.y + xn;
     const double ri = rsqrt(s2);
     const double sg = (alpha.x >= 0.0) ? -1.0 : 1.0;  // sign of beta
     const double beta = sg * (s2 * ri);
-    const double ib = sg * ri;
-    const cplx tau = make_c((beta - alpha.x) * ib, -alpha.y * ib);
-    const cplx xp0 = make_c(alpha.x - beta, alpha.y);  // x'_{k+1} = alpha - beta = 1/scale
+    const double xp0x = alpha.x - beta;  // x'_{k+1} = alpha - beta = 1/scale (imaginary part: alpha.y)
+    if (tid == 32 * (NW - 1)) {
+      const double ib = sg * ri;
+      const cplx tau = make_c((beta - alpha.x) * ib, -alpha.y * ib);
+      const double den = __drcp_rn(xp0x * xp0x + alpha.y * alpha.y);
+      const cplx scale = make_c(xp0x * den, -alpha.y * den);
+      const cplx ts = cmul(tau, scale);
+      // p^H v = conj(ts) scale x'^H A x' and tau conj(ts) scale = |tau|^2 |scale|^2 (real), |scale|^2 = den
+      ssc[0] = ts;
+      ssc[1] = scale;
+      ssc[2] = make_c(-0.5 * (tau.x * tau.x + tau.y * tau.y) * den, 0.0);
+      eout[cfg * dstride + koff + k] = beta;
+      tauout[cfg * dstride + koff + k] = tau;
+    }
 
-    // ---- partial products y = A22 x' ----
-    if (has0) hs_matvec_diag(a0, SI0, k, x, xp0, lane, ypart[SI0], ypart[S]);
-    hs_matvec_off(a1, SI1, SJ1, k, x, xp0, lane, ypart[SJ1], ypart[SI1]);
+    // ---- partial products y = A22 x' and the Hermitian form x'^H A22 x' ----
+    {
+      double qacc = 0.0;
+      if (HAS0) hs_matvec_diag(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
+      hs_matvec_off(a1, SI1, SJ1, k, x, xp0x, lane, ypart[SJ1], ypart[SI1], qacc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) qacc += __shfl_xor_sync(0xffffffffu, qacc, o);
+      if (lane == 0) sq[w] = qacc;
+    }
     __syncthreads();  // #2: the partial products are visible
 
-    if (w == WC) {  // combine: p = tau A v, v, a2 = -1/2 tau p^H v, w = p + a2 v
-      const double den = __drcp_rn(xp0.x * xp0.x + xp0.y * xp0.y);
-      const cplx scale = make_c(xp0.x * den, -xp0.y * den);
-      const cplx ts = cmul(tau, scale);
-      cplx vv[RPL], pp[RPL];
-      cplx dt = make_c(0.0, 0.0);
+    if (lane < RPW) {  // combine, RPW rows per warp: p = tau A v, v, a2 = -1/2 tau p^H v, w = p + a2 v -> DMMA operands
+      const int r = RPW * w + lane;
+      double Q = 0.0;
 #pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        const int r = lane + 32 * i;
-        vv[i] = make_c(0.0, 0.0);
-        pp[i] = make_c(0.0, 0.0);
-        if (r < D) {
-          cplx y = ypart[0][r];
+      for (int i = 0; i < NW; ++i) Q += sq[i];
+      const cplx ts = ssc[0], scale = ssc[1];
+      const double a2 = ssc[2].x * Q;
+      cplx y = ypart[0][r];
 #pragma unroll
-          for (int c = 1; c <= S; ++c) y = cadd(y, ypart[c][r]);
-          vv[i] = (r == k + 1) ? make_c(1.0, 0.0) : cmul(scale, x[r]);  // x[r] = 0 for r <= k
-          pp[i] = cmul(ts, y);
-          dt = cadd(dt, ccmul(pp[i], vv[i]));  // conj(p) v
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dt = cadd(dt, hs_shfl(dt, o));
-      // a2 is real for Hermitian A (its imaginary part is rounding noise)
-      const double a2 = -0.5 * (tau.x * dt.x - tau.y * dt.y);
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        const int r = lane + 32 * i;
-        if (r < D) {
-          sv[r] = vv[i];
-          sw[r] = make_c(fma(a2, vv[i].x, pp[i].x), fma(a2, vv[i].y, pp[i].y));
-          if (r >= k + 2 && r < d) Vp[cfg * vcap + voff + (r - k - 2)] = vv[i];  // reflector k for the back-transformation
-        }
-      }
-      if (lane == 0) {
-        eout[cfg * dstride + koff + k] = beta;
-        tauout[cfg * dstride + koff + k] = tau;
+      for (int c = 1; c <= S; ++c) y = cadd(y, ypart[c][r]);
+      cplx xr = sx[k & 1][r];  // x[r] = 0 for r <= k
+      cplx v = cmul(scale, xr);
+      if (r == k + 1) v = make_c(1.0, 0.0);
+      const cplx pv = cmul(ts, y);
+      const cplx ww = make_c(fma(a2, v.x, pv.x), fma(a2, v.y, pv.y));
+      reinterpret_cast<double4 *>(sAr)[r] = make_double4(-v.x, -v.y, -ww.x, -ww.y);
+      reinterpret_cast<double4 *>(sAi)[r] = make_double4(-v.y, v.x, -ww.y, ww.x);
+      reinterpret_cast<double4 *>(sB)[r] = make_double4(ww.x, ww.y, v.x, v.y);
+      const int iv = r - k - 2;  // reflector k for the back-transformation
+      if (iv >= 0 && r < d) {
+        const int mk = d - k - 2;
+        Vp[cfg * vcap + (size_t)mk * (mk - 1) / 2 + iv] = v;
       }
     }
-    __syncthreads();  // #3: v and w are visible
+    __syncthreads();  // #3: the update operands are visible
 
-    if (has0) hs_update<true>(a0, SI0, SI0, k, sv, sw, lane);
-    hs_update<false>(a1, SI1, SJ1, k, sv, sw, lane);
+    if (HAS0) hs_update<true>(a0, SI0, SI0, k, sAr, sAi, sB, lane);
+    hs_update<false>(a1, SI1, SJ1, k, sAr, sAi, sB, lane);
     publish_col(k + 1);
   }
+  };
+  if (has0)
+    run(std::true_type{});
+  else
+    run(std::false_type{});
   if (kend == d - 1) {
     if (tid == 0) eout[cfg * dstride + koff + d - 1] = 0.0;
   } else {  // hand the trailing block (both triangles) to the next phase

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(32 * TRW_WARPS)
 hql_tridiag_warpf_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cplx *__restrict__ Z,
                          const double *__restrict__ Bf, const cplx *__restrict__ Ain,
                          double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Vp,
-                         size_t vcap, cplx *__restrict__ tauout) {
+                         size_t vcap, cplx *__restrict__ tauout, int dstride, int koff) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ld = d | 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,11 +182,11 @@ hql_tridiag_warpf_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cp
     xn = warp_sum(xn);
     const cplx alpha = make_c(__shfl_sync(0xffffffffu, x.x, k + 1), __shfl_sync(0xffffffffu, x.y, k + 1));
     const double dk = __shfl_sync(0xffffffffu, akk, k);
-    if (lane == 0) dout[cfg * d + k] = dk;
+    if (lane == 0) dout[cfg * dstride + koff + k] = dk;
     if (xn == 0.0 && alpha.y == 0.0) {  // H_k = I
       if (lane == 0) {
-        eout[cfg * d + k] = alpha.x;
-        tauout[cfg * d + k] = make_c(0.0, 0.0);
+        eout[cfg * dstride + koff + k] = alpha.x;
+        tauout[cfg * dstride + koff + k] = make_c(0.0, 0.0);
       }
       for (int i = lane; i < mk; i += 32) Vp[cfg * vcap + voff + i] = make_c(0.0, 0.0);
       v = make_c(0.0, 0.0);
@@ -208,8 +208,8 @@ hql_tridiag_warpf_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cp
     else if (r > k + 1 && r < d)
       v = cmul(scale, x);
     if (lane == 0) {
-      eout[cfg * d + k] = beta;
-      tauout[cfg * d + k] = tau;
+      eout[cfg * dstride + koff + k] = beta;
+      tauout[cfg * dstride + koff + k] = tau;
     }
     if (r >= k + 2 && r < d) Vp[cfg * vcap + voff + (r - k - 2)] = v;
   };
@@ -257,8 +257,8 @@ hql_tridiag_warpf_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cp
     if (k == d - 2) {  // last step: only the final diagonal entry remains
       const double dl = __shfl_sync(0xffffffffu, a1.x, d - 1);
       if (lane == 0) {
-        dout[cfg * d + d - 1] = dl;
-        eout[cfg * d + d - 1] = 0.0;
+        dout[cfg * dstride + koff + d - 1] = dl;
+        eout[cfg * dstride + koff + d - 1] = 0.0;
       }
       break;
     }
@@ -301,8 +301,8 @@ hql_tridiag_warpf_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cp
     __syncwarp();
   }
   if (d == 1 && lane == 0) {
-    dout[cfg * d] = sA[0].x;
-    eout[cfg * d] = 0.0;
+    dout[cfg * dstride + koff] = sA[0].x;
+    eout[cfg * dstride + koff] = 0.0;
   }
 }
 
