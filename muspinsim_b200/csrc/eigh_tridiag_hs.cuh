@@ -46,6 +46,9 @@ struct HsGeom {
 };
 
 __device__ __forceinline__ cplx hs_shfl(cplx v, int m) {
+#ifdef HS_NOSHFL
+  return v;
+#endif
   return make_c(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 __device__ __forceinline__ cplx hs_sel(bool c, cplx a, cplx b) { return make_c(c ? a.x : b.x, c ? a.y : b.y); }
@@ -90,7 +93,7 @@ __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[3][3], int SI, i
     for (int ti = 0; ti < 3; ++ti) yr[ti] = make_c(0.0, 0.0);
 #pragma unroll
     for (int tj = 0; tj < 3; ++tj) {
-      if (24 * SJ + 8 * tj + 7 > k) {  // tile column has live columns (uniform)
+      {  // (dead columns <= k have x = 0: no liveness branch, the straight-line code schedules better)
         cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];  // zero for columns <= k (publish_col)
         if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
         if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
@@ -112,7 +115,7 @@ __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[3][3], int SI, i
 #pragma unroll
     for (int tj = 0; tj < 3; ++tj) {
       cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
-      if (24 * SJ + 8 * tj + 7 > k) {
+      {
 #pragma unroll
         for (int ti = 0; ti < 3; ++ti) {
           ccfma(yc0, make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xr[ti]);
@@ -209,7 +212,7 @@ __device__ __forceinline__ void hs_update(HsTile (&a)[3][3], int SI, int SJ, int
   for (int tj = 0; tj < 3; ++tj) bb[tj] = sB[4 * (24 * SJ + 8 * tj) + lane];  // [column 8 J + g][q]
 #pragma unroll
   for (int tj = 0; tj < 3; ++tj) {
-    if (24 * SJ + 8 * tj + 7 > k) {
+    if (!DIAG || 24 * SJ + 8 * tj + 7 > k) {  // off-diagonal superblocks: dead columns are updated too (never read again)
 #pragma unroll
       for (int ti = (DIAG ? tj : 0); ti < 3; ++ti) {
         dmma884(a[ti][tj].re[0], a[ti][tj].re[1], are[ti], bb[tj]);
@@ -349,10 +352,20 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
   publish_col(0);
   const int kend = (nsteps < d - 1) ? nsteps : d - 1;
   // the step loop exists twice: warps with / without a diagonal superblock (no per-step branches on it)
+#ifdef HS_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define HS_T(i) { long long t_ = clock64(); tacc[i] += t_ - tprev; tprev = t_; }
+#else
+#define HS_T(i)
+#endif
   auto run = [&](auto has0_tag) {
   constexpr bool HAS0 = decltype(has0_tag)::value;
+#ifdef HS_TIMING
+  long long tprev = clock64();
+#endif
   for (int k = 0; k < kend; ++k) {
     __syncthreads();  // #1: column k and its partial norms are visible
+    HS_T(0)
     const cplx *x = sx[k & 1];
     double xn = 0.0;
 #pragma unroll
@@ -390,6 +403,7 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
       tauout[cfg * dstride + koff + k] = tau;
     }
 
+    HS_T(1)
     // ---- partial products y = A22 x' and the Hermitian form x'^H A22 x' ----
     {
       double qacc = 0.0;
@@ -399,7 +413,9 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
       for (int o = 16; o > 0; o >>= 1) qacc += __shfl_xor_sync(0xffffffffu, qacc, o);
       if (lane == 0) sq[w] = qacc;
     }
+    HS_T(2)
     __syncthreads();  // #2: the partial products are visible
+    HS_T(3)
 
     if (lane < RPW) {  // combine, RPW rows per warp: p = tau A v, v, a2 = -1/2 tau p^H v, w = p + a2 v -> DMMA operands
       const int r = RPW * w + lane;
@@ -425,17 +441,26 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
         Vp[cfg * vcap + (size_t)mk * (mk - 1) / 2 + iv] = v;
       }
     }
+    HS_T(4)
     __syncthreads();  // #3: the update operands are visible
+    HS_T(5)
 
     if (HAS0) hs_update<true>(a0, SI0, SI0, k, sAr, sAi, sB, lane);
     hs_update<false>(a1, SI1, SJ1, k, sAr, sAi, sB, lane);
+    HS_T(6)
     publish_col(k + 1);
+    HS_T(7)
   }
   };
   if (has0)
     run(std::true_type{});
   else
     run(std::false_type{});
+#ifdef HS_TIMING
+  if (blockIdx.x == 0 && lane == 0)
+    printf("HS_T NT %d w %d steps %d: B1 %lld scal %lld mv %lld B2 %lld comb %lld B3 %lld upd %lld pub %lld\n", NT, w, kend, tacc[0] / kend,
+           tacc[1] / kend, tacc[2] / kend, tacc[3] / kend, tacc[4] / kend, tacc[5] / kend, tacc[6] / kend, tacc[7] / kend);
+#endif
   if (kend == d - 1) {
     if (tid == 0) eout[cfg * dstride + koff + d - 1] = 0.0;
   } else {  // hand the trailing block (both triangles) to the next phase
