@@ -225,13 +225,13 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
           else
             hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
         } else if (o.tridiag_hs && d > 48) {
-          // live block d -> 72 -> 48 (half-storage DMMA kernel, 2 / 3 matrices per SM) -> 24 -> done (rows-per-warp kernel)
+          // live block d -> 72 -> 48 (half-storage DMMA kernel, 2 / 4 matrices per SM) -> 32 (rows-per-warp kernel) -> done (warp per matrix)
           cplx *bufs[2] = {ws.Q[buf], ws.Q[buf] + (size_t)n * 72 * 72};
           int cur = d, koff = 0, ib = 0, nl = 0;
           const cplx *in = Ain;
           bool first = true;
           for (;;) {
-            const int nxt = cur > 72 ? 72 : (cur > 48 ? 48 : (cur > 24 ? 24 : 0));
+            const int nxt = cur > 72 ? 72 : (cur > 48 ? 48 : (cur > 32 ? 32 : 0));
             const int steps = nxt ? cur - nxt : cur;
             cplx *out = nxt ? bufs[ib] : nullptr;
             const cplx *h0 = first ? H0 : nullptr, *zz = first ? Z : nullptr;
