@@ -237,11 +237,11 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
             const cplx *h0 = first ? H0 : nullptr, *zz = first ? Z : nullptr;
             const double *bb = first ? B : nullptr;
             if (cur > 72)
-              hql_tridiag_hs_kernel<12><<<g, 32 * HsGeom<12>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+              hql_tridiag_hs_kernel<12, 3><<<g, 32 * HsGeom<12, 3>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
             else if (cur > 48)
-              hql_tridiag_hs_kernel<9><<<g, 32 * HsGeom<9>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+              hql_tridiag_hs_kernel<9, 3><<<g, 32 * HsGeom<9, 3>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
             else if (cur > 32)
-              hql_tridiag_rw_kernel<48><<<g, 192, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+              hql_tridiag_hs_kernel<6, 2><<<g, 32 * HsGeom<6, 2>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
             else if (!first && o.tridiag_warp && o.tridiag_fused) {  // last phase: warp per matrix, no block barriers
               const size_t sm = hql_tridiag_warpf_smem(cur);
               cudaFuncSetAttribute(hql_tridiag_warpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -11,6 +11,7 @@
 //     elements (row g, columns 2q, 2q + 1).  A warp owns one off-diagonal superblock (9 tiles) and, warps
 //     0 .. S-1, the lower 6 tiles of a diagonal one: 120 registers of matrix per thread, 168 in all, i.e.
 //     three warps per scheduler: TWO 96 x 96 matrices per SM (four at 72 x 72), whose phases overlap;
+//     the 48 x 48 phase uses superblocks of 2 x 2 tiles (T = 2: 56 registers of matrix, six CTAs per SM);
 //   * the rank-2 update A -= v w^H + w v^H is exactly one k = 4 DMMA per tile and per part:
 //     Re -= [v_r.x v_r.y w_r.x w_r.y] . [w_c.x w_c.y v_c.x v_c.y]^T, Im likewise with the row operand
 //     permuted -- 2 DMMAs per tile instead of 128 DFMAs per warp, and the operands are ONE 16-byte
@@ -37,12 +38,14 @@ struct HsTile {
   double re[2], im[2];
 };
 
-template <int NT>
+// NT tiles of 8 per side, superblocks of T x T tiles: (12, 3) = 96, (9, 3) = 72, (6, 2) = 48.
+template <int NT, int T>
 struct HsGeom {
-  static constexpr int S = NT / 3;              // superblock rows
+  static constexpr int S = NT / T;              // superblock rows (4 or 3)
   static constexpr int NW = S * (S - 1) / 2;    // warps = off-diagonal superblocks (6 or 3)
   static constexpr int D = 8 * NT;
-  static constexpr int CTAS = 12 / NW;          // 12 warps per SM at 168 registers
+  static constexpr int TB = 8 * T;              // rows of a superblock
+  static constexpr int CTAS = (T == 3) ? 12 / NW : 5;  // T = 3: 12 warps per SM at 168 registers
 };
 
 __device__ __forceinline__ cplx hs_shfl(cplx v, int m) {
@@ -53,17 +56,23 @@ __device__ __forceinline__ cplx hs_shfl(cplx v, int m) {
 }
 __device__ __forceinline__ cplx hs_sel(bool c, cplx a, cplx b) { return make_c(c ? a.x : b.x, c ? a.y : b.y); }
 
-// Reduce three per-row-tile values over the 4 lanes of a row: lane q ends up with row tile q (q = 3
-// duplicates tile 2) and stores it.
-__device__ __forceinline__ void hs_reduce_rows(const cplx (&yr)[3], int lane, cplx *dst) {
+// Reduce T per-row-tile values over the 4 lanes of a row: lane q ends up with row tile q (higher q
+// duplicate the last tile) and stores it.
+template <int T>
+__device__ __forceinline__ void hs_reduce_rows(const cplx (&yr)[T], int lane, cplx *dst) {
   const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
-  const cplx rcv = hs_shfl(hs_sel(b0, yr[0], yr[1]), 1);
-  const cplx t = cadd(hs_sel(b0, yr[1], yr[0]), rcv);
-  const cplx t2 = cadd(yr[2], hs_shfl(yr[2], 1));
-  const cplx rcv2 = hs_shfl(hs_sel(b1, t, t2), 2);
-  const cplx f = cadd(hs_sel(b1, t2, t), rcv2);
   const int g = lane >> 2, q = lane & 3;
-  if (q < 3) dst[8 * q + g] = f;
+  const cplx rcv = hs_shfl(hs_sel(b0, yr[0], yr[1]), 1);
+  const cplx t = cadd(hs_sel(b0, yr[1], yr[0]), rcv);  // tile b0
+  if (T == 3) {
+    const cplx t2 = cadd(yr[T - 1], hs_shfl(yr[T - 1], 1));
+    const cplx rcv2 = hs_shfl(hs_sel(b1, t, t2), 2);
+    const cplx f = cadd(hs_sel(b1, t2, t), rcv2);
+    if (q < 3) dst[8 * q + g] = f;
+  } else {
+    const cplx f = cadd(t, hs_shfl(t, 2));
+    if (q < 2) dst[8 * q + g] = f;
+  }
 }
 // Stage 1 of the reduction over the 8 lanes of a column: two columns -> one (column 2q + g0).
 __device__ __forceinline__ cplx hs_reduce_cols1(cplx yc0, cplx yc1, int lane) {
@@ -71,112 +80,130 @@ __device__ __forceinline__ cplx hs_reduce_cols1(cplx yc0, cplx yc1, int lane) {
   const cplx rcv = hs_shfl(hs_sel(g0, yc0, yc1), 4);
   return cadd(hs_sel(g0, yc1, yc0), rcv);
 }
+// Stages 2 and 3 for NU tile columns (u[tj] = column 2q + g0 of tile tj) and the store.
+template <int NU>
+__device__ __forceinline__ void hs_reduce_cols23(const cplx (&u)[NU > 0 ? NU : 1], int lane, cplx *dst) {
+  const bool g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
+  const int col = 2 * (lane & 3) + ((lane >> 2) & 1);
+  if (NU == 3) {
+    const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
+    const cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
+    const cplx z2 = cadd(u[NU - 1], hs_shfl(u[NU - 1], 8));
+    const cplx rcv2 = hs_shfl(hs_sel(g2, z, z2), 16);
+    const cplx f = cadd(hs_sel(g2, z2, z), rcv2);  // g2 = 0: tile g1, g2 = 1: tile 2
+    if (!(g1 && g2)) dst[8 * (g2 ? 2 : (g1 ? 1 : 0)) + col] = f;
+  } else if (NU == 2) {
+    const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
+    cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
+    z = cadd(z, hs_shfl(z, 16));
+    if (!g2) dst[8 * (g1 ? 1 : 0) + col] = z;
+  } else if (NU == 1) {
+    cplx z = cadd(u[0], hs_shfl(u[0], 8));
+    z = cadd(z, hs_shfl(z, 16));
+    if (!g1 && !g2) dst[col] = z;
+  }
+}
 
 // y += A x' over an OFF-DIAGONAL superblock (SI > SJ): row direction y_I += A x_J (partial sums to
-// yrow_dst[24 SI + ...]) and column direction y_J += A^H x_I (partial sums to ycol_dst[24 SJ + ...]).
+// yrow_dst[TB SI + ...]) and column direction y_J += A^H x_I (partial sums to ycol_dst[TB SJ + ...]).
 // x' = x except x'_{k+1} = alpha - beta: only the real part differs (xp0x).  qacc += 2 Re(x_I^H A x_J).
-__device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[3][3], int SI, int SJ, int k, const cplx *x, double xp0x,
+template <int T>
+__device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[T][T], int SI, int SJ, int k, const cplx *x, double xp0x,
                                               int lane, cplx *yrow_dst, cplx *ycol_dst, double &qacc) {
+  constexpr int TB = 8 * T;
   const int g = lane >> 2, q = lane & 3;
-  const int r0 = 24 * SI + g, c0 = 24 * SJ + 2 * q;
-  cplx xr[3];
+  const int r0 = TB * SI + g, c0 = TB * SJ + 2 * q;
+  cplx xr[T];
 #pragma unroll
-  for (int ti = 0; ti < 3; ++ti) {
+  for (int ti = 0; ti < T; ++ti) {
     xr[ti] = x[r0 + 8 * ti];
     if (r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
   }
   // two passes over the register tiles (rows, then columns) keep the live set small: 168 registers
   // hold 120 of matrix, and the one-pass version spilled
   {
-    cplx yr[3];
+    cplx yr[T];
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti) yr[ti] = make_c(0.0, 0.0);
+    for (int ti = 0; ti < T; ++ti) yr[ti] = make_c(0.0, 0.0);
 #pragma unroll
-    for (int tj = 0; tj < 3; ++tj) {
-      {  // (dead columns <= k have x = 0: no liveness branch, the straight-line code schedules better)
-        cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];  // zero for columns <= k (publish_col)
-        if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
-        if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
+    for (int tj = 0; tj < T; ++tj) {
+      // (dead columns <= k have x = 0: no liveness branch, the straight-line code schedules better)
+      cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];  // zero for columns <= k (publish_col)
+      if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
+      if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
 #pragma unroll
-        for (int ti = 0; ti < 3; ++ti) {
-          cfma(yr[ti], make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xc0);
-          cfma(yr[ti], make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xc1);
-        }
+      for (int ti = 0; ti < T; ++ti) {
+        cfma(yr[ti], make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xc0);
+        cfma(yr[ti], make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xc1);
       }
     }
     double t = 0.0;
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti) t = fma(xr[ti].x, yr[ti].x, fma(xr[ti].y, yr[ti].y, t));
+    for (int ti = 0; ti < T; ++ti) t = fma(xr[ti].x, yr[ti].x, fma(xr[ti].y, yr[ti].y, t));
     qacc = fma(2.0, t, qacc);
-    hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
+    hs_reduce_rows<T>(yr, lane, yrow_dst + TB * SI);
   }
   {
-    cplx u[3];
+    cplx u[T];
 #pragma unroll
-    for (int tj = 0; tj < 3; ++tj) {
+    for (int tj = 0; tj < T; ++tj) {
       cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
-      {
 #pragma unroll
-        for (int ti = 0; ti < 3; ++ti) {
-          ccfma(yc0, make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xr[ti]);
-          ccfma(yc1, make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xr[ti]);
-        }
+      for (int ti = 0; ti < T; ++ti) {
+        ccfma(yc0, make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xr[ti]);
+        ccfma(yc1, make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xr[ti]);
       }
       u[tj] = hs_reduce_cols1(yc0, yc1, lane);
     }
-    const bool g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
-    const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
-    const cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
-    const cplx z2 = cadd(u[2], hs_shfl(u[2], 8));
-    const cplx rcv2 = hs_shfl(hs_sel(g2, z, z2), 16);
-    const cplx f = cadd(hs_sel(g2, z2, z), rcv2);  // g2 = 0: tile g1, g2 = 1: tile 2
-    if (!(g1 && g2)) ycol_dst[24 * SJ + 8 * (g2 ? 2 : (g1 ? 1 : 0)) + 2 * q + ((lane >> 2) & 1)] = f;
+    hs_reduce_cols23<T>(u, lane, ycol_dst + TB * SJ);
   }
 }
 
 // The same over the lower tiles (tj <= ti) of the DIAGONAL superblock SI: the diagonal tiles are full
-// Hermitian 8 x 8 blocks (row direction only), the three tiles below them work in both directions.
+// Hermitian 8 x 8 blocks (row direction only), the tiles below them work in both directions.
 // qacc += x_I^H A_II x_I (row- and column-direction partial products together cover the whole block).
-__device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[3][3], int SI, int k, const cplx *x, double xp0x,
+template <int T>
+__device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, int k, const cplx *x, double xp0x,
                                                int lane, cplx *yrow_dst, cplx *ycol_dst, double &qacc) {
+  constexpr int TB = 8 * T;
   const int g = lane >> 2, q = lane & 3;
-  const int r0 = 24 * SI + g, c0 = 24 * SI + 2 * q;
-  cplx xr[3];
+  const int r0 = TB * SI + g, c0 = TB * SI + 2 * q;
+  cplx xr[T];
   double t = 0.0;
 #pragma unroll
-  for (int ti = 0; ti < 3; ++ti) {
+  for (int ti = 0; ti < T; ++ti) {
     xr[ti] = x[r0 + 8 * ti];
     if (r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
   }
   {  // row direction (pass 1)
-    cplx yr[3];
+    cplx yr[T];
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti) yr[ti] = make_c(0.0, 0.0);
+    for (int ti = 0; ti < T; ++ti) yr[ti] = make_c(0.0, 0.0);
 #pragma unroll
-    for (int tj = 0; tj < 3; ++tj) {
-      if (24 * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
+    for (int tj = 0; tj < T; ++tj) {
+      if (TB * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
         cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
         if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
         if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
 #pragma unroll
-        for (int ti = tj; ti < 3; ++ti) {
+        for (int ti = tj; ti < T; ++ti) {
           cfma(yr[ti], make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xc0);
           cfma(yr[ti], make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xc1);
         }
       }
     }
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti) t = fma(xr[ti].x, yr[ti].x, fma(xr[ti].y, yr[ti].y, t));
-    hs_reduce_rows(yr, lane, yrow_dst + 24 * SI);
+    for (int ti = 0; ti < T; ++ti) t = fma(xr[ti].x, yr[ti].x, fma(xr[ti].y, yr[ti].y, t));
+    hs_reduce_rows<T>(yr, lane, yrow_dst + TB * SI);
   }
   {  // column direction of the tiles below the diagonal (pass 2)
-    cplx u[2];
+    cplx u[T - 1];
 #pragma unroll
-    for (int tj = 0; tj < 2; ++tj) {
+    for (int tj = 0; tj < T - 1; ++tj) {
       cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
-      if (24 * SI + 8 * tj + 7 > k) {
+      if (TB * SI + 8 * tj + 7 > k) {
 #pragma unroll
-        for (int ti = tj + 1; ti < 3; ++ti) {
+        for (int ti = tj + 1; ti < T; ++ti) {
           ccfma(yc0, make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xr[ti]);
           ccfma(yc1, make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xr[ti]);
         }
@@ -188,33 +215,30 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[3][3], int SI, 
       u[tj] = hs_reduce_cols1(yc0, yc1, lane);
     }
     qacc += t;
-    const bool g1 = (lane & 8) != 0, g2 = (lane & 16) != 0;
-    const cplx rcv = hs_shfl(hs_sel(g1, u[0], u[1]), 8);
-    cplx z = cadd(hs_sel(g1, u[1], u[0]), rcv);  // tile g1
-    z = cadd(z, hs_shfl(z, 16));
-    if (!g2) ycol_dst[24 * SI + 8 * (g1 ? 1 : 0) + 2 * q + ((lane >> 2) & 1)] = z;
+    hs_reduce_cols23<T - 1>(u, lane, ycol_dst + TB * SI);
   }
 }
 
 // A -= v w^H + w v^H on one superblock: two DMMAs per live tile.  DIAG: lower tiles only.
 // Operands in shared memory, already in fragment order (written by the combine step):
 //   sAr[r] = -(v.x, v.y, w.x, w.y), sAi[r] = (-v.y, v.x, -w.y, w.x), sB[c] = (w.x, w.y, v.x, v.y).
-template <bool DIAG>
-__device__ __forceinline__ void hs_update(HsTile (&a)[3][3], int SI, int SJ, int k, const double *sAr, const double *sAi,
+template <int T, bool DIAG>
+__device__ __forceinline__ void hs_update(HsTile (&a)[T][T], int SI, int SJ, int k, const double *sAr, const double *sAi,
                                           const double *sB, int lane) {
-  double are[3], aim[3], bb[3];
+  constexpr int TB = 8 * T;
+  double are[T], aim[T], bb[T];
 #pragma unroll
-  for (int ti = 0; ti < 3; ++ti) {
-    are[ti] = sAr[4 * (24 * SI + 8 * ti) + lane];  // [row 8 I + g][q]
-    aim[ti] = sAi[4 * (24 * SI + 8 * ti) + lane];
+  for (int ti = 0; ti < T; ++ti) {
+    are[ti] = sAr[4 * (TB * SI + 8 * ti) + lane];  // [row 8 I + g][q]
+    aim[ti] = sAi[4 * (TB * SI + 8 * ti) + lane];
   }
 #pragma unroll
-  for (int tj = 0; tj < 3; ++tj) bb[tj] = sB[4 * (24 * SJ + 8 * tj) + lane];  // [column 8 J + g][q]
+  for (int tj = 0; tj < T; ++tj) bb[tj] = sB[4 * (TB * SJ + 8 * tj) + lane];  // [column 8 J + g][q]
 #pragma unroll
-  for (int tj = 0; tj < 3; ++tj) {
-    if (!DIAG || 24 * SJ + 8 * tj + 7 > k) {  // off-diagonal superblocks: dead columns are updated too (never read again)
+  for (int tj = 0; tj < T; ++tj) {
+    if (!DIAG || TB * SJ + 8 * tj + 7 > k) {  // off-diagonal superblocks: dead columns are updated too (never read again)
 #pragma unroll
-      for (int ti = (DIAG ? tj : 0); ti < 3; ++ti) {
+      for (int ti = (DIAG ? tj : 0); ti < T; ++ti) {
         dmma884(a[ti][tj].re[0], a[ti][tj].re[1], are[ti], bb[tj]);
         dmma884(a[ti][tj].im[0], a[ti][tj].im[1], aim[ti], bb[tj]);
       }
@@ -222,15 +246,16 @@ __device__ __forceinline__ void hs_update(HsTile (&a)[3][3], int SI, int SJ, int
   }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(32 * HsGeom<NT>::NW, HsGeom<NT>::CTAS)
+template <int NT, int T>
+__global__ void __launch_bounds__(32 * HsGeom<NT, T>::NW, HsGeom<NT, T>::CTAS)
 hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__restrict__ H0,
                       const cplx *__restrict__ Z, const double *__restrict__ Bf, const cplx *__restrict__ Ain,
                       double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Vp, size_t vcap,
                       cplx *__restrict__ tauout, cplx *__restrict__ Aout) {
-  using G = HsGeom<NT>;
-  constexpr int S = G::S, NW = G::NW, D = G::D;
+  using G = HsGeom<NT, T>;
+  constexpr int S = G::S, NW = G::NW, D = G::D, TB = G::TB;
   constexpr int RPW = D / NW;  // rows per warp in the combine step (16 or 24)
+  static_assert(RPW <= 32 && RPW * NW == D, "combine step: one row per lane");
   __shared__ __align__(16) cplx sx[2][D];        // column k of the trailing matrix, by parity of k
   __shared__ __align__(16) double sxn[2][8];     // per-warp partial ||x[2:]||^2, by parity of k
   __shared__ __align__(16) double sq[8];         // per-warp partial x'^H A x'
@@ -248,7 +273,7 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
   const bool has0 = w < S;
   const int SI0 = has0 ? w : 0;
   int SI1, SJ1;
-  if (NT == 12) {
+  if (S == 4) {
     // w = 0: (3,2)  1: (3,1)  2: (2,1)  3: (3,0)  4: (1,0)  5: (2,0)
     SI1 = (w == 2 || w == 5) ? 2 : ((w == 4) ? 1 : 3);
     SJ1 = (w == 0) ? 2 : ((w == 1 || w == 2) ? 1 : 0);
@@ -257,7 +282,7 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
     SJ1 = (w == 0) ? 1 : 0;
   }
 
-  HsTile a0[3][3], a1[3][3];  // a0: only tj <= ti is used
+  HsTile a0[T][T], a1[T][T];  // a0: only tj <= ti is used
   {
     double bx = 0, by = 0, bz = 0;
     if (!Ain) {
@@ -282,18 +307,18 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
       return v;
     };
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti)
+    for (int ti = 0; ti < T; ++ti)
 #pragma unroll
-      for (int tj = 0; tj < 3; ++tj)
+      for (int tj = 0; tj < T; ++tj)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (tj <= ti) {
             cplx v = make_c(0.0, 0.0);
-            if (has0) v = load_elem(24 * SI0 + 8 * ti + g, 24 * SI0 + 8 * tj + 2 * q + s);
+            if (has0) v = load_elem(TB * SI0 + 8 * ti + g, TB * SI0 + 8 * tj + 2 * q + s);
             a0[ti][tj].re[s] = v.x;
             a0[ti][tj].im[s] = v.y;
           }
-          const cplx v1 = load_elem(24 * SI1 + 8 * ti + g, 24 * SJ1 + 8 * tj + 2 * q + s);
+          const cplx v1 = load_elem(TB * SI1 + 8 * ti + g, TB * SJ1 + 8 * tj + 2 * q + s);
           a1[ti][tj].re[s] = v1.x;
           a1[ti][tj].im[s] = v1.y;
         }
@@ -303,27 +328,27 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
   // Publish column kc of the (updated) matrix for rows > kc, the partial norms of rows > kc + 1 and
   // the diagonal element.  In half storage column kc lives in the superblocks (., kc / 24); the tile
   // column and the fragment slot are uniform, so they are branches, not selects.
-  auto publish_sb = [&](const HsTile (&a)[3][3], int SI, int kc, int tjk, bool diag, double &xn) {
+  auto publish_sb = [&](const HsTile (&a)[T][T], int SI, int kc, int tjk, bool diag, double &xn) {
     const int par = kc & 1;
-    cplx v[3];
+    cplx v[T];
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti) v[ti] = make_c(0.0, 0.0);
+    for (int ti = 0; ti < T; ++ti) v[ti] = make_c(0.0, 0.0);
 #pragma unroll
-    for (int tj = 0; tj < 3; ++tj)
+    for (int tj = 0; tj < T; ++tj)
       if (tj == tjk) {
         if (kc & 1) {
 #pragma unroll
-          for (int ti = 0; ti < 3; ++ti)
+          for (int ti = 0; ti < T; ++ti)
             if (!diag || tj <= ti) v[ti] = make_c(a[ti][tj].re[1], a[ti][tj].im[1]);
         } else {
 #pragma unroll
-          for (int ti = 0; ti < 3; ++ti)
+          for (int ti = 0; ti < T; ++ti)
             if (!diag || tj <= ti) v[ti] = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
         }
       }
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti) {
-      const int r = 24 * SI + 8 * ti + g;
+    for (int ti = 0; ti < T; ++ti) {
+      const int r = TB * SI + 8 * ti + g;
       if (r > kc) sx[par][r] = v[ti];  // (diagonal superblock: tiles above the diagonal only hold rows < kc)
       if (r > kc + 1) xn = fma(v[ti].y, v[ti].y, fma(v[ti].x, v[ti].x, xn));  // rows >= d hold zeros
       if (r == kc) {
@@ -334,7 +359,7 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
     }
   };
   auto publish_col = [&](int kc) {
-    const int J = kc >> 3, SJk = J / 3, tjk = J - 3 * SJk, qk = (kc & 7) >> 1;
+    const int J = kc >> 3, SJk = J / T, tjk = J - T * SJk, qk = (kc & 7) >> 1;
     double xn = 0.0;
     const bool in0 = has0 && SI0 == SJk, in1 = SJ1 == SJk;
     if (in0 || in1) {  // uniform
@@ -407,8 +432,8 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
     // ---- partial products y = A22 x' and the Hermitian form x'^H A22 x' ----
     {
       double qacc = 0.0;
-      if (HAS0) hs_matvec_diag(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
-      hs_matvec_off(a1, SI1, SJ1, k, x, xp0x, lane, ypart[SJ1], ypart[SI1], qacc);
+      if (HAS0) hs_matvec_diag<T>(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
+      hs_matvec_off<T>(a1, SI1, SJ1, k, x, xp0x, lane, ypart[SJ1], ypart[SI1], qacc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) qacc += __shfl_xor_sync(0xffffffffu, qacc, o);
       if (lane == 0) sq[w] = qacc;
@@ -445,8 +470,8 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
     __syncthreads();  // #3: the update operands are visible
     HS_T(5)
 
-    if (HAS0) hs_update<true>(a0, SI0, SI0, k, sAr, sAi, sB, lane);
-    hs_update<false>(a1, SI1, SJ1, k, sAr, sAi, sB, lane);
+    if (HAS0) hs_update<T, true>(a0, SI0, SI0, k, sAr, sAi, sB, lane);
+    hs_update<T, false>(a1, SI1, SJ1, k, sAr, sAi, sB, lane);
     HS_T(6)
     publish_col(k + 1);
     HS_T(7)
@@ -473,14 +498,14 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
       }
     };
 #pragma unroll
-    for (int ti = 0; ti < 3; ++ti)
+    for (int ti = 0; ti < T; ++ti)
 #pragma unroll
-      for (int tj = 0; tj < 3; ++tj)
+      for (int tj = 0; tj < T; ++tj)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (tj <= ti && has0)
-            store_elem(24 * SI0 + 8 * ti + g, 24 * SI0 + 8 * tj + 2 * q + s, make_c(a0[ti][tj].re[s], a0[ti][tj].im[s]), tj < ti);
-          store_elem(24 * SI1 + 8 * ti + g, 24 * SJ1 + 8 * tj + 2 * q + s, make_c(a1[ti][tj].re[s], a1[ti][tj].im[s]), true);
+            store_elem(TB * SI0 + 8 * ti + g, TB * SI0 + 8 * tj + 2 * q + s, make_c(a0[ti][tj].re[s], a0[ti][tj].im[s]), tj < ti);
+          store_elem(TB * SI1 + 8 * ti + g, TB * SJ1 + 8 * tj + 2 * q + s, make_c(a1[ti][tj].re[s], a1[ti][tj].im[s]), true);
         }
   }
 }
