@@ -29,6 +29,7 @@ struct EighOpts {
   bool apply_warp = true;      // "apply_warp": rotation replay with one warp per CTA (d > 32)
   int tql_threads = 0;         // "tql_threads": matrices per block of the QL kernel (8, 16 or 32; 0 = auto: 32 for d <= 32, else 16)
   bool tridiag_rw = true;      // "tridiag_rw": rows-per-warp register tridiagonalisation (d <= 96); 0: shared-memory kernel
+  bool tridiag_hsw = false;    // "tridiag_hsw": register-resident half-storage warp kernel for 8 < d <= 32 (and the last phase of larger d) instead of the shared-memory warp kernel: same speed at d = 32, 4 % slower at d = 24 (cross-check)
   bool tridiag_hs = true;      // "tridiag_hs": half-storage DMMA tridiagonalisation for the phases with a live block > 48 (48 < d <= 96)
   bool use_reflect(int d) const { return reflect && d >= 3 && d <= 96; }
 };
@@ -170,6 +171,17 @@ struct EighWs {
   }
 };
 
+inline void launch_tridiag_hsw(int d, int64_t n, const cplx *H0, const cplx *Z, const double *B, const cplx *Ain, double *dd_,
+                               double *ee_, cplx *vp_, size_t vcap, cplx *tt_, int dstride, int koff, cudaStream_t st) {
+  const unsigned grid = (unsigned)((n + HSW_WARPS - 1) / HSW_WARPS);
+  if (d <= 16)
+    hql_tridiag_hsw_kernel<2><<<grid, 32 * HSW_WARPS, 0, st>>>(d, n, H0, Z, B, Ain, dd_, ee_, vp_, vcap, tt_, dstride, koff);
+  else if (d <= 24)
+    hql_tridiag_hsw_kernel<3><<<grid, 32 * HSW_WARPS, 0, st>>>(d, n, H0, Z, B, Ain, dd_, ee_, vp_, vcap, tt_, dstride, koff);
+  else
+    hql_tridiag_hsw_kernel<4><<<grid, 32 * HSW_WARPS, 0, st>>>(d, n, H0, Z, B, Ain, dd_, ee_, vp_, vcap, tt_, dstride, koff);
+}
+
 // Stage A of the Householder+QL solver: tridiagonalise + form Q into buffer set `buf`.
 // (For Jacobi, stage A is the whole solver.)  Returns 0, a cudaError_t (> 0), or -5.
 inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, const cplx *Z, const double *B,
@@ -200,7 +212,9 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
     const size_t smem = hql_tridiag_smem(d, g);
     if (smem > MUSIM_MAX_SMEM_OPTIN) return -5;
     ProfScope ps(prof, st, PH_EIGH_TRIDIAG);
-    if (o.use_reflect(d) && o.tridiag_warp && o.tridiag_fused && d <= 32) {
+    if (o.use_reflect(d) && o.tridiag_warp && o.tridiag_hsw && d > 8 && d <= 32) {
+      launch_tridiag_hsw(d, n, H0, Z, B, Ain, ws.dbuf[buf], ws.ebuf[buf], ws.Vp[buf], ws.vcap, ws.tauv[buf], d, 0, st);
+    } else if (o.use_reflect(d) && o.tridiag_warp && o.tridiag_fused && d <= 32) {
       const size_t sm = hql_tridiag_warpf_smem(d);
       cudaFuncSetAttribute(hql_tridiag_warpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       hql_tridiag_warpf_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(
@@ -242,7 +256,9 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
               hql_tridiag_hs_kernel<9, 3><<<g, 32 * HsGeom<9, 3>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
             else if (cur > 32)
               hql_tridiag_hs_kernel<6, 2><<<g, 32 * HsGeom<6, 2>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
-            else if (!first && o.tridiag_warp && o.tridiag_fused) {  // last phase: warp per matrix, no block barriers
+            else if (!first && o.tridiag_warp && o.tridiag_hsw && cur > 8) {  // last phase: warp per matrix, registers only
+              launch_tridiag_hsw(cur, n, nullptr, nullptr, nullptr, in, dd_, ee_, vp_, ws.vcap, tt_, d, koff, st);
+            } else if (!first && o.tridiag_warp && o.tridiag_fused) {  // last phase: warp per matrix, no block barriers
               const size_t sm = hql_tridiag_warpf_smem(cur);
               cudaFuncSetAttribute(hql_tridiag_warpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
               hql_tridiag_warpf_kernel<<<(unsigned)((n + TRW_WARPS - 1) / TRW_WARPS), 32 * TRW_WARPS, sm, st>>>(

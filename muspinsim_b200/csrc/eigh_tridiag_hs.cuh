@@ -64,7 +64,13 @@ __device__ __forceinline__ void hs_reduce_rows(const cplx (&yr)[T], int lane, cp
   const int g = lane >> 2, q = lane & 3;
   const cplx rcv = hs_shfl(hs_sel(b0, yr[0], yr[1]), 1);
   const cplx t = cadd(hs_sel(b0, yr[1], yr[0]), rcv);  // tile b0
-  if (T == 3) {
+  if (T == 4) {
+    const cplx rcv3 = hs_shfl(hs_sel(b0, yr[T - 2], yr[T - 1]), 1);
+    const cplx t3 = cadd(hs_sel(b0, yr[T - 1], yr[T - 2]), rcv3);  // tile 2 + b0
+    const cplx rcv2 = hs_shfl(hs_sel(b1, t, t3), 2);
+    const cplx f = cadd(hs_sel(b1, t3, t), rcv2);  // tile q
+    dst[8 * q + g] = f;
+  } else if (T == 3) {
     const cplx t2 = cadd(yr[T - 1], hs_shfl(yr[T - 1], 1));
     const cplx rcv2 = hs_shfl(hs_sel(b1, t, t2), 2);
     const cplx f = cadd(hs_sel(b1, t2, t), rcv2);
@@ -508,6 +514,159 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
           store_elem(TB * SI1 + 8 * ti + g, TB * SJ1 + 8 * tj + 2 * q + s, make_c(a1[ti][tj].re[s], a1[ti][tj].im[s]), true);
         }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp per matrix for d <= 8 T (T = 2, 3, 4: d <= 16 / 24 / 32): the whole matrix is ONE diagonal
+// superblock, i.e. T (T + 1) / 2 register tiles per warp, no block barrier at all.  Replaces the
+// shared-memory warp kernel (eigh_tridiag_warp.cuh: LSU 78 % busy, every element of A loaded twice and
+// stored once per step): the matrix never leaves the registers, the rank-2 update is 2 DMMAs per tile.
+// Also the last phase of the large-matrix reduction (dstride / koff as in the kernels above).
+// ---------------------------------------------------------------------------------------
+#define HSW_WARPS 4
+
+template <int T>
+__global__ void __launch_bounds__(32 * HSW_WARPS, (T == 4 ? 3 : 4))
+hql_tridiag_hsw_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cplx *__restrict__ Z,
+                       const double *__restrict__ Bf, const cplx *__restrict__ Ain, double *__restrict__ dout,
+                       double *__restrict__ eout, cplx *__restrict__ Vp, size_t vcap, cplx *__restrict__ tauout,
+                       int dstride, int koff) {
+  constexpr int D = 8 * T;
+  __shared__ __align__(16) cplx sx_[HSW_WARPS][D];
+  __shared__ __align__(16) cplx yp_[HSW_WARPS][2][D];  // row- / column-direction partial products
+  __shared__ __align__(16) double sAr_[HSW_WARPS][4 * D], sAi_[HSW_WARPS][4 * D], sB_[HSW_WARPS][4 * D];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int64_t cfg = (int64_t)blockIdx.x * HSW_WARPS + w;
+  if (cfg >= n) return;  // whole warp
+  cplx *sx = sx_[w];
+  cplx(*yp)[D] = yp_[w];
+  double *sAr = sAr_[w], *sAi = sAi_[w], *sB = sB_[w];
+  const size_t dd = (size_t)d * d;
+
+  HsTile a[T][T];  // only tj <= ti is used
+  {
+    double bx = 0, by = 0, bz = 0;
+    if (!Ain) {
+      bx = Bf[cfg * 3 + 0];
+      by = Bf[cfg * 3 + 1];
+      bz = Bf[cfg * 3 + 2];
+    }
+#pragma unroll
+    for (int ti = 0; ti < T; ++ti)
+#pragma unroll
+      for (int tj = 0; tj <= ti; ++tj)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int r = 8 * ti + g, c = 8 * tj + 2 * q + s;
+          cplx v = make_c(0.0, 0.0);
+          if (r < d && c < d) {
+            const size_t idx = (size_t)r * d + c;
+            if (Ain) {
+              v = Ain[cfg * dd + idx];
+            } else {
+              v = H0[idx];
+              const cplx z0 = Z[idx], z1 = Z[dd + idx], z2 = Z[2 * dd + idx];
+              v.x += bx * z0.x + by * z1.x + bz * z2.x;
+              v.y += bx * z0.y + by * z1.y + bz * z2.y;
+            }
+            if (r == c) v.y = 0.0;
+          }
+          a[ti][tj].re[s] = v.x;
+          a[ti][tj].im[s] = v.y;
+        }
+  }
+  if (lane < D) {
+    sx[lane] = make_c(0.0, 0.0);
+    yp[1][lane] = make_c(0.0, 0.0);  // the last tile has no column-direction part
+  }
+  __syncwarp();
+
+  for (int k = 0; k < d; ++k) {
+    // column k of the (updated) matrix: rows > k to sx, the norm of rows > k + 1, the diagonal element
+    double xn = 0.0;
+    {
+      const int tjk = k >> 3, qk = (k & 7) >> 1;
+      if (q == qk) {
+        cplx v[T];
+#pragma unroll
+        for (int ti = 0; ti < T; ++ti) v[ti] = make_c(0.0, 0.0);
+#pragma unroll
+        for (int tj = 0; tj < T; ++tj)
+          if (tj == tjk) {
+            if (k & 1) {
+#pragma unroll
+              for (int ti = tj; ti < T; ++ti) v[ti] = make_c(a[ti][tj].re[1], a[ti][tj].im[1]);
+            } else {
+#pragma unroll
+              for (int ti = tj; ti < T; ++ti) v[ti] = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
+            }
+          }
+#pragma unroll
+        for (int ti = 0; ti < T; ++ti) {
+          const int r = 8 * ti + g;
+          if (r > k) sx[r] = v[ti];
+          if (r > k + 1) xn = fma(v[ti].y, v[ti].y, fma(v[ti].x, v[ti].x, xn));  // rows >= d hold zeros
+          if (r == k) {
+            dout[cfg * dstride + koff + k] = v[ti].x;
+            sx[k] = make_c(0.0, 0.0);
+          }
+        }
+      }
+    }
+    if (k == d - 1) break;
+    xn = warp_sum(xn);
+    __syncwarp();
+    const cplx alpha = sx[k + 1];
+    const int mk = d - k - 2;
+    cplx *vrow = Vp + (cfg * vcap + (size_t)mk * (mk - 1) / 2);
+    if (xn == 0.0 && alpha.y == 0.0) {  // identity reflector (uniform)
+      if (lane == 0) {
+        eout[cfg * dstride + koff + k] = alpha.x;
+        tauout[cfg * dstride + koff + k] = make_c(0.0, 0.0);
+      }
+      for (int i = lane; i < mk; i += 32) vrow[i] = make_c(0.0, 0.0);
+      __syncwarp();
+      continue;
+    }
+    const double s2 = alpha.x * alpha.x + alpha.y * alpha.y + xn;
+    const double ri = rsqrt(s2);
+    const double sg = (alpha.x >= 0.0) ? -1.0 : 1.0;  // sign of beta
+    const double beta = sg * (s2 * ri);
+    const double xp0x = alpha.x - beta;  // x'_{k+1} = alpha - beta = 1/scale (imaginary part: alpha.y)
+    double qacc = 0.0;
+    hs_matvec_diag<T>(a, 0, k, sx, xp0x, lane, yp[0], yp[1], qacc);
+    const double Q = warp_sum(qacc);  // x'^H A x'
+    __syncwarp();
+    {
+      const double ib = sg * ri;
+      const cplx tau = make_c((beta - alpha.x) * ib, -alpha.y * ib);
+      const double den = __drcp_rn(xp0x * xp0x + alpha.y * alpha.y);
+      const cplx scale = make_c(xp0x * den, -alpha.y * den);
+      const cplx ts = cmul(tau, scale);
+      const double a2 = -0.5 * (tau.x * tau.x + tau.y * tau.y) * den * Q;  // -1/2 tau p^H v (see the CTA kernel)
+      if (lane < D) {
+        const int r = lane;
+        const cplx y = cadd(yp[0][r], yp[1][r]);
+        cplx v = cmul(scale, sx[r]);  // x[r] = 0 for r <= k
+        if (r == k + 1) v = make_c(1.0, 0.0);
+        const cplx pv = cmul(ts, y);
+        const cplx ww = make_c(fma(a2, v.x, pv.x), fma(a2, v.y, pv.y));
+        reinterpret_cast<double4 *>(sAr)[r] = make_double4(-v.x, -v.y, -ww.x, -ww.y);
+        reinterpret_cast<double4 *>(sAi)[r] = make_double4(-v.y, v.x, -ww.y, ww.x);
+        reinterpret_cast<double4 *>(sB)[r] = make_double4(ww.x, ww.y, v.x, v.y);
+        const int iv = r - k - 2;
+        if (iv >= 0 && r < d) vrow[iv] = v;
+      }
+      if (lane == 0) {
+        eout[cfg * dstride + koff + k] = beta;
+        tauout[cfg * dstride + koff + k] = tau;
+      }
+    }
+    __syncwarp();
+    hs_update<T, true>(a, 0, 0, k, sAr, sAi, sB, lane);
+  }
+  if (lane == 0) eout[cfg * dstride + koff + d - 1] = 0.0;
 }
 
 }  // namespace musim
