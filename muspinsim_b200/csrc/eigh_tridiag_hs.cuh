@@ -168,7 +168,9 @@ __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[T][T], int SI, i
 // The same over the lower tiles (tj <= ti) of the DIAGONAL superblock SI: the diagonal tiles are full
 // Hermitian 8 x 8 blocks (row direction only), the tiles below them work in both directions.
 // qacc += x_I^H A_II x_I (row- and column-direction partial products together cover the whole block).
-template <int T>
+// LIVE: skip dead tile columns with uniform branches (pays when one warp owns the whole matrix); the CTA
+// kernel runs straight-line code instead (dead columns have x = 0), which the compiler schedules better.
+template <int T, bool LIVE>
 __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, int k, const cplx *x, double xp0x,
                                                int lane, cplx *yrow_dst, cplx *ycol_dst, double &qacc) {
   constexpr int TB = 8 * T;
@@ -187,7 +189,7 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, 
     for (int ti = 0; ti < T; ++ti) yr[ti] = make_c(0.0, 0.0);
 #pragma unroll
     for (int tj = 0; tj < T; ++tj) {
-      if (TB * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
+      if (!LIVE || TB * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
         cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
         if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
         if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
@@ -207,7 +209,7 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, 
 #pragma unroll
     for (int tj = 0; tj < T - 1; ++tj) {
       cplx yc0 = make_c(0.0, 0.0), yc1 = make_c(0.0, 0.0);
-      if (TB * SI + 8 * tj + 7 > k) {
+      if (!LIVE || TB * SI + 8 * tj + 7 > k) {
 #pragma unroll
         for (int ti = tj + 1; ti < T; ++ti) {
           ccfma(yc0, make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xr[ti]);
@@ -228,7 +230,7 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, 
 // A -= v w^H + w v^H on one superblock: two DMMAs per live tile.  DIAG: lower tiles only.
 // Operands in shared memory, already in fragment order (written by the combine step):
 //   sAr[r] = -(v.x, v.y, w.x, w.y), sAi[r] = (-v.y, v.x, -w.y, w.x), sB[c] = (w.x, w.y, v.x, v.y).
-template <int T, bool DIAG>
+template <int T, bool DIAG, bool LIVE = false>
 __device__ __forceinline__ void hs_update(HsTile (&a)[T][T], int SI, int SJ, int k, const double *sAr, const double *sAi,
                                           const double *sB, int lane) {
   constexpr int TB = 8 * T;
@@ -242,7 +244,7 @@ __device__ __forceinline__ void hs_update(HsTile (&a)[T][T], int SI, int SJ, int
   for (int tj = 0; tj < T; ++tj) bb[tj] = sB[4 * (TB * SJ + 8 * tj) + lane];  // [column 8 J + g][q]
 #pragma unroll
   for (int tj = 0; tj < T; ++tj) {
-    if (!DIAG || TB * SJ + 8 * tj + 7 > k) {  // off-diagonal superblocks: dead columns are updated too (never read again)
+    if (!LIVE || TB * SJ + 8 * tj + 7 > k) {  // (dead columns are never read again: updating them is harmless)
 #pragma unroll
       for (int ti = (DIAG ? tj : 0); ti < T; ++ti) {
         dmma884(a[ti][tj].re[0], a[ti][tj].re[1], are[ti], bb[tj]);
@@ -438,7 +440,7 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
     // ---- partial products y = A22 x' and the Hermitian form x'^H A22 x' ----
     {
       double qacc = 0.0;
-      if (HAS0) hs_matvec_diag<T>(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
+      if (HAS0) hs_matvec_diag<T, false>(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
       hs_matvec_off<T>(a1, SI1, SJ1, k, x, xp0x, lane, ypart[SJ1], ypart[SI1], qacc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) qacc += __shfl_xor_sync(0xffffffffu, qacc, o);
@@ -635,7 +637,7 @@ hql_tridiag_hsw_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cplx
     const double beta = sg * (s2 * ri);
     const double xp0x = alpha.x - beta;  // x'_{k+1} = alpha - beta = 1/scale (imaginary part: alpha.y)
     double qacc = 0.0;
-    hs_matvec_diag<T>(a, 0, k, sx, xp0x, lane, yp[0], yp[1], qacc);
+    hs_matvec_diag<T, true>(a, 0, k, sx, xp0x, lane, yp[0], yp[1], qacc);
     const double Q = warp_sum(qacc);  // x'^H A x'
     __syncwarp();
     {
@@ -664,7 +666,7 @@ hql_tridiag_hsw_kernel(int d, int64_t n, const cplx *__restrict__ H0, const cplx
       }
     }
     __syncwarp();
-    hs_update<T, true>(a, 0, 0, k, sAr, sAi, sB, lane);
+    hs_update<T, true, true>(a, 0, 0, k, sAr, sAi, sB, lane);
   }
   if (lane == 0) eout[cfg * dstride + koff + d - 1] = 0.0;
 }
