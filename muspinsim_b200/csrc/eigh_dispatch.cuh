@@ -250,12 +250,13 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
             cplx *out = nxt ? bufs[ib] : nullptr;
             const cplx *h0 = first ? H0 : nullptr, *zz = first ? Z : nullptr;
             const double *bb = first ? B : nullptr;
+            // (the next half-storage phase reads the lower triangle only -- if its 8 x 8 tiles line up with this one's)
             if (cur > 72)
-              hql_tridiag_hs_kernel<12, 3><<<g, 32 * HsGeom<12, 3>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+              hql_tridiag_hs_kernel<12, 3><<<g, 32 * HsGeom<12, 3>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out, (steps & 7) ? 1 : 0);
             else if (cur > 48)
-              hql_tridiag_hs_kernel<9, 3><<<g, 32 * HsGeom<9, 3>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+              hql_tridiag_hs_kernel<9, 3><<<g, 32 * HsGeom<9, 3>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out, (steps & 7) ? 1 : 0);
             else if (cur > 32)
-              hql_tridiag_hs_kernel<6, 2><<<g, 32 * HsGeom<6, 2>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out);
+              hql_tridiag_hs_kernel<6, 2><<<g, 32 * HsGeom<6, 2>::NW, 0, st>>>(cur, d, koff, steps, h0, zz, bb, in, dd_, ee_, vp_, ws.vcap, tt_, out, 1);
             else if (!first && o.tridiag_warp && o.tridiag_hsw && cur > 8) {  // last phase: warp per matrix, registers only
               launch_tridiag_hsw(cur, n, nullptr, nullptr, nullptr, in, dd_, ee_, vp_, ws.vcap, tt_, d, koff, st);
             } else if (!first && o.tridiag_warp && o.tridiag_fused) {  // last phase: warp per matrix, no block barriers

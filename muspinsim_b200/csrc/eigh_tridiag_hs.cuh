@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32 * HsGeom<NT, T>::NW, HsGeom<NT, T>::CTAS)
 hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__restrict__ H0,
                       const cplx *__restrict__ Z, const double *__restrict__ Bf, const cplx *__restrict__ Ain,
                       double *__restrict__ dout, double *__restrict__ eout, cplx *__restrict__ Vp, size_t vcap,
-                      cplx *__restrict__ tauout, cplx *__restrict__ Aout) {
+                      cplx *__restrict__ tauout, cplx *__restrict__ Aout, int mirror) {
   using G = HsGeom<NT, T>;
   constexpr int S = G::S, NW = G::NW, D = G::D, TB = G::TB;
   constexpr int RPW = D / NW;  // rows per warp in the combine step (16 or 24)
@@ -496,13 +496,13 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
 #endif
   if (kend == d - 1) {
     if (tid == 0) eout[cfg * dstride + koff + d - 1] = 0.0;
-  } else {  // hand the trailing block (both triangles) to the next phase
+  } else {  // hand the trailing block to the next phase (mirror: both triangles; the next half-storage phase reads the lower one only)
     const int ds = d - kend;
     cplx *Ao = Aout + cfg * (size_t)ds * ds;
-    auto store_elem = [&](int r, int c, cplx v, bool mirror) {
+    auto store_elem = [&](int r, int c, cplx v, bool mir) {
       if (r >= kend && c >= kend && r < d && c < d) {
         Ao[(size_t)(r - kend) * ds + (c - kend)] = v;
-        if (mirror) Ao[(size_t)(c - kend) * ds + (r - kend)] = cconj(v);
+        if (mir) Ao[(size_t)(c - kend) * ds + (r - kend)] = cconj(v);
       }
     };
 #pragma unroll
@@ -512,8 +512,8 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (tj <= ti && has0)
-            store_elem(TB * SI0 + 8 * ti + g, TB * SI0 + 8 * tj + 2 * q + s, make_c(a0[ti][tj].re[s], a0[ti][tj].im[s]), tj < ti);
-          store_elem(TB * SI1 + 8 * ti + g, TB * SJ1 + 8 * tj + 2 * q + s, make_c(a1[ti][tj].re[s], a1[ti][tj].im[s]), true);
+            store_elem(TB * SI0 + 8 * ti + g, TB * SI0 + 8 * tj + 2 * q + s, make_c(a0[ti][tj].re[s], a0[ti][tj].im[s]), tj < ti && mirror);
+          store_elem(TB * SI1 + 8 * ti + g, TB * SJ1 + 8 * tj + 2 * q + s, make_c(a1[ti][tj].re[s], a1[ti][tj].im[s]), mirror != 0);
         }
   }
 }
