@@ -65,7 +65,7 @@ struct BackWyGeom {
 // 15 warps per issue (profiles/r2_ncu_k4.md).
 // ---------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(4 * D, 2)
+__global__ void __launch_bounds__(4 * D, (D <= 32 ? 5 : 2))
 hql_tfactor_kernel(int d, const cplx *__restrict__ Vp, size_t vcap, const cplx *__restrict__ tau,
                    double *__restrict__ Timg) {
   using G = BackWyGeom<D>;
@@ -153,13 +153,13 @@ hql_tfactor_kernel(int d, const cplx *__restrict__ Vp, size_t vcap, const cplx *
 // ---------------------------------------------------------------------------------------
 // The back-transformation proper.  HALVES CTAs per matrix, NB / HALVES warps each.
 // ---------------------------------------------------------------------------------------
-template <int D, int HALVES>
-__global__ void __launch_bounds__(4 * D / HALVES, HALVES)
+template <int D, int HALVES, int MINB = HALVES>
+__global__ void __launch_bounds__(4 * D / HALVES, MINB)
 hql_backwy_kernel(int d, const double *__restrict__ Zt, const cplx *__restrict__ Vp, size_t vcap,
                   const double *__restrict__ Timg, cplx *__restrict__ U) {
   using G = BackWyGeom<D>;
   constexpr int NB = G::NB, TLD = G::TLD, NT = 4 * D / HALVES, NW = NB / HALVES;
-  static_assert(D % 32 == 0 && D <= 96 && NB % HALVES == 0, "D = 32, 64 or 96");
+  static_assert(D % 8 == 0 && D <= 96 && NB % HALVES == 0, "D = 24, 32, 64 or 96");
   extern __shared__ __align__(16) unsigned char bw_smem[];
   double *Vre = reinterpret_cast<double *>(bw_smem);  // blocks b = 0 .. NB-1, [8][ld(b)] each
   double *Vim = Vre + G::VPLANE;

@@ -21,6 +21,7 @@ enum { EIGH_AUTO = 0, EIGH_JACOBI = 1, EIGH_HQL = 2 };
 struct EighOpts {
   bool reflect = true;         // "reflect": K4 applies the reflectors to Zt (d <= 96); 0: Q formed in K1 + GEMM
   bool tdc = true;             // "tdc": tridiagonal divide and conquer (32 < d <= 96) instead of QL + rotation replay
+  bool back_wy_small = true;   // "back_wy_small": the compact-WY kernels also for 16 < d <= 32 (D = 24 / 32 instantiations, one CTA per matrix)
   bool back_wy = true;         // "back_wy": K4 in compact-WY blocks on the FP64 tensor pipe (32 < d <= 96); 0: level-2 reflector kernel
   bool tridiag_warp = true;    // "tridiag_warp": warp-per-matrix tridiagonalisation for d <= 32
   bool small24 = true;         // "small24": D = 16 / 24 instantiations of the replay / reflector kernels for d <= 16 / 24 (else D = 32)
@@ -145,7 +146,7 @@ struct EighWs {
         EW_ALLOC(tauv[i], (size_t)n * d);
       }
       EW_ALLOC(Zt, (size_t)n * dd);
-      if (d > 32 && d <= 96) EW_ALLOC(Timg, (size_t)n * BackWyGeom<96>::TIMG);
+      if (d > 16 && d <= 96) EW_ALLOC(Timg, (size_t)n * (d <= 32 ? BackWyGeom<32>::TIMG : BackWyGeom<96>::TIMG));
       if (d > 32 && d <= 96) {
         EW_ALLOC(l_hdr, (size_t)n * 4);
         EW_ALLOC(l_d, (size_t)n * 4 * 24);
@@ -239,7 +240,8 @@ inline int launch_eigh_stageA(int method, int d, int64_t n, const cplx *H0, cons
           else
             hql_tridiag_rw_kernel<96><<<g, 384, 0, st>>>(d, d, 0, d, H0, Z, B, Ain, dd_, ee_, vp_, ws.vcap, tt_, nullptr);
         } else if (o.tridiag_hs && d > 48) {
-          // live block d -> 72 -> 48 (half-storage DMMA kernel, 2 / 4 matrices per SM) -> 32 (rows-per-warp kernel) -> done (warp per matrix)
+          // live block d -> 72 -> 48 -> 32 (half-storage DMMA kernels, 2 / 4 / 5 matrices per SM) -> done (warp per matrix);
+          // a 64 phase on 2 x 2-tile superblocks in between was slower (11.4 vs 11.0 ms at C5)
           cplx *bufs[2] = {ws.Q[buf], ws.Q[buf] + (size_t)n * 72 * 72};
           int cur = d, koff = 0, ib = 0, nl = 0;
           const cplx *in = Ain;
@@ -424,8 +426,18 @@ inline int launch_eigh_stageB(int method, int d, int64_t n, double *lam, cplx *U
   if (!use_tdc) ++*launches;
   {
     ProfScope ps(prof, st, PH_EIGH_BACK);
-    if (o.use_reflect(d) && o.back_wy && d > 32) {
-      if (d <= 64) {
+    if (o.use_reflect(d) && o.back_wy && (d > 32 || (o.back_wy_small && d > 16))) {
+      if (d <= 24) {
+        const size_t sm = BackWyGeom<24>::smem_bytes;
+        cudaFuncSetAttribute(hql_backwy_kernel<24, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_tfactor_kernel<24><<<(unsigned)n, 96, BackWyGeom<24>::tf_smem_bytes, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
+        hql_backwy_kernel<24, 1, 8><<<(unsigned)n, 96, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.Timg, U);
+      } else if (d <= 32) {
+        const size_t sm = BackWyGeom<32>::smem_bytes;
+        cudaFuncSetAttribute(hql_backwy_kernel<32, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        hql_tfactor_kernel<32><<<(unsigned)n, 128, BackWyGeom<32>::tf_smem_bytes, st>>>(d, ws.Vp[buf], ws.vcap, ws.tauv[buf], ws.Timg);
+        hql_backwy_kernel<32, 1, 6><<<(unsigned)n, 128, sm, st>>>(d, ws.Zt, ws.Vp[buf], ws.vcap, ws.Timg, U);
+      } else if (d <= 64) {
         const size_t sm = BackWyGeom<64>::smem_bytes;
         cudaFuncSetAttribute(hql_backwy_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         cudaFuncSetAttribute(hql_tfactor_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BackWyGeom<64>::tf_smem_bytes);

@@ -45,7 +45,7 @@ struct HsGeom {
   static constexpr int NW = S * (S - 1) / 2;    // warps = off-diagonal superblocks (6 or 3)
   static constexpr int D = 8 * NT;
   static constexpr int TB = 8 * T;              // rows of a superblock
-  static constexpr int CTAS = (T == 3) ? 12 / NW : 5;  // T = 3: 12 warps per SM at 168 registers
+  static constexpr int CTAS = (T == 3) ? 12 / NW : (NW == 3 ? 5 : 3);  // T = 3: 12 warps per SM at 168 registers
 };
 
 __device__ __forceinline__ cplx hs_shfl(cplx v, int m) {
@@ -262,8 +262,8 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
                       cplx *__restrict__ tauout, cplx *__restrict__ Aout, int mirror) {
   using G = HsGeom<NT, T>;
   constexpr int S = G::S, NW = G::NW, D = G::D, TB = G::TB;
-  constexpr int RPW = D / NW;  // rows per warp in the combine step (16 or 24)
-  static_assert(RPW <= 32 && RPW * NW == D, "combine step: one row per lane");
+  constexpr int RPW = (D + NW - 1) / NW;  // rows per warp in the combine step (16, 24 or 11)
+  static_assert(RPW <= 32, "combine step: one row per lane");
   __shared__ __align__(16) cplx sx[2][D];        // column k of the trailing matrix, by parity of k
   __shared__ __align__(16) double sxn[2][8];     // per-warp partial ||x[2:]||^2, by parity of k
   __shared__ __align__(16) double sq[8];         // per-warp partial x'^H A x'
@@ -450,7 +450,7 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
     __syncthreads();  // #2: the partial products are visible
     HS_T(3)
 
-    if (lane < RPW) {  // combine, RPW rows per warp: p = tau A v, v, a2 = -1/2 tau p^H v, w = p + a2 v -> DMMA operands
+    if (lane < RPW && RPW * w + lane < D) {  // combine, RPW rows per warp: p = tau A v, v, a2 = -1/2 tau p^H v, w = p + a2 v -> DMMA operands
       const int r = RPW * w + lane;
       double Q = 0.0;
 #pragma unroll

@@ -187,6 +187,8 @@ extern "C" int musim_set_option(musim_handle *h, const char *key, long value) {
     h->eo.small24 = value != 0;
   else if (!strcmp(key, "tridiag_rw"))  // 0: shared-memory tridiagonalisation kernel
     h->eo.tridiag_rw = value != 0;
+  else if (!strcmp(key, "back_wy_small"))  // 0: level-2 reflector kernel for d <= 32
+    h->eo.back_wy_small = value != 0;
   else if (!strcmp(key, "tridiag_hsw"))  // 1: register-resident half-storage warp kernel for 8 < d <= 32
     h->eo.tridiag_hsw = value != 0;
   else if (!strcmp(key, "tridiag_hs"))  // 0: rows-per-warp full-storage kernel for every phase

@@ -259,6 +259,9 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
     if (tile_live) {
 #pragma unroll
     for (int ks = 0; ks < ZG_KS; ks += 4) {
+      // T = 1 (d <= 32, e.g. the 24 x 24 systems of the ALC scans): skip the k steps and the 8-row / 8-column
+      // tiles that lie entirely in the zero padding (uniform branches): 144 instead of 256 DMMAs per warp at d = 24
+      if (T == 1 && k0 + ks >= d) continue;
       double ar[4], ai[4], br[2], bi[2], nb[2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -282,6 +285,7 @@ zgemm_dmma_kernel(int d, const cplx *__restrict__ A, size_t a_stride, const cplx
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
+          if (T == 1 && (wm * 32 + i * 8 >= d || wn * 16 + j * 8 >= d)) continue;
           dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);  // + Ar Br
           dmma884(cr[i][j][0], cr[i][j][1], ai[i], nb[j]);  // - Ai Bi
           dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);  // + Ar Bi

@@ -28,7 +28,7 @@ def test_golden(name):
 
 
 @pytest.mark.parametrize("opts", [{"polar": 1}, {"polar": 3}, {"eigh": 1}, {"eigh": 2, "polar": 2}, {"chunk": 3},
-                                  {"polar_mma": 0}, {"rho0_dense": 1}, {"int_fused": 0}, {"zgemm_pipe": 0}, {"sorted": 1}, {"back_wy": 0}, {"tdc": 0}, {"tdc": 0, "back_wy": 0}, {"reflect": 0}, {"tridiag_rw": 0}, {"gemm": 1}, {"tridiag_warp": 0}, {"small24": 0}, {"tridiag_fused": 0}, {"tridiag_phases": 0}, {"tridiag_hs": 0}, {"tridiag_hsw": 1}, {"apply_warp": 0}, {"tql_threads": 32}, {"tql_threads": 16}, {"tql_threads": 8}])
+                                  {"polar_mma": 0}, {"rho0_dense": 1}, {"int_fused": 0}, {"zgemm_pipe": 0}, {"sorted": 1}, {"back_wy": 0}, {"tdc": 0}, {"tdc": 0, "back_wy": 0}, {"reflect": 0}, {"tridiag_rw": 0}, {"gemm": 1}, {"tridiag_warp": 0}, {"small24": 0}, {"tridiag_fused": 0}, {"tridiag_phases": 0}, {"tridiag_hs": 0}, {"tridiag_hsw": 1}, {"back_wy_small": 0}, {"apply_warp": 0}, {"tql_threads": 32}, {"tql_threads": 16}, {"tql_threads": 8}])
 @pytest.mark.parametrize("name", ["c2_fast_d16", "c2_general_d8_T0p3", "c3_alc_d12", "c5_fast_d96",
                                   "polarization_filerange", "ground_state_T0"])
 def test_golden_all_kernel_variants(name, opts):
