@@ -461,7 +461,8 @@ def main():
             r2.handle.close()
         api = {"value": n_total / min(walls), "unit": UNIT, "wall_s": min(walls), "first_call_wall_s": walls[0],
                "what": "ExperimentRunner(spec).run(): spec -> system matrices, configuration table, new device handle, "
-                       "workspace allocation, evaluation, result on the host (best of 2)"}
+                       "workspaces (the second call re-uses the blocks the first call's destroyed handle left in the library's "
+                       "cache; first_call_wall_s pays cudaMalloc), evaluation, result on the host (best of 2)"}
 
     # ---- roofline of the dominant kernel ----
     peak_dfma = _lib.fp64_peak(local, 0)

@@ -160,6 +160,12 @@ int musim_fp64_peak(int device, int kind, double *tflops);
 
 const char *musim_last_error(musim_handle *h);
 int musim_destroy(musim_handle *h);
+/* Workspaces that a destroyed handle returns are kept in a per-device cache of the library (by exact
+ * size), so that the next handle of the process (the reference builds a new ExperimentRunner per
+ * input file / fit evaluation, muspinsim/__main__.py, fitting.py:126-151) does not pay cudaMalloc /
+ * cudaFree of tens of GB again.  This call frees the cached blocks (the cache also empties itself when an
+ * allocation fails or when it would hold more than half of the device memory). */
+int musim_trim_pool(int device);
 /* Celio's method (Phys. Rev. Lett. 56, 2720): Trotter-split evolution of `n_states` state vectors and
  * the muon polarisation <psi| sigma_mu (x) 1 |psi> at every time step, summed over the states into
  * results[num_times] (+=).  Replaces the reference's C++ extension call

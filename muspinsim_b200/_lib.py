@@ -33,6 +33,7 @@ EXPORTS = [
     "musim_launch_count",
     "musim_phase_ms",
     "musim_fp64_peak",
+    "musim_trim_pool",
     "musim_celio_evolve",
     "musim_celio_launch_count",
     "musim_device_count",
@@ -89,6 +90,8 @@ def load():
     lib.musim_phase_ms.restype = dbl
     lib.musim_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(dbl)]
     lib.musim_fp64_peak.restype = i32
+    lib.musim_trim_pool.argtypes = [i32]
+    lib.musim_trim_pool.restype = i32
     lib.musim_celio_evolve.argtypes = [i32, i64, i32, vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp, i32]
     lib.musim_celio_evolve.restype = i32
     lib.musim_celio_launch_count.argtypes = []
@@ -295,6 +298,13 @@ def celio_evolve(device, psi, sigma_mu, k, contribs, num_times, results, streame
 def device_count():
     """Number of CUDA devices visible to the process (0 without a driver / GPU)."""
     return int(load().musim_device_count())
+
+
+def trim_pool(device=0):
+    """Return the library's cached device memory (workspaces of destroyed handles) to the driver."""
+    rc = load().musim_trim_pool(int(device))
+    if rc != 0:
+        raise MusimError("musim_trim_pool failed: %s (%d)" % (_ERRORS.get(rc, "?"), rc))
 
 
 def fp64_peak(device=0, kind=0):

@@ -192,11 +192,11 @@ inline int celio_evolve_host(int device, long long dim, int n_states, const doub
   }
 #define CE(call) \
   if (e == cudaSuccess) e = (call)
-  CE(cudaMalloc((void **)&dpsi, (size_t)n_states * dim * sizeof(cplx)));
-  CE(cudaMalloc((void **)&dM, std::max<size_t>(1, msum) * sizeof(cplx)));
-  CE(cudaMalloc((void **)&didx, std::max<size_t>(1, idx32.size()) * sizeof(int)));
-  CE(cudaMalloc((void **)&dg, std::max(1, n_gates) * sizeof(CelioGate)));
-  CE(cudaMalloc((void **)&dres, (size_t)nt * sizeof(double)));
+  CE(dev_malloc((void **)&dpsi, (size_t)n_states * dim * sizeof(cplx)));
+  CE(dev_malloc((void **)&dM, std::max<size_t>(1, msum) * sizeof(cplx)));
+  CE(dev_malloc((void **)&didx, std::max<size_t>(1, idx32.size()) * sizeof(int)));
+  CE(dev_malloc((void **)&dg, std::max(1, n_gates) * sizeof(CelioGate)));
+  CE(dev_malloc((void **)&dres, (size_t)nt * sizeof(double)));
   CE(cudaMemcpy(dpsi, psi, (size_t)n_states * dim * sizeof(cplx), cudaMemcpyHostToDevice));
   if (msum) CE(cudaMemcpy(dM, matrices, msum * sizeof(cplx), cudaMemcpyHostToDevice));
   if (!idx32.empty()) CE(cudaMemcpy(didx, idx32.data(), idx32.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -246,11 +246,11 @@ inline int celio_evolve_host(int device, long long dim, int n_states, const doub
   std::vector<double> hres(nt);
   CE(cudaMemcpy(hres.data(), dres, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost));
 #undef CE
-  cudaFree(dpsi);
-  cudaFree(dM);
-  cudaFree(didx);
-  cudaFree(dg);
-  cudaFree(dres);
+  dev_free(dpsi);
+  dev_free(dM);
+  dev_free(didx);
+  dev_free(dg);
+  dev_free(dres);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   if (e != cudaSuccess) return -2;
   for (int t = 0; t < nt; ++t) results[t] += hres[t];

@@ -81,40 +81,40 @@ struct EighWs {
   }
 
   void release() {
-    cudaFree(Vg);
+    dev_free(Vg);
     for (int i = 0; i < 2; ++i) {
-      cudaFree(dbuf[i]);
-      cudaFree(ebuf[i]);
-      cudaFree(Q[i]);
-      cudaFree(Vp[i]);
-      cudaFree(tauv[i]);
+      dev_free(dbuf[i]);
+      dev_free(ebuf[i]);
+      dev_free(Q[i]);
+      dev_free(Vp[i]);
+      dev_free(tauv[i]);
       dbuf[i] = ebuf[i] = nullptr;
       Q[i] = nullptr;
       Vp[i] = tauv[i] = nullptr;
     }
-    cudaFree(Zt);
-    cudaFree(Timg);
+    dev_free(Zt);
+    dev_free(Timg);
     Timg = nullptr;
-    cudaFree(l_hdr);
-    cudaFree(l_d);
-    cudaFree(l_e);
-    cudaFree(l_lam);
-    cudaFree(l_Z);
-    cudaFree(l_rot);
-    cudaFree(l_swp);
-    cudaFree(l_nswp);
-    cudaFree(l_perm);
+    dev_free(l_hdr);
+    dev_free(l_d);
+    dev_free(l_e);
+    dev_free(l_lam);
+    dev_free(l_Z);
+    dev_free(l_rot);
+    dev_free(l_swp);
+    dev_free(l_nswp);
+    dev_free(l_perm);
     l_hdr = l_d = l_e = l_lam = l_Z = nullptr;
     l_rot = nullptr;
     l_swp = nullptr;
     l_nswp = nullptr;
     l_perm = nullptr;
-    cudaFree(Awork);
+    dev_free(Awork);
     Awork = nullptr;
-    cudaFree(rot);
-    cudaFree(swp);
-    cudaFree(nswp);
-    cudaFree(perm);
+    dev_free(rot);
+    dev_free(swp);
+    dev_free(nswp);
+    dev_free(perm);
     Vg = nullptr;
     Zt = nullptr;
     rot = nullptr;
@@ -133,7 +133,7 @@ struct EighWs {
     const size_t dd = (size_t)d * d;
     cudaError_t e = cudaSuccess;
 #define EW_ALLOC(ptr, count)                                              \
-  if (e == cudaSuccess) e = cudaMalloc((void **)&ptr, (count) * sizeof(*ptr));
+  if (e == cudaSuccess) e = dev_malloc((void **)&ptr, (count) * sizeof(*ptr));
     if (method == EIGH_HQL) {
       rot_cap = 2 * dd + 64 + 14 * (size_t)(6 * d + 16);  // ~1.2 d^2 rotations observed + <= 14 padding entries per sweep; overflow is reported as ENOTCONV
       swp_cap = 6 * d + 16;

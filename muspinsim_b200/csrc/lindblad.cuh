@@ -537,10 +537,10 @@ struct LindWs {
   void release() {
     cplx **ps[] = {&L, &X, &X2, &X3, &X4, &Ra, &Rb, &E1, &E0, &EBs, &r0, &ov, &gwork};
     for (auto p : ps) {
-      cudaFree(*p);
+      dev_free(*p);
       *p = nullptr;
     }
-    cudaFree(norm);
+    dev_free(norm);
     norm = nullptr;
     cap = 0;
   }
@@ -552,7 +552,7 @@ struct LindWs {
     const size_t nn = (size_t)n * n;
     cudaError_t e = cudaSuccess;
     auto al = [&](cplx **p, size_t c) {
-      if (e == cudaSuccess) e = cudaMalloc((void **)p, c * sizeof(cplx));
+      if (e == cudaSuccess) e = dev_malloc((void **)p, c * sizeof(cplx));
     };
     al(&L, cnt * nn);
     al(&r0, (size_t)cnt * n);
@@ -569,7 +569,7 @@ struct LindWs {
       al(&E0, cnt * nn);
       al(&EBs, cnt * nn);
     }
-    if (e == cudaSuccess) e = cudaMalloc((void **)&norm, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = dev_malloc((void **)&norm, sizeof(unsigned long long));
     if (e == cudaSuccess) cap = cnt;
     return e;
   }

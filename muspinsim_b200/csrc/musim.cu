@@ -114,18 +114,18 @@ struct DeviceGuard {
 
 template <typename T>
 static cudaError_t dev_alloc(T **p, size_t n) {
-  return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
+  return dev_malloc(reinterpret_cast<void **>(p), n * sizeof(T));
 }
 
 static void free_ws(musim_handle *h) {
   for (auto &L : h->lane) {
-    cudaFree(L.lam);
-    cudaFree(L.U);
-    cudaFree(L.T1);
-    cudaFree(L.Y);
-    cudaFree(L.X);
-    cudaFree(L.W);
-    cudaFree(L.Oc);
+    dev_free(L.lam);
+    dev_free(L.U);
+    dev_free(L.T1);
+    dev_free(L.Y);
+    dev_free(L.X);
+    dev_free(L.W);
+    dev_free(L.Oc);
     L.ews.release();
     L.lam = nullptr;
     L.U = L.T1 = L.Y = L.X = L.W = L.Oc = nullptr;
@@ -338,7 +338,7 @@ extern "C" int musim_set_rho0(musim_handle *h, const double *rho0) {
   ON_DEVICE(h->device);
   const size_t dd = (size_t)h->d * h->d;
   if (!rho0) {
-    cudaFree(h->rho0_explicit);
+    dev_free(h->rho0_explicit);
     h->rho0_explicit = nullptr;
     return MUSIM_OK;
   }
@@ -350,8 +350,8 @@ extern "C" int musim_set_rho0(musim_handle *h, const double *rho0) {
 extern "C" int musim_set_dissipators(musim_handle *h, int n, const double *A, const double *gamma) {
   if (!h || n < 0 || (n > 0 && (!A || !gamma))) return MUSIM_EINVAL;
   ON_DEVICE(h->device);
-  cudaFree(h->exA);
-  cudaFree(h->exg);
+  dev_free(h->exA);
+  dev_free(h->exg);
   h->exA = nullptr;
   h->exg = nullptr;
   h->n_explicit = 0;
@@ -369,19 +369,19 @@ extern "C" int musim_destroy(musim_handle *h) {
   if (!h) return MUSIM_OK;
   DeviceGuard guard_(h->device);
   free_ws(h);
-  cudaFree(h->H0);
-  cudaFree(h->Z);
-  cudaFree(h->M);
-  cudaFree(h->rho0_explicit);
-  cudaFree(h->Sops);
-  cudaFree(h->pairs);
-  cudaFree(h->times_dev);
-  cudaFree(h->status);
-  cudaFree(h->stage);
+  dev_free(h->H0);
+  dev_free(h->Z);
+  dev_free(h->M);
+  dev_free(h->rho0_explicit);
+  dev_free(h->Sops);
+  dev_free(h->pairs);
+  dev_free(h->times_dev);
+  dev_free(h->status);
+  dev_free(h->stage);
   h->lws.release();
   h->nws.release();
-  cudaFree(h->exA);
-  cudaFree(h->exg);
+  dev_free(h->exA);
+  dev_free(h->exg);
   h->prof.destroy();
   delete h;
   return MUSIM_OK;
@@ -413,7 +413,7 @@ extern "C" int musim_eigh(int device, int d, int64_t batch, const double *A, dou
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaMemcpy(hstat, status, sizeof hstat, cudaMemcpyDeviceToHost);
   ws.release();
-  cudaFree(status);
+  dev_free(status);
   if (rc == MUSIM_EUNSUP) return MUSIM_EUNSUP;
   if (rc != 0 || e != cudaSuccess) return MUSIM_ECUDA;
   if (hstat[0] != 0) return MUSIM_ENOTCONV;
@@ -506,7 +506,7 @@ extern "C" int musim_run(musim_handle *h, int mode, int64_t n_cfg, const double 
   if (!integral) {
     tg = analyse_times(nt, times);
     if (nt > h->times_cap) {
-      cudaFree(h->times_dev);
+      dev_free(h->times_dev);
       h->times_dev = nullptr;
       CK(dev_alloc(&h->times_dev, (size_t)nt));
       h->times_cap = nt;
@@ -725,10 +725,10 @@ extern "C" int musim_run_host(musim_handle *h, int mode, int64_t n_cfg, const do
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t total = 2 * al(bB) + 2 * al(bT) + al(bS) + al(bO);
   if (total > h->stage_bytes) {
-    cudaFree(h->stage);
+    dev_free(h->stage);
     h->stage = nullptr;
     h->stage_bytes = 0;
-    CK(cudaMalloc(&h->stage, total));
+    CK(dev_malloc(&h->stage, total));
     h->stage_bytes = total;
   }
   h->axes_fp = 0;  // the staging buffer no longer holds an expanded axis table
@@ -887,10 +887,10 @@ extern "C" int musim_run_axes_host(musim_handle *h, int mode, int64_t n_cfg, int
   }
   const bool resident = (fp == h->axes_fp) && total <= h->stage_bytes;
   if (total > h->stage_bytes) {
-    cudaFree(h->stage);
+    dev_free(h->stage);
     h->stage = nullptr;
     h->stage_bytes = 0;
-    CK(cudaMalloc(&h->stage, total));
+    CK(dev_malloc(&h->stage, total));
     h->stage_bytes = total;
   }
   char *base = (char *)h->stage;
@@ -954,6 +954,13 @@ extern "C" int64_t musim_celio_launch_count(void) { return g_celio_launches; }
 // ---------------------------------------------------------------------------------------
 // FP64 peak micro-benchmarks
 // ---------------------------------------------------------------------------------------
+extern "C" int musim_trim_pool(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MUSIM_EINVAL;
+  DeviceGuard guard_(device);
+  return dev_trim(device) == cudaSuccess ? MUSIM_OK : MUSIM_ECUDA;
+}
+
 extern "C" int musim_fp64_peak(int device, int kind, double *tflops) {
   musim_handle *h = nullptr;
   if (!tflops || kind < 0 || kind > 1) return MUSIM_EINVAL;
@@ -987,7 +994,7 @@ extern "C" int musim_fp64_peak(int device, int kind, double *tflops) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  cudaFree(buf);
+  dev_free(buf);
   *tflops = best;
   return MUSIM_OK;
 }

@@ -461,9 +461,9 @@ struct NufftWs {
   bool coef_ready = false;
 
   void release() {
-    cudaFree(G);
-    cudaFree(touched);
-    cudaFree(deconv);
+    dev_free(G);
+    dev_free(touched);
+    dev_free(deconv);
     G = nullptr;
     touched = nullptr;
     deconv = nullptr;
@@ -504,14 +504,14 @@ inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const Pair
     ws.coef_ready = true;
   }
   if (ws.M != M || ws.rows < n_slots) {
-    cudaFree(ws.G);
-    cudaFree(ws.touched);
+    dev_free(ws.G);
+    dev_free(ws.touched);
     ws.G = nullptr;
     ws.touched = nullptr;
     ws.rows = 0;
-    e = cudaMalloc((void **)&ws.G, (size_t)n_slots * M * sizeof(cplx));
+    e = dev_malloc((void **)&ws.G, (size_t)n_slots * M * sizeof(cplx));
     if (e != cudaSuccess) return e;
-    e = cudaMalloc((void **)&ws.touched, (size_t)n_slots * sizeof(int));
+    e = dev_malloc((void **)&ws.touched, (size_t)n_slots * sizeof(int));
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(ws.G, 0, (size_t)n_slots * M * sizeof(cplx), st);
     if (e != cudaSuccess) return e;
@@ -523,9 +523,9 @@ inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const Pair
   if (ws.dN != N || ws.dM != M) {
     std::vector<double> dec;
     nu_build_deconv(N, M, dec);
-    cudaFree(ws.deconv);
+    dev_free(ws.deconv);
     ws.deconv = nullptr;
-    e = cudaMalloc((void **)&ws.deconv, (size_t)N * sizeof(double));
+    e = dev_malloc((void **)&ws.deconv, (size_t)N * sizeof(double));
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(ws.deconv, dec.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
