@@ -49,9 +49,6 @@ struct HsGeom {
 };
 
 __device__ __forceinline__ cplx hs_shfl(cplx v, int m) {
-#ifdef HS_NOSHFL
-  return v;
-#endif
   return make_c(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
 __device__ __forceinline__ cplx hs_sel(bool c, cplx a, cplx b) { return make_c(c ? a.x : b.x, c ? a.y : b.y); }
@@ -354,13 +351,27 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
             if (!diag || tj <= ti) v[ti] = make_c(a[ti][tj].re[0], a[ti][tj].im[0]);
         }
       }
+    if (!diag) {
+      // off-diagonal superblock: every row is below the column (r >= kc + 1; '=' only for the first row of the block)
 #pragma unroll
-    for (int ti = 0; ti < T; ++ti) {
-      const int r = TB * SI + 8 * ti + g;
-      if (r > kc) sx[par][r] = v[ti];  // (diagonal superblock: tiles above the diagonal only hold rows < kc)
-      if (r > kc + 1) xn = fma(v[ti].y, v[ti].y, fma(v[ti].x, v[ti].x, xn));  // rows >= d hold zeros
-      if (r == kc) {
-        dout[cfg * dstride + koff + kc] = v[ti].x;
+      for (int ti = 0; ti < T; ++ti) {
+        const int r = TB * SI + 8 * ti + g;
+        sx[par][r] = v[ti];
+        if (ti > 0 || r > kc + 1) xn = fma(v[ti].y, v[ti].y, fma(v[ti].x, v[ti].x, xn));  // rows >= d hold zeros
+      }
+    } else {
+#pragma unroll
+      for (int ti = 0; ti < T; ++ti) {
+        const int r = TB * SI + 8 * ti + g;
+        if (r > kc) sx[par][r] = v[ti];  // (tiles above the diagonal only hold rows < kc)
+        if (r > kc + 1) xn = fma(v[ti].y, v[ti].y, fma(v[ti].x, v[ti].x, xn));
+      }
+      if (g == (kc & 7)) {  // the diagonal element sits in tile (tjk, tjk), row kc & 7
+        cplx dv = make_c(0.0, 0.0);
+#pragma unroll
+        for (int ti = 0; ti < T; ++ti)
+          if (ti == tjk) dv = v[ti];
+        dout[cfg * dstride + koff + kc] = dv.x;
         sx[par][kc] = make_c(0.0, 0.0);
         if (kc > 0) sx[par][kc - 1] = make_c(0.0, 0.0);
       }

@@ -1,3 +1,4 @@
+"""Where the wall time of ExperimentRunner(spec).run() goes at C5: constructor, handle, first run (workspaces), second run, close."""
 import sys, time, types, numpy as np, torch
 sys.path.insert(0, ".")
 from muspinsim_b200 import ExperimentRunner

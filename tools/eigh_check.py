@@ -1,3 +1,4 @@
+"""Quick check of musim_eigh against numpy for a list of sizes: python tools/eigh_check.py 24 64 96 (eigenvalue error, residual)."""
 import sys, numpy as np, torch
 sys.path.insert(0, ".")
 from muspinsim_b200 import _lib
