@@ -136,6 +136,13 @@ int musim_run_axes_host(musim_handle *h, int mode, int64_t n_cfg, int64_t first,
 int musim_eigh(int device, int d, int64_t batch, const double *A, double *evals, double *evecs,
                int method, void *cuda_stream);
 
+/* Density matrices rho(t_k) = U [R0 .* exp(-2 pi i (l_i - l_j) t_k)] U^H, R0 = U^H rho0 U: the result of
+ * Hamiltonian.evolve(rho0, times, operators=None) (hamiltonian.py:86-115, the branch without
+ * operators).  evals[d], evecs[d,d] as musim_eigh returns them, rho0[d,d] complex, rho_t[nt,d,d] complex:
+ * DEVICE pointers; times[nt] (microseconds) is a HOST pointer. */
+int musim_evolve_rho(int device, int d, const double *evals, const double *evecs, const double *rho0,
+                     int nt, const double *times, double *rho_t, void *cuda_stream);
+
 /* Host-side tables of the type-1 NUFFT polarisation kernel (polar_nufft.cuh), computed without a
  * GPU: fine-grid size *M for nt time points, spreading width *w, polynomial degree *deg,
  * coef[w*(deg+1)] (per-tap monomial coefficients in y = 2x of the "exponential of semicircle"

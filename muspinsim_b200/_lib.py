@@ -30,6 +30,7 @@ EXPORTS = [
     "musim_run_axes_host",
     "musim_nufft_tables",
     "musim_eigh",
+    "musim_evolve_rho",
     "musim_launch_count",
     "musim_phase_ms",
     "musim_fp64_peak",
@@ -84,6 +85,8 @@ def load():
     lib.musim_nufft_tables.restype = i32
     lib.musim_eigh.argtypes = [i32, i32, i64, vp, vp, vp, i32, vp]
     lib.musim_eigh.restype = i32
+    lib.musim_evolve_rho.argtypes = [i32, i32, vp, vp, vp, i32, vp, vp, vp]
+    lib.musim_evolve_rho.restype = i32
     lib.musim_launch_count.argtypes = [vp]
     lib.musim_launch_count.restype = i64
     lib.musim_phase_ms.argtypes = [vp, ctypes.c_char_p]
@@ -314,6 +317,16 @@ def fp64_peak(device=0, kind=0):
     if rc:
         raise MusimError("musim_fp64_peak failed (%d)" % rc)
     return v.value
+
+
+def evolve_rho_device(device, d, evals_ptr, evecs_ptr, rho0_ptr, times, rho_t_ptr, stream=0):
+    """rho(t) for every time (musim_evolve_rho): device pointers, `times` a host float64 array."""
+    lib = load()
+    t = np.ascontiguousarray(times, dtype=np.float64)
+    rc = lib.musim_evolve_rho(int(device), int(d), evals_ptr, evecs_ptr, rho0_ptr, int(t.size), t.ctypes.data,
+                              rho_t_ptr, stream)
+    if rc:
+        raise MusimError("musim_evolve_rho failed: %s (%d)" % (_ERRORS.get(rc, "?"), rc))
 
 
 def eigh_device(device, d, batch, A_ptr, evals_ptr, evecs_ptr, method=0, stream=0):

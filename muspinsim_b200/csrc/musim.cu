@@ -954,6 +954,64 @@ extern "C" int64_t musim_celio_launch_count(void) { return g_celio_launches; }
 // ---------------------------------------------------------------------------------------
 // FP64 peak micro-benchmarks
 // ---------------------------------------------------------------------------------------
+// rho(t) = U [R0 .* exp(-2 pi i (l_i - l_j) t)] U^H with R0 = U^H rho0 U: the density-matrix output of
+// Hamiltonian.evolve(rho0, times, operators=None) (hamiltonian.py:86-115).  All pointers are DEVICE pointers
+// except `times` (host); evals / evecs as musim_eigh returns them.
+extern "C" int musim_evolve_rho(int device, int d, const double *evals, const double *evecs, const double *rho0,
+                                int nt, const double *times, double *rho_t, void *cuda_stream) {
+  musim_handle *h = nullptr;
+  if (d < 1 || nt < 0 || !evals || !evecs || !rho0 || (nt > 0 && (!times || !rho_t))) return MUSIM_EINVAL;
+  if (nt == 0) return MUSIM_OK;
+  ON_DEVICE(device);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t dd = (size_t)d * d;
+  const cplx *U = reinterpret_cast<const cplx *>(evecs);
+  const cplx *R = reinterpret_cast<const cplx *>(rho0);
+  cplx *out = reinterpret_cast<cplx *>(rho_t);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, ((size_t)256 << 20) / (dd * sizeof(cplx))));
+  cplx *T1 = nullptr, *R0 = nullptr, *Ud = nullptr, *X = nullptr, *Y = nullptr;
+  double *tdev = nullptr;
+  cudaError_t e = dev_alloc(&T1, dd);
+  if (e == cudaSuccess) e = dev_alloc(&R0, dd);
+  if (e == cudaSuccess) e = dev_alloc(&Ud, dd);
+  if (e == cudaSuccess) e = dev_alloc(&X, dd * chunk);
+  if (e == cudaSuccess) e = dev_alloc(&Y, dd * chunk);
+  if (e == cudaSuccess) e = dev_alloc(&tdev, (size_t)nt);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tdev, times, (size_t)nt * sizeof(double), cudaMemcpyHostToDevice, st);
+  int64_t launches = 0;
+  const MuonObs nomu = {1, 0};
+  auto gemm = [&](bool conj_a, int64_t n, const cplx *A, size_t as, const cplx *B, size_t bs, cplx *C) {
+    if (conj_a) {
+      if (!launch_zgemm_dmma<true, 0, false>(d, n, A, as, B, bs, C, 1.0, nullptr, nomu, nullptr, st))
+        launch_gemm<true, 0>(d, n, A, as, B, bs, C, 1.0, st, &launches);
+    } else {
+      if (!launch_zgemm_dmma<false, 0, false>(d, n, A, as, B, bs, C, 1.0, nullptr, nomu, nullptr, st))
+        launch_gemm<false, 0>(d, n, A, as, B, bs, C, 1.0, st, &launches);
+    }
+  };
+  if (e == cudaSuccess) {
+    gemm(false, 1, R, 0, U, 0, T1);    // T1 = rho0 U
+    gemm(true, 1, U, 0, T1, 0, R0);    // R0 = U^H T1
+    conj_transpose_kernel<<<(unsigned)((dd + 255) / 256), 256, 0, st>>>(d, U, Ud);
+    for (int t0 = 0; t0 < nt; t0 += chunk) {
+      const int n = std::min(chunk, nt - t0);
+      const size_t total = dd * (size_t)n;
+      rho_phase_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 32), 256, 0, st>>>(d, n, R0, evals, tdev + t0, X);
+      gemm(false, n, U, 0, X, dd, Y);                     // Y_t = U X_t
+      gemm(false, n, Y, dd, Ud, 0, out + (size_t)t0 * dd);  // rho_t = Y_t U^H
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  dev_free(T1);
+  dev_free(R0);
+  dev_free(Ud);
+  dev_free(X);
+  dev_free(Y);
+  dev_free(tdev);
+  return e == cudaSuccess ? MUSIM_OK : MUSIM_ECUDA;
+}
+
 extern "C" int musim_trim_pool(int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MUSIM_EINVAL;

@@ -479,4 +479,30 @@ __global__ void integral_kernel(int d, const cplx *__restrict__ W, const double 
   if (threadIdx.x == 0) atomicAdd(&out[slot[cfg]], wgt[cfg] * acc * it);
 }
 
+// ---------------------------------------------------------------------------------------
+// Density-matrix output of Hamiltonian.evolve(operators=None) (hamiltonian.py:86-115):
+// X[t][i][j] = R0[i][j] exp(-2 pi i (l_i - l_j) t) in the eigenbasis, and the conjugate transpose
+// of the eigenvector matrix (the right factor of U X U^H for the batched GEMM).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rho_phase_kernel(int d, int nt, const cplx *__restrict__ R0, const double *__restrict__ lam,
+                 const double *__restrict__ times, cplx *__restrict__ X) {
+  const size_t dd = (size_t)d * d;
+  const size_t total = dd * (size_t)nt;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = e / dd, ij = e - t * dd;
+    const int i = (int)(ij / d), j = (int)(ij - (size_t)i * d);
+    const cplx ph = cis_m2pi((lam[i] - lam[j]) * times[t]);
+    X[e] = cmul(R0[ij], ph);
+  }
+}
+__global__ void __launch_bounds__(256)
+conj_transpose_kernel(int d, const cplx *__restrict__ U, cplx *__restrict__ Ud) {
+  const int n = d * d;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int i = e / d, j = e - i * d;
+    Ud[(size_t)j * d + i] = cconj(U[e]);
+  }
+}
+
 }  // namespace musim

@@ -132,11 +132,30 @@ class Hamiltonian:
         if not isinstance(operators, (list, tuple)):
             operators = [operators]
         validate_times(times)
-        if len(operators) == 0:
-            raise NotImplementedError("density-matrix output (operators=None) is outside the hot path")
         r = self._check_rho0(rho0)
+        if len(operators) == 0:
+            return self._evolve_rho(r, times.astype(float))
         cols = [self._expect(_lib.MODE_EVOLVE, r, times.astype(float), 1.0, o) for o in operators]
         return np.array(cols).T.astype(complex)
+
+    def _evolve_rho(self, rho0, times):
+        """hamiltonian.py:108-116: without operators the reference returns the density matrices themselves,
+        rho(t) = V [rho0' .* exp(-2 pi i (l_i - l_j) t)] V^H; here as one complex array [nt, d, d]
+        (musim_evolve_rho: two batched GEMMs over the time points on the device)."""
+        import torch
+
+        d = self._matrix.shape[0]
+        dev = torch.device("cuda", self._device)
+        A = torch.from_numpy(np.ascontiguousarray(self._matrix)[None]).to(dev)
+        ev = torch.empty(1, d, dtype=torch.float64, device=dev)
+        U = torch.empty(1, d, d, dtype=torch.complex128, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.eigh_device(self._device, d, 1, A.data_ptr(), ev.data_ptr(), U.data_ptr(), 0, stream)
+        R = torch.from_numpy(np.ascontiguousarray(rho0, dtype=complex)).to(dev)
+        out = torch.empty(len(times), d, d, dtype=torch.complex128, device=dev)
+        _lib.evolve_rho_device(self._device, d, ev.data_ptr(), U.data_ptr(), R.data_ptr(), times, out.data_ptr(), stream)
+        torch.cuda.synchronize(dev)
+        return out.cpu().numpy()
 
     def integrate_decaying(self, rho0, tau, operators):
         """hamiltonian.py:119-164: sum_ab rho'_ab O'_ba / (1/tau + 2 pi i (l_a - l_b)) per operator."""

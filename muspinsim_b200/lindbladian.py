@@ -92,9 +92,32 @@ class Lindbladian:
         if any(_dense(o).shape != r.shape for o in operators):
             raise ValueError("Incompatible measure operator dimension")
         if len(operators) == 0:
-            raise NotImplementedError("density-matrix output (operators=[]) is outside the hot path")
+            return self._evolve_rho(r, times.astype(float))
         cols = [self._run(_lib.MODE_LINDBLAD, r, times.astype(float), 1.0, o) for o in operators]
         return np.array(cols).T.astype(complex)
+
+    def _evolve_rho(self, rho0, times):
+        """lindbladian.py:103-109: without operators the reference returns the density matrices; here as
+        [nt, d, d].  rho(t) stays Hermitian, so its d^2 real parameters are the expectation values of the
+        Hermitian matrix units: rho_ii = <|i><i|>, Re rho_ij = <|i><j| + |j><i|> / 2,
+        Im rho_ij = -<-i (|i><j| - |j><i|)> / 2 -- d^2 runs of the expectation-value path (a capability
+        path for the small systems the Lindbladian is used with, not a tuned one)."""
+        d = rho0.shape[0]
+        out = np.zeros((len(times), d, d), dtype=complex)
+        for i in range(d):
+            E = np.zeros((d, d), dtype=complex)
+            E[i, i] = 1.0
+            out[:, i, i] = self._run(_lib.MODE_LINDBLAD, rho0, times, 1.0, E).real
+            for j in range(i + 1, d):
+                X = np.zeros((d, d), dtype=complex)
+                X[i, j] = X[j, i] = 1.0
+                Y = np.zeros((d, d), dtype=complex)
+                Y[i, j], Y[j, i] = -1.0j, 1.0j
+                re = 0.5 * self._run(_lib.MODE_LINDBLAD, rho0, times, 1.0, X).real
+                im = -0.5 * self._run(_lib.MODE_LINDBLAD, rho0, times, 1.0, Y).real
+                out[:, i, j] = re + 1j * im
+                out[:, j, i] = re - 1j * im
+        return out
 
     def integrate_decaying(self, rho0, tau, operators):
         """lindbladian.py:113-173."""

@@ -43,6 +43,9 @@ def test_version_and_argument_validation_without_gpu():
     assert lib.musim_device_count() >= 0
     assert lib.musim_run(None, 0, 0, None, None, None, None, None, 0, None, 1.0, 1, None, None) == -1
     assert lib.musim_eigh(0, 0, 0, None, None, None, 0, None) == -1
+    assert lib.musim_evolve_rho(0, 0, None, None, None, 0, None, None, None) == -1
+    assert lib.musim_evolve_rho(0, 4, None, None, None, 3, None, None, None) == -1
+    assert lib.musim_trim_pool(-1) == -1
     assert lib.musim_destroy(None) == 0
     assert lib.musim_run_axes_host(None, 0, 0, 0, 1, None, None, None, None, None, None, None, None, None, 0, None,
                                    1.0, 1, None) == -1

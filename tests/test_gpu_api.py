@@ -49,6 +49,93 @@ def test_evolve_fast_evolve_integrate():
     assert np.allclose(fe, 0.5 * np.cos(2 * np.pi * t), atol=1e-12)
 
 
+def test_evolve_without_operators_returns_the_density_matrices():
+    """hamiltonian.py:108-116: with no operators the reference returns the density matrices rho(t);
+    here as [nt, d, d].  Checked against the closed form, the numpy restatement of the reference's
+    lines, and -- where oracle/_ref travelled -- the reference's own Hamiltonian.evolve."""
+    from muspinsim_b200.hamiltonian import Hamiltonian
+
+    sx, sz = _sx_sz()
+    t = np.linspace(0, 1, 7)
+    rho = Hamiltonian(sx).evolve(0.5 * np.eye(2) + sz, t)  # spin precessing about x
+    assert rho.shape == (7, 2, 2)
+    assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1.0, atol=1e-13)
+    assert np.allclose(np.einsum("tij,ji->t", rho, sz), 0.5 * np.cos(2 * np.pi * t), atol=1e-13)
+
+    rng = np.random.default_rng(7)
+    for d, nt in ((12, 33), (48, 9), (96, 5), (100, 3)):
+        A = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        Hm = A + A.conj().T
+        B = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        r0 = B @ B.conj().T
+        r0 /= np.trace(r0).real
+        times = np.sort(rng.uniform(0.0, 0.3, nt))
+        got = Hamiltonian(Hm).evolve(r0, times)
+        ev, V = np.linalg.eigh(Hm)
+        r0e = V.conj().T @ r0 @ V
+        ll = -2.0j * np.pi * (ev[:, None] - ev[None, :])
+        want = np.array([V @ (np.exp(ll * tt) * r0e) @ V.conj().T for tt in times])
+        assert np.max(np.abs(got - want)) < 1e-11
+        assert np.allclose(got, np.conj(np.transpose(got, (0, 2, 1))), atol=1e-12)  # Hermitian at every time
+
+    from oracle import ref_driver
+
+    if ref_driver.available():
+        ref_driver._import()
+        from muspinsim.hamiltonian import Hamiltonian as RefH
+        from muspinsim.spinop import DensityOperator
+
+        d = 8
+        A = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        Hm = A + A.conj().T
+        B = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        r0 = B @ B.conj().T
+        r0 /= np.trace(r0).real
+        times = np.linspace(0.0, 0.5, 6)
+        ref = RefH(Hm, dim=(2, 2, 2)).evolve(DensityOperator(r0, dim=(2, 2, 2)), times)
+        ref = np.array([np.asarray(x.matrix.toarray() if hasattr(x.matrix, "toarray") else x.matrix) for x in ref])
+        assert np.max(np.abs(Hamiltonian(Hm, dim=(2, 2, 2)).evolve(r0, times) - ref)) < 1e-11
+
+
+def test_lindbladian_evolve_without_operators_returns_the_density_matrices():
+    """lindbladian.py:103-109 (operators=[]): density matrices of a dissipative two-spin system; consistent
+    with the expectation values of the same object, trace-preserving, Hermitian, and equal to the
+    reference's own Lindbladian.evolve where oracle/_ref travelled."""
+    from muspinsim_b200.hamiltonian import Hamiltonian
+    from muspinsim_b200.lindbladian import Lindbladian
+
+    rng = np.random.default_rng(11)
+    d = 4
+    A = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    Hm = 0.5 * (A + A.conj().T)
+    J = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    B = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    r0 = B @ B.conj().T
+    r0 /= np.trace(r0).real
+    O = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    O = O + O.conj().T
+    times = np.linspace(0.0, 0.4, 5)
+    L = Lindbladian.from_hamiltonian(Hamiltonian(Hm, dim=(2, 2)), [(J, 0.3)])
+    got = L.evolve(r0, times)
+    assert got.shape == (5, d, d)
+    assert np.allclose(got[0], r0, atol=1e-11)
+    assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-10)
+    assert np.allclose(got, np.conj(np.transpose(got, (0, 2, 1))), atol=1e-12)
+    assert np.allclose(np.einsum("tij,ji->t", got, O), L.evolve(r0, times, [O])[:, 0], atol=1e-10)
+    from oracle import ref_driver
+
+    if ref_driver.available():
+        ref_driver._import()
+        from muspinsim.hamiltonian import Hamiltonian as RefH
+        from muspinsim.lindbladian import Lindbladian as RefL
+        from muspinsim.spinop import DensityOperator, SpinOperator
+
+        ref = RefL.from_hamiltonian(RefH(Hm, dim=(2, 2)), [(SpinOperator(J, dim=(2, 2)), 0.3)]).evolve(
+            DensityOperator(r0, dim=(2, 2)), times)
+        want = np.array([np.asarray(x.matrix.toarray() if hasattr(x.matrix, "toarray") else x.matrix) for x in ref])
+        assert np.max(np.abs(got - want)) < 1e-9
+
+
 def test_validation_errors():
     from muspinsim_b200.hamiltonian import Hamiltonian
 
