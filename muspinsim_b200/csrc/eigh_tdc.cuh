@@ -60,6 +60,16 @@ struct QuadGroup {  // four adjacent lanes share one root (tdc_core.cuh)
     v += __shfl_xor_sync(mask, v, 2);
     return v;
   }
+  __device__ __forceinline__ int isum(int v) const {
+    v += __shfl_xor_sync(mask, v, 1);
+    v += __shfl_xor_sync(mask, v, 2);
+    return v;
+  }
+  __device__ __forceinline__ double max(double v) const {
+    v = fmax(v, __shfl_xor_sync(mask, v, 1));
+    v = fmax(v, __shfl_xor_sync(mask, v, 2));
+    return v;
+  }
   __device__ __forceinline__ double prod(double v) const {
     v *= __shfl_xor_sync(mask, v, 1);
     v *= __shfl_xor_sync(mask, v, 2);
@@ -209,29 +219,35 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
       }
     }
     __syncthreads();
-    // P2: tolerance, first deflation test, sort by rank
-    if (mine) {
-      const double rho = m_rho[mslot];
+    // P2: tolerance, first deflation test, sort by rank.  Quad g / 4 lanes per element (the O(n) scans per
+    // element ran on d of the 4 d threads while the other warps waited at the barrier)
+    int gslot, glo, gmid, ghi;
+    describe(g, gslot, glo, gmid, ghi);
+    if (g < d) {
+      const double rho = m_rho[gslot];
       double dmax = 0.0, zmax = 0.0;
-      for (int i = lo; i < hi; ++i) {
-        dmax = fmax(dmax, fabs(Dv[i]));
-        zmax = fmax(zmax, fabs(zv[i]));
-      }
-      const double tol = 8.0 * tdc::EPS * fmax(dmax, zmax);
-      const bool skip = (rho == 0.0) || (rho * zmax <= tol);
-      const double my = Dv[tid];
+      const double my = Dv[g];
       int rank = 0;
-      for (int i = lo; i < hi; ++i) {
+      for (int i = glo + grp.p; i < ghi; i += 4) {
         const double di = Dv[i];
-        rank += (di < my) || (di == my && i < tid);
+        dmax = fmax(dmax, fabs(di));
+        zmax = fmax(zmax, fabs(zv[i]));
+        rank += (di < my) || (di == my && i < g);
       }
-      sD[lo + rank] = my;
-      sZ[lo + rank] = zv[tid];
-      sidx[lo + rank] = tid;
-      flag[lo + rank] = (rho * fabs(zv[tid]) <= tol) ? 1 : 0;
-      if (tid == lo) {
-        m_tol[mslot] = tol;
-        m_skip[mslot] = skip ? 1 : 0;
+      dmax = grp.max(dmax);
+      zmax = grp.max(zmax);
+      rank = grp.isum(rank);
+      const double tol = 8.0 * tdc::EPS * fmax(dmax, zmax);
+      const bool skip_ = (rho == 0.0) || (rho * zmax <= tol);
+      if (grp.p == 0) {
+        sD[glo + rank] = my;
+        sZ[glo + rank] = zv[g];
+        sidx[glo + rank] = g;
+        flag[glo + rank] = (rho * fabs(zv[g]) <= tol) ? 1 : 0;
+        if (g == glo) {
+          m_tol[gslot] = tol;
+          m_skip[gslot] = skip_ ? 1 : 0;
+        }
       }
     }
     __syncthreads();
@@ -266,56 +282,59 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
         cq[tid] = rr.c * y - rr.s * x;
       }
     }
-    // P5: compaction into the new order [survivors (ascending), deflated]
-    if (mine && !skip) {
-      int k = 0, before = 0;
-      for (int q = lo; q < hi; ++q) {
-        const int sv = flag[q] ? 0 : 1;
-        k += sv;
-        before += (q < tid) ? sv : 0;
-      }
-      const bool surv = !flag[tid];
-      const int i = surv ? before : k + ((tid - lo) - before);
-      nd[lo + i] = sD[tid];
-      zk[lo + i] = sZ[tid];
-      wgt[lo + i] = m_rho[mslot] * sZ[tid] * sZ[tid];
-      ncol[lo + i] = sidx[tid];
-      // reduction order of the GEMM: survivors grouped by support [top | bottom | both], every group
-      // padded to whole k-chunks of 4 (entry -1): a chunk then touches only the row tiles of its block
-      int k0 = 0, k1 = 0, b0 = 0, b1 = 0, b2 = 0;
-      for (int q = lo; q < hi; ++q) {
+    // P5: compaction into the new order [survivors (ascending), deflated]; quad per element as in P2
+    if (g < d && m_skip[gslot] == 0) {
+      int k = 0, before = 0, k0 = 0, k1 = 0, b0 = 0, b1 = 0, b2 = 0;
+      for (int q = glo + grp.p; q < ghi; q += 4) {
         if (flag[q]) continue;
         const int kd = kind[sidx[q]];
+        ++k;
         k0 += kd == 0;
         k1 += kd == 1;
-        if (q < tid) {
+        if (q < g) {
+          ++before;
           b0 += kd == 0;
           b1 += kd == 1;
           b2 += kd == 2;
         }
       }
-      const int p0 = (k0 + 3) & ~3, p1 = (k1 + 3) & ~3, p2 = (k - k0 - k1 + 3) & ~3;
-      if (surv) {
-        const int kd = kind[sidx[tid]];
-        red[mslot * RED + (kd == 0 ? b0 : (kd == 1 ? p0 + b1 : p0 + p1 + b2))] = i;
-      }
-      // padding entries (at most 3 per group), written by the first threads of the merge
-      {
-        const int t3 = tid - lo;
-        if (t3 < p0 - k0) red[mslot * RED + k0 + t3] = -1;
-        if (t3 < p1 - k1) red[mslot * RED + p0 + k1 + t3] = -1;
-        if (t3 < p2 - (k - k0 - k1)) red[mslot * RED + p0 + p1 + (k - k0 - k1) + t3] = -1;
-      }
-      if (tid == lo) {
-        m_k[mslot] = k;
-        m_k0[mslot] = k0;
-        m_k1[mslot] = k1;
+      k = grp.isum(k);
+      before = grp.isum(before);
+      k0 = grp.isum(k0);
+      k1 = grp.isum(k1);
+      b0 = grp.isum(b0);
+      b1 = grp.isum(b1);
+      b2 = grp.isum(b2);
+      if (grp.p == 0) {
+        const bool surv = !flag[g];
+        const int i = surv ? before : k + ((g - glo) - before);
+        nd[glo + i] = sD[g];
+        zk[glo + i] = sZ[g];
+        wgt[glo + i] = m_rho[gslot] * sZ[g] * sZ[g];
+        ncol[glo + i] = sidx[g];
+        // reduction order of the GEMM: survivors grouped by support [top | bottom | both], every group
+        // padded to whole k-chunks of 4 (entry -1): a chunk then touches only the row tiles of its block
+        const int p0 = (k0 + 3) & ~3, p1 = (k1 + 3) & ~3, p2 = (k - k0 - k1 + 3) & ~3;
+        if (surv) {
+          const int kd = kind[sidx[g]];
+          red[gslot * RED + (kd == 0 ? b0 : (kd == 1 ? p0 + b1 : p0 + p1 + b2))] = i;
+        }
+        // padding entries (at most 3 per group), written by the first elements of the merge
+        {
+          const int t3 = g - glo;
+          if (t3 < p0 - k0) red[gslot * RED + k0 + t3] = -1;
+          if (t3 < p1 - k1) red[gslot * RED + p0 + k1 + t3] = -1;
+          if (t3 < p2 - (k - k0 - k1)) red[gslot * RED + p0 + p1 + (k - k0 - k1) + t3] = -1;
+        }
+        if (g == glo) {
+          m_k[gslot] = k;
+          m_k0[gslot] = k0;
+          m_k1[gslot] = k1;
+        }
       }
     }
     __syncthreads();
     // quad g owns root / entry g of the merge that contains g
-    int gslot, glo, gmid, ghi;
-    describe(g, gslot, glo, gmid, ghi);
     const bool gact = (g < d) && (m_skip[gslot] == 0);
     const int gk = gact ? m_k[gslot] : 0;
     const int gj = g - glo;
@@ -408,15 +427,18 @@ tdc_merge_kernel(int d, const double *__restrict__ hdr, const double *__restrict
       const int k = (mine && !skip) ? m_k[mslot] : 0;
       if (mine) fin[tid] = skip ? Dv[tid] : ((tid - lo) < k ? lamn[tid] : nd[tid]);
       __syncthreads();
-      if (mine) {
-        const double my = fin[tid];
+      if (g < d) {
+        const double my = fin[g];
         int rank = 0;
-        for (int i = 0; i < d; ++i) {
+        for (int i = grp.p; i < d; i += 4) {
           const double fi = fin[i];
-          rank += (fi < my) || (fi == my && i < tid);
+          rank += (fi < my) || (fi == my && i < g);
         }
-        dest[tid] = rank;
-        lam[mat * d + rank] = my * (orgnrm > 0.0 ? orgnrm : 1.0);
+        rank = grp.isum(rank);
+        if (grp.p == 0) {
+          dest[g] = rank;
+          lam[mat * d + rank] = my * (orgnrm > 0.0 ? orgnrm : 1.0);
+        }
       }
       if (wactive && wskip) {  // nothing was merged at the top: Q is unchanged, column jj stays column jj
 #pragma unroll
