@@ -110,8 +110,7 @@ __device__ __forceinline__ void hs_reduce_cols23(const cplx (&u)[NU > 0 ? NU : 1
 // y += A x' over an OFF-DIAGONAL superblock (SI > SJ): row direction y_I += A x_J (partial sums to
 // yrow_dst[TB SI + ...]) and column direction y_J += A^H x_I (partial sums to ycol_dst[TB SJ + ...]).
 // x' = x except x'_{k+1} = alpha - beta: only the real part differs (xp0x).  qacc += 2 Re(x_I^H A x_J).
-// FIX: this superblock's rows or columns contain index k+1 (uniform): only then x' differs from x.
-template <int T, bool FIX>
+template <int T>
 __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[T][T], int SI, int SJ, int k, const cplx *x, double xp0x,
                                               int lane, cplx *yrow_dst, cplx *ycol_dst, double &qacc) {
   constexpr int TB = 8 * T;
@@ -121,7 +120,7 @@ __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[T][T], int SI, i
 #pragma unroll
   for (int ti = 0; ti < T; ++ti) {
     xr[ti] = x[r0 + 8 * ti];
-    if (FIX && r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
+    if (r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
   }
   // two passes over the register tiles (rows, then columns) keep the live set small: 168 registers
   // hold 120 of matrix, and the one-pass version spilled
@@ -133,8 +132,8 @@ __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[T][T], int SI, i
     for (int tj = 0; tj < T; ++tj) {
       // (dead columns <= k have x = 0: no liveness branch, the straight-line code schedules better)
       cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];  // zero for columns <= k (publish_col)
-      if (FIX && c0 + 8 * tj == k + 1) xc0.x = xp0x;
-      if (FIX && c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
+      if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
+      if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
 #pragma unroll
       for (int ti = 0; ti < T; ++ti) {
         cfma(yr[ti], make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xc0);
@@ -168,7 +167,7 @@ __device__ __forceinline__ void hs_matvec_off(const HsTile (&a)[T][T], int SI, i
 // qacc += x_I^H A_II x_I (row- and column-direction partial products together cover the whole block).
 // LIVE: skip dead tile columns with uniform branches (pays when one warp owns the whole matrix); the CTA
 // kernel runs straight-line code instead (dead columns have x = 0), which the compiler schedules better.
-template <int T, bool LIVE, bool FIX = true>
+template <int T, bool LIVE>
 __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, int k, const cplx *x, double xp0x,
                                                int lane, cplx *yrow_dst, cplx *ycol_dst, double &qacc) {
   constexpr int TB = 8 * T;
@@ -179,7 +178,7 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, 
 #pragma unroll
   for (int ti = 0; ti < T; ++ti) {
     xr[ti] = x[r0 + 8 * ti];
-    if (FIX && r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
+    if (r0 + 8 * ti == k + 1) xr[ti].x = xp0x;
   }
   {  // row direction (pass 1)
     cplx yr[T];
@@ -189,8 +188,8 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, 
     for (int tj = 0; tj < T; ++tj) {
       if (!LIVE || TB * SI + 8 * tj + 7 > k) {  // live columns; the tile rows ti >= tj are then live too
         cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
-        if (FIX && c0 + 8 * tj == k + 1) xc0.x = xp0x;
-        if (FIX && c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
+        if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
+        if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
 #pragma unroll
         for (int ti = tj; ti < T; ++ti) {
           cfma(yr[ti], make_c(a[ti][tj].re[0], a[ti][tj].im[0]), xc0);
@@ -214,8 +213,8 @@ __device__ __forceinline__ void hs_matvec_diag(const HsTile (&a)[T][T], int SI, 
           ccfma(yc1, make_c(a[ti][tj].re[1], a[ti][tj].im[1]), xr[ti]);
         }
         cplx xc0 = x[c0 + 8 * tj], xc1 = x[c0 + 8 * tj + 1];
-        if (FIX && c0 + 8 * tj == k + 1) xc0.x = xp0x;
-        if (FIX && c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
+        if (c0 + 8 * tj == k + 1) xc0.x = xp0x;
+        if (c0 + 8 * tj + 1 == k + 1) xc1.x = xp0x;
         t = fma(xc0.x, yc0.x, fma(xc0.y, yc0.y, fma(xc1.x, yc1.x, fma(xc1.y, yc1.y, t))));
       }
       u[tj] = hs_reduce_cols1(yc0, yc1, lane);
@@ -452,17 +451,8 @@ hql_tridiag_hs_kernel(int d, int dstride, int koff, int nsteps, const cplx *__re
     // ---- partial products y = A22 x' and the Hermitian form x'^H A22 x' ----
     {
       double qacc = 0.0;
-      const int sbk = (k + 1) / TB;  // the superblock row / column that holds index k+1 (the only entry where x' != x)
-      if (HAS0) {
-        if (SI0 == sbk)
-          hs_matvec_diag<T, false, true>(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
-        else
-          hs_matvec_diag<T, false, false>(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
-      }
-      if (SI1 == sbk || SJ1 == sbk)
-        hs_matvec_off<T, true>(a1, SI1, SJ1, k, x, xp0x, lane, ypart[SJ1], ypart[SI1], qacc);
-      else
-        hs_matvec_off<T, false>(a1, SI1, SJ1, k, x, xp0x, lane, ypart[SJ1], ypart[SI1], qacc);
+      if (HAS0) hs_matvec_diag<T, false>(a0, SI0, k, x, xp0x, lane, ypart[SI0], ypart[S], qacc);
+      hs_matvec_off<T>(a1, SI1, SJ1, k, x, xp0x, lane, ypart[SJ1], ypart[SI1], qacc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) qacc += __shfl_xor_sync(0xffffffffu, qacc, o);
       if (lane == 0) sq[w] = qacc;
