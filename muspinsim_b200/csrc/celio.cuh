@@ -140,8 +140,9 @@ celio_gate_kernel(long long dim, int n_states, cplx *__restrict__ psi, CelioGate
 
 __global__ void __launch_bounds__(256)
 celio_measure_kernel(long long dim, long long half, int n_states, const cplx *__restrict__ psi, cplx s00, cplx s01,
-                     cplx s11, double *__restrict__ out) {
+                     cplx s11, double *__restrict__ out, const int *__restrict__ step) {
   __shared__ double red[8];
+  if (step) out += *step;  // replayed CUDA graph: the time index lives on the device (celio_tick_kernel)
   const long long tot = half * (long long)n_states;
   double acc = 0.0;
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < tot; w += (long long)gridDim.x * blockDim.x) {
@@ -159,6 +160,8 @@ celio_measure_kernel(long long dim, long long half, int n_states, const cplx *__
     if (lane == 0) atomicAdd(out, v);
   }
 }
+
+__global__ void celio_tick_kernel(int *step) { ++*step; }
 
 // Host driver.  All pointers are HOST pointers; results[nt] is accumulated into (+=), summed over
 // the states, exactly like repeated calls of the reference's celio_evolve on one results array.
@@ -226,21 +229,47 @@ inline int celio_evolve_host(int device, long long dim, int n_states, const doub
         e = cudaGetLastError();
       }
     } else {
+      // Streamed path: one launch per gate over all states, one per measurement.  With small states the time
+      // loop is launch bound (nt x (k n_gates + 1) launches of a few microseconds), so ONE time step is captured
+      // as a CUDA graph -- measure (time index read from the device), tick, k x n_gates gate kernels -- and
+      // replayed nt - 1 times; the last measurement is a plain launch.
       const long long work = (long long)n_states * dim;
       const int blocks = (int)std::min<long long>((work / 2 + 255) / 256, 148LL * 16);
-      for (int t = 0; t < nt && e == cudaSuccess; ++t) {
-        celio_measure_kernel<<<blocks, 256>>>(dim, half, n_states, dpsi, s00, s01, s11, dres + t);
+      cudaStream_t cs = nullptr;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t gexec = nullptr;
+      int *dstep = nullptr;
+      e = cudaDeviceSynchronize();  // the uploads / memset above ran on the legacy stream; `cs` does not wait for it
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = dev_malloc((void **)&dstep, sizeof(int));
+      if (e == cudaSuccess) e = cudaMemsetAsync(dstep, 0, sizeof(int), cs);
+      if (e == cudaSuccess && nt > 1) {
+        e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+          celio_measure_kernel<<<blocks, 256, 0, cs>>>(dim, half, n_states, dpsi, s00, s01, s11, dres, dstep);
+          celio_tick_kernel<<<1, 1, 0, cs>>>(dstep);
+          for (int rep = 0; rep < k; ++rep)
+            for (int c = 0; c < n_gates; ++c) {
+              const long long tot = hg[c].od * (long long)n_states;
+              const int gb = (int)std::min<long long>((tot + 255) / 256, 148LL * 16);
+              celio_gate_kernel<<<gb, 256, 0, cs>>>(dim, n_states, dpsi, hg[c]);
+            }
+          e = cudaStreamEndCapture(cs, &graph);
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&gexec, graph, 0);
+        for (int t = 0; t < nt - 1 && e == cudaSuccess; ++t) e = cudaGraphLaunch(gexec, cs);
+        if (launches) *launches += (int64_t)(nt - 1) * (2 + (int64_t)k * n_gates);
+      }
+      if (e == cudaSuccess) {
+        celio_measure_kernel<<<blocks, 256, 0, cs>>>(dim, half, n_states, dpsi, s00, s01, s11, dres, dstep);
         if (launches) ++*launches;
-        if (t == nt - 1) break;
-        for (int rep = 0; rep < k; ++rep)
-          for (int c = 0; c < n_gates; ++c) {
-            const long long tot = hg[c].od * (long long)n_states;
-            const int gb = (int)std::min<long long>((tot + 255) / 256, 148LL * 16);
-            celio_gate_kernel<<<gb, 256>>>(dim, n_states, dpsi, hg[c]);
-            if (launches) ++*launches;
-          }
         e = cudaGetLastError();
       }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+      dev_free(dstep);
+      if (cs) cudaStreamDestroy(cs);
     }
   }
   std::vector<double> hres(nt);
