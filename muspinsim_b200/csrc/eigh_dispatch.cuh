@@ -68,13 +68,21 @@ struct EighWs {
   size_t rot_cap = 0;
   int swp_cap = 0;
 
+  // complex entries of Q per matrix: the eigenvector / phase buffer.  The trailing blocks handed between the K1 phases
+  // need 72^2 + 48^2 entries for d > 48 and 64^2 + 32^2 for 32 < d <= 48; small systems only need d^2 (a fixed
+  // floor would shrink the launch groups of the 10^7-configuration scans at d = 24 by 13 x)
+  static size_t q_entries(int d) {
+    const size_t dd = (size_t)d * d;
+    return d > 48 ? std::max<size_t>(dd, 72 * 72 + 48 * 48) : (d > 32 ? std::max<size_t>(dd, 64 * 64 + 32 * 32) : dd);
+  }
+
   static bool jacobi_vglobal(int d) { return eigh_jacobi_smem(d, false) > MUSIM_MAX_SMEM_OPTIN; }
 
   static size_t bytes_per_matrix(int method, int d) {
     const size_t dd = (size_t)d * d;
     if (method == EIGH_HQL)
       return (d > HQL_MAX_D ? (size_t)d * (d | 1) * sizeof(cplx) : 0) +
-             2 * (2 * d * sizeof(double) + std::max<size_t>(dd, 72 * 72 + 48 * 48) * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
+             2 * (2 * d * sizeof(double) + q_entries(d) * sizeof(cplx) + (dd / 2 + d) * sizeof(cplx)) + dd * sizeof(double) +
              (2 * dd + 64 + 14 * (6 * d + 16)) * sizeof(double2) + (6 * d + 16) * sizeof(SweepIdx) + sizeof(int) +
              d * sizeof(unsigned short);
     return jacobi_vglobal(d) ? (size_t)d * (d | 1) * sizeof(cplx) : 0;
@@ -141,7 +149,7 @@ struct EighWs {
       for (int i = 0; i < (dbl ? 2 : 1); ++i) {
         EW_ALLOC(dbuf[i], (size_t)n * d);
         EW_ALLOC(ebuf[i], (size_t)n * d);
-        EW_ALLOC(Q[i], (size_t)n * std::max<size_t>(dd, 72 * 72 + 48 * 48));
+        EW_ALLOC(Q[i], (size_t)n * q_entries(d));
         EW_ALLOC(Vp[i], (size_t)n * vcap);
         EW_ALLOC(tauv[i], (size_t)n * d);
       }
