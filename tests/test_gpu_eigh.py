@@ -124,3 +124,33 @@ def test_divide_and_conquer_range(d):
             np.diag(np.abs(np.arange(d) - (d - 1) / 2)).astype(complex) + np.diag(np.ones(d - 1), 1) + np.diag(np.ones(d - 1), -1),
             _rand_herm(rng, 1, d)[0] * 1e-7, _rand_herm(rng, 1, d)[0] * 7e4]
     _check(np.array([0.5 * (m + m.conj().T) for m in mats]), 2)
+
+
+@pytest.mark.parametrize("d", [49, 56, 63, 64, 65, 71, 72, 73, 80, 88, 95, 96])
+def test_structured_matrices_at_the_phase_boundaries(d):
+    """The half-storage tridiagonalisation hands the trailing block from phase to phase (96 -> 72 -> 48 -> 32):
+    sizes on both sides of every boundary, with the structures that exercise identity reflectors, dead tiles and
+    deflation -- dense, block-diagonal, sparse, low rank + identity, already tridiagonal, graded."""
+    rng = np.random.default_rng(1000 + d)
+    mats = []
+    for kind in range(6):
+        A = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        A = A + A.conj().T
+        if kind == 1:
+            m = d // 3
+            A[:m, m:] = 0
+            A[m:, :m] = 0
+        elif kind == 2:
+            A = A * (rng.uniform(size=(d, d)) < 0.08)
+            A = A + A.conj().T
+        elif kind == 3:
+            v = rng.normal(size=(d, 3)) + 1j * rng.normal(size=(d, 3))
+            A = v @ v.conj().T + 2 * np.eye(d)
+        elif kind == 4:
+            A = np.diag(rng.normal(size=d)).astype(complex) + np.diag(rng.normal(size=d - 1), 1)
+            A = A + A.conj().T
+        elif kind == 5:
+            s = np.logspace(0, -8, d)
+            A = A * s[:, None] * s[None, :]
+        mats.append(A)
+    _check(np.array(mats), 2, tol=1e-13)
