@@ -27,9 +27,15 @@ class _ReferenceSystemView(MuonSpinSystem):
         self._dim = tuple(int(x) for x in sysr.dimension)
         self._mu_i = int(sysr.muon_index)
         self._e_i = set(sysr.elec_indices)
-        self._terms = []
-        H = ref_runner.Hsys.matrix  # spinsys.py:613-626 via experiment.py:119
-        self._H = np.asarray(H.toarray() if hasattr(H, "toarray") else H, dtype=complex)
+        # interaction terms (label, indices, tensor): what Celio's method builds its gates from (celio.py:73-140)
+        self._terms = [(t.label, tuple(int(i) for i in t.indices), np.array(t.tensor, dtype=float))
+                       for t in getattr(sysr, "_terms", [])]
+        d = int(np.prod(self._dim))
+        if getattr(ref_runner.config, "celio_k", 0):
+            self._H = np.zeros((d, d), dtype=complex)  # Hsys is a CelioHamiltonian (no dense matrix); not needed
+        else:
+            H = ref_runner.Hsys.matrix  # spinsys.py:613-626 via experiment.py:119
+            self._H = np.asarray(H.toarray() if hasattr(H, "toarray") else H, dtype=complex)
         self._ref = sysr
         from .spinsys import spin_operators
 
@@ -70,11 +76,17 @@ _HANDLES = {}
 
 
 def runner_from_reference(ref_runner, device=None, comm=None):
-    if getattr(ref_runner.config, "celio_k", 0):
-        raise NotImplementedError("Celio's method stays on the reference path")
+    celio_k = int(getattr(ref_runner.config, "celio_k", 0) or 0)
+    celio_avg = int(getattr(ref_runner.config, "celio_averages", 0) or 0)
+    if celio_k and not celio_avg:
+        # the density-matrix Trotter variant (celio.py:207-287) stays on the reference path
+        raise NotImplementedError("Celio's method without random initial states stays on the reference path")
     dissip = {int(i): float(a) for i, a in ref_runner.config.dissipation_terms.items()}
-    return ExperimentRunner(system=system_from_reference(ref_runner), table=table_from_reference(ref_runner.config),
-                            dissipation=dissip, device=device, comm=comm, handle_cache=_HANDLES)
+    r = ExperimentRunner(system=system_from_reference(ref_runner), table=table_from_reference(ref_runner.config),
+                         dissipation=dissip, device=device, comm=comm, handle_cache=None if celio_k else _HANDLES)
+    if celio_k:  # `celio k averages` (experiment.py:454-470): batched state-vector evolution on the GPU
+        r._celio_k, r._celio_averages = celio_k, celio_avg
+    return r
 
 
 def local_device():
@@ -116,8 +128,8 @@ def patch_reference():
     original = mexp.ExperimentRunner.run
 
     def run(self):
-        if getattr(self.config, "celio_k", 0):
-            return original(self)
+        if getattr(self.config, "celio_k", 0) and not getattr(self.config, "celio_averages", 0):
+            return original(self)  # density-matrix Trotter variant: reference path
         return run_reference_runner(self, mpi=getattr(mexp, "mpi", None))
 
     run._musim_original = original

@@ -138,3 +138,42 @@ def test_fitting_runner_through_the_patched_path(method):
     assert abs(sol_cpu.x[0] - 10.0) < 1e-4
     assert abs(sol_gpu.x[0] - sol_cpu.x[0]) < 1e-6
     assert np.max(np.abs(fr._runner.config.results - ms.FittingRunner(ms.MuSpinInput(io.StringIO(text)))._ytarg)) < 1e-6
+
+
+def test_patched_reference_runner_with_celio_averages():
+    """`celio k averages` through the reference's own objects: the patched ExperimentRunner.run evaluates the
+    random initial states as one batch on the GPU (experiment.py:454-470 loops over them with the C++
+    extension).  Both draw the states from numpy's global generator in the same order, so a seeded run must
+    reproduce the reference's result; without `averages` the density-matrix variant stays on the reference path."""
+    ref_driver = _need_ref()
+    if not hasattr(np, "product"):
+        np.product = np.prod  # the reference's celio.py predates numpy 2 (test infrastructure only)
+    from muspinsim_b200 import _lib, adapter
+
+    spec = {"name": "celio_dropin", "spins": ["mu", "F", "F"],
+            "couplings": [{"type": "dipolar", "i": 1, "j": 2, "value": [0.0, 0.0, 1.17]},
+                          {"type": "dipolar", "i": 1, "j": 3, "value": [0.0, 0.0, -1.17]}],
+            "field": [[0.0, 0.0, 0.002]], "time": np.linspace(0, 2.0, 21), "celio": [3, 5],
+            "orientation": [[0.0, 0.0, 0.0], [0.3, 0.7, 1.1]], "orientation_mode": "zyz"}
+    np.random.seed(5)
+    want = ref_driver.make_runner(spec).run()
+    r_gpu = ref_driver.make_runner(spec)
+    adapter.patch_reference()
+    try:
+        l0 = _lib.load().musim_celio_launch_count()
+        np.random.seed(5)
+        got = r_gpu.run()
+        assert _lib.load().musim_celio_launch_count() > l0, "the Celio run did not reach the CUDA library"
+        # density-matrix variant (no averages): untouched reference path, no GPU launches
+        spec2 = dict(spec, celio=[3], time=np.linspace(0, 0.5, 4), orientation=[[0.0, 0.0, 0.0]])
+        l1 = _lib.load().musim_celio_launch_count()
+        r2 = ref_driver.make_runner(spec2)
+        try:
+            r2.run()
+        except Exception:
+            pass  # (the reference's own slow path needs qutip; only the routing matters here)
+        assert _lib.load().musim_celio_launch_count() == l1
+    finally:
+        adapter.unpatch_reference()
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) < TOL
