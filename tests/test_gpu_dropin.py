@@ -177,3 +177,31 @@ def test_patched_reference_runner_with_celio_averages():
         adapter.unpatch_reference()
     assert got.shape == want.shape
     assert np.max(np.abs(got - want)) < TOL
+
+
+def test_command_line_through_the_gpu_path(tmp_path):
+    """`python -m muspinsim_b200 input.in -o out` = the reference's own CLI (muspinsim/__main__.py) with the hot
+    loop on the GPU: the `.dat` file it writes equals the one `python -m muspinsim` writes from the same input."""
+    import subprocess
+    import sys
+
+    _need_ref()
+    from oracle.muspin_oracle import spec_to_infile
+
+    spec, _ = load_golden("hfine_powder_eulrange3")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(root, "oracle", "_ref"), os.path.join(root, "oracle", "shims"), root,
+                                         env.get("PYTHONPATH", "")])
+    outs = {}
+    for mod in ("muspinsim", "muspinsim_b200"):
+        wd = tmp_path / mod
+        wd.mkdir()
+        (wd / "input.in").write_text(spec_to_infile(spec))
+        p = subprocess.run([sys.executable, "-m", mod, str(wd / "input.in"), "-o", str(wd / "out")], env=env, cwd=str(wd),
+                           capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[mod] = _dat_files(str(wd / "out"))
+    assert outs["muspinsim"] and sorted(outs["muspinsim"]) == sorted(outs["muspinsim_b200"])
+    for f, ref in outs["muspinsim"].items():
+        assert np.max(np.abs(outs["muspinsim_b200"][f] - ref)) < TOL
