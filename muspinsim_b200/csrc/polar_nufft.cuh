@@ -20,10 +20,18 @@
 // Aliasing error for w = 12, M/N >= 2: 7e-13 * sum|c| (tools/nufft_prototype.py), far inside the
 // 1e-9 parity bar; non-uniform time arrays keep the direct kernel.
 //
-// Spread kernel mapping: one private grid per WARP in shared memory (M complex = 32 KB at
-// N <= 1024: 7 warps per SM), so there are no atomics: a half-warp handles one point, lane = tap,
-// plain read-modify-write of 12 consecutive cells.  The two half-warps' windows may overlap
-// (then the two updates are issued one after the other).
+// Half grid: only the REAL part of the transform is wanted, and Re(c e^{2 pi i k' u}) =
+// Re(conj(c) e^{2 pi i k' (-u)}), so every point is first moved to u in [0, 1/2] (strength conjugated
+// if it was mirrored -- once per point, nothing per tap).  The points then occupy the cells
+// -5 .. M/2 + 6 only; the private grids hold exactly that range (no wrap-around mask either), and
+// when a private grid is flushed its margin cells m < 0 (m > M/2) are added, conjugated, to cell -m
+// (M - m) of the global grid -- the same mirror identity applied to a cell instead of a point.  The
+// global grid keeps M cells (upper half zero) and the FFT kernel is the plain complex one.
+//
+// Spread kernel mapping: one private grid per WARP in shared memory ((M/2 + 32) complex = 16.5 KB
+// at N <= 1024: 8 warps per SM, the register file is the cap), so there are no atomics: a half-warp
+// handles one point, lane = tap, plain read-modify-write of 12 consecutive cells.  The two
+// half-warps' windows may overlap (then the two updates are issued one after the other).
 #pragma once
 #include <cstddef>
 #include <vector>
@@ -34,6 +42,7 @@
 namespace musim {
 
 #define NU_W 12
+#define NU_MARG (NU_W / 2 - 1)  // cells of margin below cell 0 of the half grid (tap 0 of a point in cell 0)
 #define MUSIM_NU_SMEM (227 * 1024)
 #define NU_DEG 10
 #define NU_BETA (2.30 * NU_W)
@@ -88,24 +97,24 @@ __global__ void __launch_bounds__(256)
 polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, int n_cfg, int S, int plen,
                           int units_per_cta, const cplx *__restrict__ W, const double *__restrict__ lam,
                           const double *__restrict__ wgt, const int *__restrict__ slot, int N, double t0,
-                          double dt, int M, cplx *__restrict__ G, int *__restrict__ touched) {
+                          double dt, int M, int PG, cplx *__restrict__ G, int *__restrict__ touched) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   cplx *grid_all = reinterpret_cast<cplx *>(smem_raw);
-  cplx *grid = grid_all + (size_t)warp * M;
-  NuPoint *stage = reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * M) + warp * 32;
-  int *wslot = reinterpret_cast<int *>(reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * M) + nwarps * 32);
+  cplx *grid = grid_all + (size_t)warp * PG;
+  NuPoint *stage = reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * PG) + warp * 32;
+  int *wslot = reinterpret_cast<int *>(reinterpret_cast<NuPoint *>(grid_all + (size_t)nwarps * PG) + nwarps * 32);
   int *ctr = wslot + nwarps;
   const int tap = lane & 15, half = lane >> 4;
   const bool tap_on = tap < NU_W;
-  const int Mm = M - 1;
+  const int Mh = M >> 1;
   const unsigned grid_s = (unsigned)__cvta_generic_to_shared(grid);
   const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
   double cf[NU_DEG + 1];
 #pragma unroll
   for (int m = 0; m <= NU_DEG; ++m) cf[m] = tap_on ? nu_coef[tap_on ? tap : 0][m] : 0.0;
 
-  for (int m = lane; m < M; m += 32) grid[m] = make_c(0.0, 0.0);
+  for (int m = lane; m < PG; m += 32) grid[m] = make_c(0.0, 0.0);
   if (threadIdx.x == 0) *ctr = 0;
   __syncthreads();
 
@@ -116,12 +125,25 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
   const double halfN = (double)(N / 2);
   int cur_slot = -1;
 
+  // private cell q holds fine-grid cell m = q - NU_MARG of the HALF grid [0, M/2] plus the margins the
+  // windows of points near its two ends reach into; a margin cell is the mirror image of cell -m
+  // (or M - m): it is added, conjugated, to that cell (see "Half grid" above)
+  auto fold_add = [&](cplx *Gs, int q, cplx v) {
+    int m = q - NU_MARG;
+    if (m < 0) {
+      m = -m;
+      v.y = -v.y;
+    } else if (m > Mh) {
+      m = M - m;
+      v.y = -v.y;
+    }
+    if (v.x != 0.0) atomicAdd(&Gs[m].x, v.x);
+    if (v.y != 0.0) atomicAdd(&Gs[m].y, v.y);
+  };
   auto flush_warp = [&](int s) {
     cplx *Gs = G + (size_t)s * M;
-    for (int m = lane; m < M; m += 32) {
-      const cplx v = grid[m];
-      if (v.x != 0.0) atomicAdd(&Gs[m].x, v.x);
-      if (v.y != 0.0) atomicAdd(&Gs[m].y, v.y);
+    for (int m = lane; m < PG; m += 32) {
+      fold_add(Gs, m, grid[m]);
       grid[m] = make_c(0.0, 0.0);
     }
     if (lane == 0) touched[s] = 1;
@@ -189,12 +211,11 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
       const double f = q.li - q.lj;
       const double x = f * dt;
       const double uu = rint(x) - x;  // -frac(f dt) in [-1/2, 1/2]: cycles per time step
-      double pos = uu * (double)M;
-      if (pos < 0.0) pos += (double)M;
-      double fl = floor(pos);
-      if (fl >= (double)M) fl = (double)M - 1.0;  // pos rounded up to M
+      const bool mirror = uu < 0.0;   // half grid: the point at -u with the conjugate strength has the same real part
+      const double pos = fabs(uu) * (double)M;  // in [0, M/2]
+      const double fl = floor(pos);
       pt.y = 2.0 * (pos - fl) - 1.0;
-      pt.base = ((int)fl - (NU_W / 2 - 1)) & Mm;
+      pt.base = (int)fl - (NU_W / 2 - 1) + NU_MARG;  // private cell of tap 0, in [0, M/2 + NU_MARG]
       // strength: weights * exp(-2 pi i f t0) * exp(2 pi i (N/2) u)
       double ph = fma(halfN, uu, -f * t0);
       ph -= rint(ph);
@@ -203,12 +224,13 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
       const double sc = (ij.i == ij.j) ? q.wc : 2.0 * q.wc;
       pt.cre = sc * fma(q.w.x, cs, -q.w.y * sn);
       pt.cim = sc * fma(q.w.x, sn, q.w.y * cs);
+      if (mirror) pt.cim = -pt.cim;
     }
     // points q and q + 16 are updated in the same step by the two half-warps: do their windows
     // (16 cells: lanes 12..15 add zeros) overlap?  Symmetric, so both halves see the same flag.
     const int ob = __shfl_xor_sync(0xffffffffu, pt.base, 16);
-    const int diff = (pt.base - ob) & Mm;
-    pt.flag = (diff < 16 || diff > M - 16) ? 1 : 0;
+    const int diff = pt.base - ob;
+    pt.flag = (diff < 16 && diff > -16) ? 1 : 0;
     stage[2 * tap + half] = pt;
   };
 
@@ -228,7 +250,7 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
       const int2 bf = *reinterpret_cast<const int2 *>(&q->base);
       cre[st] = a.x;
       cim[st] = a.y;
-      off[st] = grid_s + ((((unsigned)bf.x + tap) & Mm) << 4);
+      off[st] = grid_s + (((unsigned)bf.x + tap) << 4);
       ovl |= (unsigned)bf.y << st;
     }
   };
@@ -312,15 +334,14 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
   if (same) {
     if (s0 >= 0) {
       cplx *Gs = G + (size_t)s0 * M;
-      for (int m = threadIdx.x; m < M; m += blockDim.x) {
+      for (int m = threadIdx.x; m < PG; m += blockDim.x) {
         cplx v = grid_all[m];
         for (int q = 1; q < nwarps; ++q) {
-          const cplx t = grid_all[(size_t)q * M + m];
+          const cplx t = grid_all[(size_t)q * PG + m];
           v.x += t.x;
           v.y += t.y;
         }
-        if (v.x != 0.0) atomicAdd(&Gs[m].x, v.x);
-        if (v.y != 0.0) atomicAdd(&Gs[m].y, v.y);
+        fold_add(Gs, m, v);
       }
       if (threadIdx.x == 0) touched[s0] = 1;
     }
@@ -478,6 +499,10 @@ inline int nu_grid_size(int N) {
   return M;
 }
 
+// Cells of a warp's private HALF grid: cells -NU_MARG .. M/2 + 15 - NU_MARG (lane 15 of a point in cell M/2:
+// the lanes 12..15 of a half-warp add zeros to the four cells behind the window), padded.
+inline int nu_private_cells(int M) { return ((M / 2 + NU_MARG + 16) + 15) & ~15; }
+
 // Whether the NUFFT path applies: uniform grid handled by the caller; here only sizes.
 inline bool nu_supported(int N, int64_t n_slots) {
   if (N < 2) return false;
@@ -535,7 +560,8 @@ inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const Pair
     ws.dM = M;
   }
   // geometry: as many warps (private grids) per CTA as shared memory allows, one CTA per SM
-  const size_t per_warp = (size_t)M * sizeof(cplx) + 32 * sizeof(NuPoint);
+  const int PG = nu_private_cells(M);
+  const size_t per_warp = (size_t)PG * sizeof(cplx) + 32 * sizeof(NuPoint);
   int nwarps = (int)std::min<size_t>(8, (size_t)(MUSIM_NU_SMEM - 256) / per_warp);
   if (nwarps < 1) return cudaErrorInvalidConfiguration;
   int dev = 0, n_sm = 148;
@@ -557,7 +583,7 @@ inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const Pair
   e = cudaFuncSetAttribute(polar_nufft_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   polar_nufft_spread_kernel<<<ctas, 32 * nwarps, smem, st>>>(d, npairs, pairs, (int)n, S, plen, (int)upc, W, lam, wgt,
-                                                            slot, N, t0, dt, M, ws.G, ws.touched);
+                                                            slot, N, t0, dt, M, PG, ws.G, ws.touched);
   const size_t fsmem = (size_t)M * sizeof(cplx);
   e = cudaFuncSetAttribute(polar_nufft_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
   if (e != cudaSuccess) return e;

@@ -220,17 +220,31 @@ def test_nufft_tables_reproduce_the_transform_on_the_host():
         u = np.rint(f * dt) - f * dt  # cycles per step in [-1/2, 1/2]
         k = np.arange(nt)
         want = (c[None, :] * np.exp(2j * np.pi * np.outer(k, u))).sum(1)
-        pos = np.where(u < 0, u * M + M, u * M)
-        fl = np.minimum(np.floor(pos), M - 1)
-        y = 2.0 * (pos - fl) - 1.0
-        base = (fl.astype(np.int64) - (w // 2 - 1)) % M
+        # half grid (polar_nufft.cuh): points mirrored to u in [0, 1/2] with conjugate strength, private
+        # cells -marg .. M/2 + w/2, margins folded (conjugated) onto the cells they mirror
         cp = c * np.exp(2j * np.pi * (nt // 2) * u)
-        grid = np.zeros(M, complex)
+        cp = np.where(u < 0, np.conj(cp), cp)
+        pos = np.abs(u) * M
+        fl = np.floor(pos)
+        y = 2.0 * (pos - fl) - 1.0
+        marg = w // 2 - 1
+        base = fl.astype(np.int64)  # private cell of tap 0 (= cell fl - marg, shifted by marg)
+        priv = np.zeros(M // 2 + marg + 16, complex)
         for l in range(w):
             phi = np.polynomial.polynomial.polyval(y, coef[l], tensor=False)
-            np.add.at(grid, (base + l) % M, cp * phi)
+            np.add.at(priv, base + l, cp * phi)
+        grid = np.zeros(M, complex)
+        for q, v in enumerate(priv):
+            m = q - marg
+            if m < 0:
+                grid[-m] += np.conj(v)
+            elif m > M // 2:
+                grid[M - m] += np.conj(v)
+            else:
+                grid[m] += v
         F = np.fft.ifft(grid) * M
-        got = F[(k - nt // 2) % M] * dec
+        got = (F[(k - nt // 2) % M] * dec).real
+        want = want.real
         assert np.max(np.abs(got - want)) < 1e-11
 
 
