@@ -29,7 +29,7 @@
 // global grid keeps M cells (upper half zero) and the FFT kernel is the plain complex one.
 //
 // Spread kernel mapping: one private grid per WARP in shared memory ((M/2 + 32) complex = 16.5 KB
-// at N <= 1024: 8 warps per SM, the register file is the cap), so there are no atomics: a half-warp
+// at N <= 1024: 12 warps per SM with the 156-register variant), so there are no atomics: a half-warp
 // handles one point, lane = tap, plain read-modify-write of 12 consecutive cells.  The two
 // half-warps' windows may overlap (then the two updates are issued one after the other).
 #pragma once
@@ -93,7 +93,10 @@ __device__ __forceinline__ double nu_horner(const double (&cf)[NU_DEG + 1], doub
 //   phase B  16 read-modify-write steps on the private grid
 // Software pipeline: pair indices are loaded three batches ahead, W / lambda two batches ahead, and
 // phase A of batch b+1 is interleaved with phase B of batch b (FP64 work under the LDS latency).
-__global__ void __launch_bounds__(256)
+// CREG: the strengths of the batch's points stay in registers (230 registers: two warps per scheduler); else they
+// are re-read from the staging buffer in every step (one more LDS.128 per step, 156 registers: three warps).
+template <bool CREG>
+__global__ void __launch_bounds__(CREG ? 256 : 384)
 polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, int n_cfg, int S, int plen,
                           int units_per_cta, const cplx *__restrict__ W, const double *__restrict__ lam,
                           const double *__restrict__ wgt, const int *__restrict__ slot, int N, double t0,
@@ -234,7 +237,8 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
     stage[2 * tap + half] = pt;
   };
 
-  double yy[16], phi[16], cre[16], cim[16];
+  double yy[16], phi[16], cre[CREG ? 16 : 1], cim[CREG ? 16 : 1];
+  cre[0] = cim[0] = 0.0;
   unsigned off[16];
   unsigned ovl = 0;
   auto load_y = [&]() {
@@ -246,10 +250,13 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
 #pragma unroll
     for (int st = 0; st < 16; ++st) {
       const NuPoint *q = stage + 2 * st + half;
-      const double2 a = *reinterpret_cast<const double2 *>(&q->cre);
+      double2 a = make_double2(0.0, 0.0);
+      if (CREG) a = *reinterpret_cast<const double2 *>(&q->cre);
       const int2 bf = *reinterpret_cast<const int2 *>(&q->base);
-      cre[st] = a.x;
-      cim[st] = a.y;
+      if (CREG) {
+        cre[st] = a.x;
+        cim[st] = a.y;
+      }
       off[st] = grid_s + (((unsigned)bf.x + tap) << 4);
       ovl |= (unsigned)bf.y << st;
     }
@@ -299,8 +306,10 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
 #pragma unroll
       for (int q = st + 1; q < 16 && q <= st + NU_DEG; ++q)
         phi[q] = fma_pinned(phi[q], yy[q], cf[NU_DEG - 1 - (st - q + NU_DEG)]);
-      vx = fma(cre[st], phi[st], vx);
-      vy = fma(cim[st], phi[st], vy);
+      double c_re = cre[CREG ? st : 0], c_im = cim[CREG ? st : 0];
+      if (!CREG) lds_f64x2(stage_s + (unsigned)((2 * st + half) * sizeof(NuPoint)), c_re, c_im);
+      vx = fma(c_re, phi[st], vx);
+      vy = fma(c_im, phi[st], vy);
       if (!((skip >> st) & 1u)) sts_f64x2(off[st], vx, vy);
     }
     if (ovl) {  // warp-uniform, rare
@@ -310,8 +319,10 @@ polar_nufft_spread_kernel(int d, int npairs, const PairIdx *__restrict__ pairs, 
         if ((skip >> st) & 1u) {
           double vx, vy;
           lds_f64x2(off[st], vx, vy);
-          vx = fma(cre[st], phi[st], vx);
-          vy = fma(cim[st], phi[st], vy);
+          double c_re = cre[CREG ? st : 0], c_im = cim[CREG ? st : 0];
+          if (!CREG) lds_f64x2(stage_s + (unsigned)((2 * st + half) * sizeof(NuPoint)), c_re, c_im);
+          vx = fma(c_re, phi[st], vx);
+          vy = fma(c_im, phi[st], vy);
           sts_f64x2(off[st], vx, vy);
         }
         __syncwarp();
@@ -563,6 +574,10 @@ inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const Pair
   const int PG = nu_private_cells(M);
   const size_t per_warp = (size_t)PG * sizeof(cplx) + 32 * sizeof(NuPoint);
   int nwarps = (int)std::min<size_t>(8, (size_t)(MUSIM_NU_SMEM - 256) / per_warp);
+  // 12 private grids fit (M <= 2048): the 156-register variant that re-reads the strengths from the staging
+  // buffer, three warps per scheduler (3.43 vs 3.91 ms at C5); else the 230-register variant with up to 8 warps
+  const bool creg = (size_t)(MUSIM_NU_SMEM - 256) / per_warp < 12;
+  if (!creg) nwarps = 12;
   if (nwarps < 1) return cudaErrorInvalidConfiguration;
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
@@ -580,10 +595,16 @@ inline cudaError_t launch_polar_nufft(NufftWs &ws, int d, int npairs, const Pair
   const long upc = (units + n_sm - 1) / n_sm;  // contiguous units per CTA, drawn dynamically by its warps
   const int ctas = (int)((units + upc - 1) / upc);
   const size_t smem = nwarps * per_warp + (nwarps + 1) * sizeof(int) + 16;
-  e = cudaFuncSetAttribute(polar_nufft_spread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(polar_nufft_spread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  polar_nufft_spread_kernel<<<ctas, 32 * nwarps, smem, st>>>(d, npairs, pairs, (int)n, S, plen, (int)upc, W, lam, wgt,
-                                                            slot, N, t0, dt, M, PG, ws.G, ws.touched);
+  e = cudaFuncSetAttribute(polar_nufft_spread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (creg)
+    polar_nufft_spread_kernel<true><<<ctas, 32 * nwarps, smem, st>>>(d, npairs, pairs, (int)n, S, plen, (int)upc, W, lam, wgt,
+                                                                  slot, N, t0, dt, M, PG, ws.G, ws.touched);
+  else
+    polar_nufft_spread_kernel<false><<<ctas, 32 * nwarps, smem, st>>>(d, npairs, pairs, (int)n, S, plen, (int)upc, W, lam, wgt,
+                                                                   slot, N, t0, dt, M, PG, ws.G, ws.touched);
   const size_t fsmem = (size_t)M * sizeof(cplx);
   e = cudaFuncSetAttribute(polar_nufft_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
   if (e != cudaSuccess) return e;
