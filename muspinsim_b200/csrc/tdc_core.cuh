@@ -231,17 +231,24 @@ TDC_HD bool leaf_ql(int n, double *D, double *E, Rows &rows) {
 // strictly increasing dk[0..k), non-zero z, rho > 0.  Returns the index `org` of the pole nearest to
 // the root and *mu = lambda - dk[org]; dk_i - lambda must then be formed as (dk_i - dk_org) - mu.
 //
-// Iteration ("middle way", Li 1994 / LAPACK dlaed4): with L, R the poles that bracket the root,
-// psi = sum_{i <= L}, phi = sum_{i >= R} are each replaced by a one-pole model that matches value
-// and slope at the current point,
-//     psi(x) ~ r_L + s / (d_L - x),  s = (d_L - mu)^2 psi'(mu),      phi(x) ~ r_R + S / (d_R - x),
-// and the resulting quadratic is solved in closed form for the step eta -- no inner iteration: every
-// pass is ONE sweep over the poles (4 interleaved reciprocal chains per lane on the device) plus a
-// fixed ~60-instruction tail.  A first version refined a two-pole + linear model by Newton steps:
-// 4.4 serial inner steps of ~80 dependent instructions per pass were half of the merge kernel.
-// Safeguards: a sign bracket [lo, hi] on g (bisection if the model step leaves it), stop when
-// |g| is within its rounding error bound, when the bracket collapses, or when the step is below
-// 2e-9 |mu| (quadratic convergence: the next error is below an ulp).
+// Iteration: with L, R the poles that bracket the root, psi = sum_{i <= L} and phi = sum_{i >= R} are each
+// replaced by a ONE-pole model  r + s / (p - x)  and the resulting quadratic is solved in closed form for the
+// step -- no inner iteration: every pass is ONE sweep over the poles (4 interleaved reciprocal chains per lane
+// on the device) plus a fixed tail.
+//   * third-order step: r, s AND the pole p match value, slope and curvature of psi (phi) at the current point
+//     (p - x = 2 psi' / psi'').  Cubic convergence, and a cluster of poles behind the neighbouring one is
+//     represented by a pole at its weighted harmonic-mean distance.
+//   * "middle way" step (Li 1994 / LAPACK dlaed4; the only step until the second half of round 2): p fixed at the
+//     neighbouring pole d_L (d_R), s = (d_L - mu)^2 psi'(mu).  Fallback when the fitted model's root leaves the
+//     bracket (a neighbouring pole of tiny weight is invisible in the sums far away from it).  With the fixed
+//     poles alone a pole of small weight next to a cluster made the iteration creep towards the root from one
+//     side (C5 Hamiltonians: 4.77 sweeps per root, 8 % of the roots >= 7 and the slowest of a merge's 96 roots
+//     ~9; now 3.7, 0.6 % and ~6.5: the CTA waits for its slowest root).
+// A first version refined a two-pole + linear model by Newton steps: 4.4 serial inner steps of ~80 dependent
+// instructions per pass were half of the merge kernel.
+// Safeguards: a sign bracket [lo, hi] on g (bisection if both model steps leave it), stop when |g| is within
+// its rounding error bound, when the bracket collapses, or when the step is below 1e-7 |mu| (third-order
+// step) / 2e-9 |mu| (middle way): the next error is below an ulp.
 template <class Group>
 TDC_HD int secular_root(int k, const double *dk, const double *wk, int j, double *mu_out, const Group &grp) {
   if (k == 1) {
@@ -274,8 +281,10 @@ TDC_HD int secular_root(int k, const double *dk, const double *wk, int j, double
   TDC_COUNT(g_sec_roots);
   for (int it = 0; it < 60; ++it) {
     TDC_COUNT(g_sec_outer);
-    // one sweep over the poles, left part (i <= L: psi) and right part (i >= R: phi) separately
-    double t0 = 0.0, dpsi = 0.0, dphi = 0.0, asum = 0.0;
+    // one sweep over the poles, left part (i <= L: psi) and right part (i >= R: phi) separately: value, slope
+    // and curvature (sum w / delta^3 = psi'' / 2).  Every term of psi has the sign of the others, likewise phi,
+    // so |psi| + |phi| is the sum of the absolute terms the rounding error bound needs.
+    double psi = 0.0, phi = 0.0, dpsi = 0.0, dphi = 0.0, ddpsi = 0.0, ddphi = 0.0;
     {
       const int p = grp.part();
       // first index >= R with the residue of this lane
@@ -284,24 +293,28 @@ TDC_HD int secular_root(int k, const double *dk, const double *wk, int j, double
       for (int i = p; i <= L; i += Group::P) {
         const double rdel = TDC_RCP((dk[i] - dorg) - mu);
         const double t = wk[i] * rdel;
-        t0 += t;
-        dpsi = fma(t, rdel, dpsi);
-        asum += fabs(t);
+        psi += t;
+        const double u = t * rdel;
+        dpsi += u;
+        ddpsi = fma(u, rdel, ddpsi);
       }
 #pragma unroll 8
       for (int i = iR; i < k; i += Group::P) {
         const double rdel = TDC_RCP((dk[i] - dorg) - mu);
         const double t = wk[i] * rdel;
-        t0 += t;
-        dphi = fma(t, rdel, dphi);
-        asum += fabs(t);
+        phi += t;
+        const double u = t * rdel;
+        dphi += u;
+        ddphi = fma(u, rdel, ddphi);
       }
     }
-    t0 = grp.sum(t0);
+    psi = grp.sum(psi);
+    phi = grp.sum(phi);
     dpsi = grp.sum(dpsi);
     dphi = grp.sum(dphi);
-    asum = grp.sum(asum);
-    const double g = 1.0 + t0;
+    ddpsi = grp.sum(ddpsi);
+    ddphi = grp.sum(ddphi);
+    const double g = 1.0 + (psi + phi);
     if (it == 0 && !last && g < 0.0) {
       // root in the right half: continue in the frame of the right pole, mu in [-gap/2, 0).  The
       // quantities just evaluated are frame independent (dk_i - lambda is the same point).
@@ -313,41 +326,53 @@ TDC_HD int secular_root(int k, const double *dk, const double *wk, int j, double
       lo = mu;
       hi = 0.0;
     }
-    const double err = 8.0 * EPS * (1.0 + asum);
+    const double err = 8.0 * EPS * (1.0 + (fabs(psi) + fabs(phi)));
     if (fabs(g) <= err) break;
     if (g < 0.0)
       lo = mu;
     else
       hi = mu;
     if (hi - lo <= 2.0 * EPS * fmax(fabs(lo), fabs(hi))) break;
-    // quadratic for the step eta:  c eta^2 - (c (DL + DR) + s + S) eta + DL DR g = 0
-    const double DL = dL - mu, DR = dR - mu;
-    double sL = DL * DL * dpsi, sR = DR * DR * dphi;
-    double c = g - DL * dpsi - DR * dphi;
-    if (it == 0) {
-      // initial guess (dlaed4): the two neighbouring poles with their TRUE weights, the rest constant
-      sL = wk[L];
-      sR = wk[R];
-      c = g - sL / DL - sR / DR;
+    // step eta from the model  c + s / (DL - eta) + S / (DR - eta) = 0, i.e. the quadratic
+    //   c eta^2 - (c (DL + DR) + s + S) eta + DL DR g = 0;
+    // the wanted root keeps x = mu + eta strictly inside the bracket
+    auto model_step = [&](double DL, double DR, double sL, double sR, double c, double &x) -> bool {
+      const double Bq = -(c * (DL + DR) + sL + sR), Cq = DL * DR * g;
+      double disc = Bq * Bq - 4.0 * c * Cq;
+      disc = disc > 0.0 ? sqrt(disc) : 0.0;
+      const double q = -0.5 * (Bq + (Bq >= 0.0 ? disc : -disc));
+      const double e1 = (c != 0.0) ? q / c : 0.0, e2 = (q != 0.0) ? Cq / q : 0.0;
+      const double x1 = mu + e1, x2 = mu + e2;
+      const bool ok1 = (c != 0.0) && x1 > lo && x1 < hi, ok2 = (q != 0.0) && x2 > lo && x2 < hi;
+      x = (ok1 && (!ok2 || fabs(e1) < fabs(e2))) ? x1 : x2;
+      return ok1 || ok2;
+    };
+    // (1) third-order model: poles FITTED to the curvature, distance 2 psi' / psi'' = dpsi / ddpsi (a weighted
+    // harmonic mean of the true distances, so never nearer than the neighbouring pole: the model stays monotone
+    // between its poles like g itself)
+    double x = 0.0;
+    bool fitted = false;
+    if (ddpsi != 0.0 && ddphi != 0.0) {
+      const double DL = dpsi * TDC_RCP(ddpsi), DR = dphi * TDC_RCP(ddphi);
+      fitted = model_step(DL, DR, DL * DL * dpsi, DR * DR * dphi, g - DL * dpsi - DR * dphi, x);
     }
-    const double Bq = -(c * (DL + DR) + sL + sR), Cq = DL * DR * g;
-    double disc = Bq * Bq - 4.0 * c * Cq;
-    disc = disc > 0.0 ? sqrt(disc) : 0.0;
-    const double q = -0.5 * (Bq + (Bq >= 0.0 ? disc : -disc));
-    // the two roots q / c and Cq / q; the wanted one keeps x strictly inside the bracket
-    const double e1 = (c != 0.0) ? q / c : 0.0, e2 = (q != 0.0) ? Cq / q : 0.0;
-    const double x1 = mu + e1, x2 = mu + e2;
-    const bool ok1 = (c != 0.0) && x1 > lo && x1 < hi, ok2 = (q != 0.0) && x2 > lo && x2 < hi;
-    double x;
-    if (ok1 && ok2)
-      x = fabs(e1) < fabs(e2) ? x1 : x2;
-    else if (ok1)
-      x = x1;
-    else if (ok2)
-      x = x2;
-    else
-      x = 0.5 * (lo + hi);
-    const bool small_step = fabs(x - mu) <= 2.0e-9 * fabs(x);
+    if (!fitted) {
+      // (2) poles fixed at the two neighbours: when the nearest pole carries a tiny weight it is invisible in
+      // the sums at this point and the fitted model puts the root beyond it
+      TDC_COUNT(g_sec_inner);
+      const double DL = dL - mu, DR = dR - mu;
+      bool ok;
+      if (it == 0) {
+        // initial guess of dlaed4: the two neighbouring poles with their TRUE weights, the rest constant
+        const double sL = wk[L], sR = wk[R];
+        ok = model_step(DL, DR, sL, sR, g - sL / DL - sR / DR, x);
+      } else {
+        ok = model_step(DL, DR, DL * DL * dpsi, DR * DR * dphi, g - DL * dpsi - DR * dphi, x);
+      }
+      if (!ok) x = 0.5 * (lo + hi);
+    }
+    // cubic (fitted) / quadratic convergence: the error after this step is below an ulp
+    const bool small_step = fabs(x - mu) <= (fitted ? 1.0e-7 : 2.0e-9) * fabs(x);
     mu = x;
     if (small_step) break;
   }
