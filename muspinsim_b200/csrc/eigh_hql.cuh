@@ -350,6 +350,12 @@ __device__ __forceinline__ void dlaev2_dev(double a, double b, double c, double 
 // NT = matrices per block (one warp, NT active lanes).  The kernel is bound by the latency of
 // one thread's serial chain (ncu: one warp per SM sub-partition issues every ~4.3 cycles, FP64
 // pipe 4 % busy), not by lanes: NT = 8 puts four times as many warps on each sub-partition.
+__device__ __forceinline__ double tql_lds(const double *p) {
+  double r;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(r) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return r;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT)
 hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *__restrict__ ein,
@@ -381,11 +387,24 @@ hql_tql_kernel(int d, int64_t n, const double *__restrict__ din, const double *_
   int l = 0, nit = 0;
   const int maxit = 60 * d;
   while (l < d) {
+    // first m >= l with a negligible e_m (m = d - 1 if none), four candidates per pass with their nine loads
+    // pinned in front of the tests (asm volatile: the compiler otherwise sinks each load to its test behind the
+    // previous branch): the shared-memory latency is paid once per four elements (source-level ncu: this
+    // scan was a third of the kernel's stall samples, all short_scoreboard).  Same tests in the same order as
+    // the one-at-a-time loop, so the same m.
     int m = l;
     while (m < d - 1) {
-      const double em = EL(m);
-      if (em * em <= (eps2 * fabs(DL(m))) * fabs(DL(m + 1)) + safmin) break;
-      ++m;
+      const int i1 = min(m + 1, d - 1), i2 = min(m + 2, d - 1), i3 = min(m + 3, d - 1), i4 = min(m + 4, d - 1);
+      const double e0 = tql_lds(&EL(m)), e1 = tql_lds(&EL(i1)), e2 = tql_lds(&EL(i2)), e3 = tql_lds(&EL(i3));
+      const double a0 = fabs(tql_lds(&DL(m))), a1 = fabs(tql_lds(&DL(i1))), a2 = fabs(tql_lds(&DL(i2))),
+                   a3 = fabs(tql_lds(&DL(i3))), a4 = fabs(tql_lds(&DL(i4)));
+      const bool s0 = e0 * e0 <= (eps2 * a0) * a1 + safmin, s1 = e1 * e1 <= (eps2 * a1) * a2 + safmin,
+                 s2 = e2 * e2 <= (eps2 * a2) * a3 + safmin, s3 = e3 * e3 <= (eps2 * a3) * a4 + safmin;
+      // offset of the first hit among the candidates that exist (index < d - 1), else 4
+      const int lim = d - 1 - m;  // > 0
+      const int hit = s0 ? 0 : ((s1 || lim <= 1) ? 1 : ((s2 || lim <= 2) ? 2 : ((s3 || lim <= 3) ? 3 : 4)));
+      m += hit;
+      if (hit < 4) break;
     }
     if (m < d - 1) EL(m) = 0.0;
     if (m == l) {
