@@ -341,7 +341,9 @@ TDC_HD int secular_root(int k, const double *dk, const double *wk, int j, double
       double disc = Bq * Bq - 4.0 * c * Cq;
       disc = disc > 0.0 ? sqrt(disc) : 0.0;
       const double q = -0.5 * (Bq + (Bq >= 0.0 ? disc : -disc));
-      const double e1 = (c != 0.0) ? q / c : 0.0, e2 = (q != 0.0) ? Cq / q : 0.0;
+      // reciprocals by TDC_RCP: a step only steers the iteration; an overflowing or NaN candidate fails the
+      // bracket test below and the next model (or bisection) takes over
+      const double e1 = (c != 0.0) ? q * TDC_RCP(c) : 0.0, e2 = (q != 0.0) ? Cq * TDC_RCP(q) : 0.0;
       const double x1 = mu + e1, x2 = mu + e2;
       const bool ok1 = (c != 0.0) && x1 > lo && x1 < hi, ok2 = (q != 0.0) && x2 > lo && x2 < hi;
       x = (ok1 && (!ok2 || fabs(e1) < fabs(e2))) ? x1 : x2;
