@@ -8,14 +8,16 @@
 // matrices per GPU) and (ii) replayed the recorded rotations on d rows (hql_apply_reg_kernel,
 // 8.8 ms, ~7 d^3 vector flops, 9 GB of rotation-stream traffic).  Here the matrix is torn into four
 // leaves of <= 24 rows:
-//   tdc_leaf_kernel   one WARP per leaf (4 per matrix, ~10 small CTAs per SM): every lane repeats
-//                     the scalar QL chain (16 x shorter than the full one), lane r updates row r of
-//                     the leaf's eigenvectors in shared memory -- no rotation ever leaves the SM;
+//   leaves            tdc_prep_kernel scales and tears the matrix into a batch of 4 n independent 24 x 24
+//                     problems for the batched QL kernels (hql_tql_kernel: one THREAD per leaf, chains
+//                     16 x shorter than the full one; hql_apply_reg_kernel<24, 24>: row-per-thread replay);
 //   tdc_merge_kernel  one CTA per matrix, two merge levels; all merges of a level run concurrently.
 //                     Secular roots, Gu/Eisenstat z and the column norms use FOUR adjacent lanes per
 //                     root (each sums a quarter of the poles; quad shuffles), the eigenvector update
 //                     Q <- Q [V 0; 0 I] is a DMMA GEMM whose B fragments (zhat_i / (d_i - lambda_j))
-//                     are formed on the fly.
+//                     are formed on the fly; the row tiles of a K chunk sit in groups of three behind
+//                     warp-uniform branches (a chunk supported on one block touches half or a quarter of
+//                     them), the compaction counts come from warp ballots.
 // The first version was ONE kernel with one thread per root and ran 31 ms at C5 (ncu: 49 % of the
 // CTA lifetime in the leaf phase with 8 of 12 warps parked at the barrier, 38 % in the secular phase
 // at one dependent instruction per 9 cycles); hence the split and the quads.
