@@ -85,7 +85,7 @@ __device__ __forceinline__ double nu_horner(const double (&cf)[NU_DEG + 1], doub
 
 // units: unit u = (configuration u / S, part u % S of its pair list, `plen` pairs each).  CTA b owns
 // the contiguous units [b * units_per_cta, ...); its warps draw them one at a time from a shared
-// counter (the 6 warps of a CTA do not share the 4 schedulers evenly).
+// counter (the warps of a CTA do not finish their units at the same time).
 //
 // Per warp and batch of 32 pairs:
 //   prep     every lane turns one pair into a point (cell offset, strength) -> staging buffer
