@@ -95,3 +95,33 @@ def test_spin_hamiltonians_including_zero_field(lib, which):
         Hh = sl.hessenberg(H)
         # a diagonal unitary scaling makes the sub-diagonal real and non-negative
         _check(lib, np.real(np.diag(Hh)).copy(), np.abs(np.diag(Hh, -1)).copy())
+
+
+def test_secular_sweep_statistics_on_the_benchmark_hamiltonians():
+    """The third-order secular step (tdc_core.cuh::secular_root, DESIGN section 3): on the tridiagonal forms of
+    the C5 Hamiltonians the solver needs < 4 sweeps per root on average (the fixed-pole "middle way" alone needed
+    4.77) and the slow tail is gone (the CTA of the merge kernel waits for its slowest root): fewer than 1.5 % of
+    the roots take 7 sweeps or more (was 8 %).  Counters of a -DTDC_STATS host build; accuracy against LAPACK."""
+    import scipy.linalg as sl
+
+    from muspinsim_b200 import configs, workloads
+    from muspinsim_b200.spinsys import system_from_spec
+
+    out = os.path.join(ROOT, "oracle", "_build", "libtdc_host_stats.so")
+    deps = [SRC, os.path.join(os.path.dirname(SRC), "tdc_core.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(p) > os.path.getmtime(out) for p in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DTDC_STATS", "-x", "c++", "-o", out, SRC])
+    lib = ctypes.CDLL(out)
+    spec = workloads.c5_large(n_orient=12, nt=4)
+    s, _ = system_from_spec(spec)
+    H0, Z3 = s.hamiltonian, s.zeeman_operators()
+    B = configs.ConfigTable(spec).B
+    for c in range(B.shape[0]):
+        Hh = sl.hessenberg(H0 + sum(B[c, a] * Z3[a] for a in range(3)))
+        _check(lib, np.real(np.diag(Hh)).copy(), np.abs(np.diag(Hh, -1)).copy())
+    cnt = (ctypes.c_long * 35)()
+    lib.tdc_host_counters(cnt)
+    roots, sweeps, hist = cnt[0], cnt[1], list(cnt[3:35])
+    assert roots >= 12 * (96 + 2 * 40)  # three merges per matrix, little deflation
+    assert sweeps / roots < 4.0
+    assert sum(hist[7:]) < 0.015 * roots
